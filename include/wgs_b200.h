@@ -50,6 +50,49 @@ int wgs_rbf_traverse(const float* support_sets, const float* alphas, const float
                      float fixed_gamma, const long long* path, const float* start, float eps, int steps,
                      float* codes, float* shifts, int chains, int K, int n_vec, int d, void* stream);
 
+/* ---- tensor-core convolution -------------------------------------------------------------------- *
+ * "split32" operand format: every 32 fp32 channels become one 128-byte row of 64 bf16 —
+ * [hi(32) | lo(32)], x = hi + lo — so a tensor of C channels (padded to a multiple of 32) is
+ * [..., C/32, 64] bf16 and has the same byte size as its fp32 source.
+ *
+ * wgs_pack_split32: rows x C fp32 (row stride `ld` floats) -> [rows, ceil(C/32), 64] split32, each
+ * element optionally multiplied by scale[(row / rows_per_group) * C + c] (per-sample per-channel
+ * modulation; scale may be NULL) — replaces `weight = scale * W * style` of
+ * models/StyleGAN2/model.py:190-191 by scaling the activations instead of the weights.            */
+int wgs_pack_split32(const float* src, long long rows, int C, long long ld, const float* scale,
+                     long long rows_per_group, void* dst, void* stream);
+
+#define WGS_MAX_TAPS 64
+typedef struct wgs_conv_desc {
+    /* input activations, split32 [in_n][in_h][in_w][c_chunks][64] */
+    const void* in;
+    int in_n, in_h, in_w, c_chunks;
+    /* weights, split32 [w_taps][w_cout][c_chunks][64] */
+    const void* w;
+    int w_taps, w_cout;
+    /* virtual output grid per image; input pixel = grid coord * in_stride + tap offset (zero outside) */
+    int out_n, grid_h, grid_w, in_stride;
+    int num_taps;
+    int tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS], tap_w[WGS_MAX_TAPS];
+    /* output fp32: &out[n*out_sn + (oy*out_ystep+out_y0)*out_sy + (ox*out_xstep+out_x0)*out_sx + co] */
+    float* out;
+    long long out_sn, out_sy, out_sx;
+    int out_y0, out_x0, out_ystep, out_xstep;
+    int cout;
+    const float* alpha;      /* [out_n, cout] per-sample per-channel scale (demodulation) or NULL */
+    const float* beta;       /* [cout] bias or NULL */
+    int act;                 /* 0 none, 1 relu, 2 leaky relu 0.2 */
+    int accumulate;          /* add to the existing output instead of overwriting */
+    int force_bn;            /* 0 = choose the channel tile automatically */
+} wgs_conv_desc;
+
+/* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls
+ * behind F.conv2d / F.conv_transpose2d at models/StyleGAN2/model.py:206,219,225,
+ * models/ProgGAN/model.py:39,55, models/BigGAN/layers.py:105, models/SNGAN/sn_gen_resnet.py:28-29 and
+ * torchvision resnet18 (lib/reconstructor.py:54), forward and data-gradient.                       */
+int wgs_conv_split32(const wgs_conv_desc* desc, void* stream);
+int wgs_conv_desc_size(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,135 @@
+"""GPU: the tcgen05 tap-list convolution (through the C ABI) against fp32 torch convolutions.
+Tolerance: 2e-5 relative L2 (3-term bf16 split, fp32 accumulation); the north-star bar is 1e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def test_pack_split32_roundtrip():
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(0)
+    for C in (32, 64, 6, 3, 96, 17):
+        x = torch.randn(5, 7, C, generator=g).cuda() * 3
+        s = conv.pack_split32(x)
+        assert s.shape == (5, 7, (C + 31) // 32, 64)
+        hi = s[..., :32].float().reshape(5, 7, -1)[..., :C]
+        lo = s[..., 32:].float().reshape(5, 7, -1)[..., :C]
+        assert rel(hi + lo, x) < 1e-5
+        assert float((hi + lo - x).abs().max()) <= 2 ** -16 * float(x.abs().max())
+        pad = s.float().reshape(5, 7, -1, 2, 32).permute(0, 1, 3, 2, 4).reshape(5, 7, 2, -1)[..., C:]
+        assert float(pad.abs().max()) == 0.0 if pad.numel() else True
+    # per-group channel scale
+    x = torch.randn(4, 6, 40, generator=g).cuda()
+    sc = torch.randn(4, 40, generator=g).cuda()
+    s = conv.pack_split32(x, scale=sc, rows_per_group=6)
+    got = (s[..., :32].float() + s[..., 32:].float()).reshape(4, 6, -1)[..., :40]
+    assert rel(got, x * sc[:, None, :]) < 1e-5
+
+
+CASES = [
+    # N, Ci, H, W, Co, k, stride, pad
+    (2, 32, 16, 16, 32, 3, 1, 1),
+    (1, 64, 32, 32, 48, 3, 1, 1),
+    (8, 512, 4, 4, 512, 3, 1, 1),
+    (3, 128, 8, 8, 256, 3, 1, 1),
+    (2, 96, 8, 8, 3, 1, 1, 0),
+    (1, 32, 20, 24, 64, 3, 2, 1),
+    (2, 6, 32, 32, 64, 7, 2, 3),
+    (1, 512, 16, 16, 512, 3, 1, 1),
+    (2, 64, 16, 16, 128, 1, 2, 0),
+    (1, 16, 64, 64, 16, 3, 1, 1),
+    (1, 32, 128, 128, 32, 3, 1, 1),
+    (5, 64, 5, 9, 32, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv2d_matches_torch(case):
+    from warpedganspace_b200 import conv
+    N, Ci, H, W, Co, k, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Ci, H, W, generator=g).cuda()
+    w = torch.randn(Co, Ci, k, k, generator=g).cuda() / (Ci * k * k) ** 0.5
+    want = F.conv2d(x, w, stride=stride, padding=pad)
+    got = conv.conv2d(conv.pack_split32(nhwc(x)), conv.pack_weights(w), k, k, stride=stride, padding=pad)
+    torch.cuda.synchronize()
+    assert got.shape == nhwc(want).shape
+    assert rel(got, nhwc(want)) < 2e-5
+
+
+def test_epilogue_alpha_beta_act_accumulate():
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(5)
+    N, Ci, H, W, Co = 3, 64, 16, 16, 80
+    x = torch.randn(N, Ci, H, W, generator=g).cuda()
+    w = torch.randn(Co, Ci, 3, 3, generator=g).cuda() / 24
+    alpha = torch.rand(N, Co, generator=g).cuda() + 0.5
+    beta = torch.randn(Co, generator=g).cuda()
+    base = torch.randn(N, H, W, Co, generator=g).cuda()
+    xs, ws = conv.pack_split32(nhwc(x)), conv.pack_weights(w)
+    y = F.conv2d(x, w, padding=1)
+    want = F.leaky_relu(y * alpha[:, :, None, None] + beta[None, :, None, None], 0.2)
+    got = conv.conv2d(xs, ws, 3, 3, padding=1, alpha=alpha, beta=beta, act=2)
+    assert rel(got, nhwc(want)) < 2e-5
+    out = base.clone()
+    conv.conv2d(xs, ws, 3, 3, padding=1, out=out, accumulate=True, act=1)
+    assert rel(out, F.relu(nhwc(y) + base)) < 2e-5
+    for bn in (16, 32, 64, 128):
+        got = conv.conv2d(xs, ws, 3, 3, padding=1, force_bn=bn)
+        assert rel(got, nhwc(y)) < 2e-5, bn
+
+
+@pytest.mark.parametrize('N,Ci,H,Co', [(2, 64, 4, 64), (1, 32, 16, 48), (2, 128, 8, 64), (1, 64, 32, 32)])
+def test_conv_transpose_stride2(N, Ci, H, Co):
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(N + Ci + H)
+    x = torch.randn(N, Ci, H, H, generator=g).cuda()
+    wt = torch.randn(Ci, Co, 3, 3, generator=g).cuda() / (Ci * 9) ** 0.5          # conv_transpose layout
+    want = F.conv_transpose2d(x, wt, stride=2, padding=0)                        # (2H+1)^2
+    ws = conv.pack_weights(wt.permute(1, 0, 2, 3).contiguous())                  # [9, Co, Ci]
+    got = conv.conv_transpose2d_s2(conv.pack_split32(nhwc(x)), ws, 3)
+    assert got.shape == nhwc(want).shape
+    assert rel(got, nhwc(want)) < 2e-5
+    # 6x6 composite kernel with crop 2 (transposed conv fused with the 4x4 blur)
+    w6 = torch.randn(Ci, Co, 6, 6, generator=g).cuda() / (Ci * 36) ** 0.5
+    want6 = F.conv_transpose2d(x, w6, stride=2, padding=2)
+    got6 = conv.conv_transpose2d_s2(conv.pack_split32(nhwc(x)), conv.pack_weights(w6.permute(1, 0, 2, 3).contiguous()),
+                                    6, crop=2)
+    assert got6.shape == nhwc(want6).shape == (N, 2 * H, 2 * H, Co)
+    assert rel(got6, nhwc(want6)) < 2e-5
+
+
+def test_simt_twin_matches(monkeypatch):
+    """The CUDA-core twin of the same contract agrees with the tensor-core kernel bit-for-bit-ish."""
+    import subprocess, sys, os
+    code = ("import torch, torch.nn.functional as F\n"
+            "from warpedganspace_b200 import conv\n"
+            "g = torch.Generator().manual_seed(1)\n"
+            "x = torch.randn(2, 64, 8, 8, generator=g).cuda(); w = torch.randn(32, 64, 3, 3, generator=g).cuda() / 24\n"
+            "torch.backends.cudnn.allow_tf32 = False\n"
+            "y = conv.conv2d(conv.pack_split32(x.permute(0,2,3,1).contiguous()), conv.pack_weights(w), 3, 3, padding=1)\n"
+            "r = F.conv2d(x, w, padding=1).permute(0,2,3,1)\n"
+            "print(float((y - r).norm() / r.norm()))\n")
+    env = dict(os.environ, WGS_CONV_IMPL='simt')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=120,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert float(out.stdout.strip().splitlines()[-1]) < 2e-5

@@ -1,0 +1,131 @@
+"""Host-side wrappers of the tensor-core convolution entry points (wgs_pack_split32 /
+wgs_conv_split32).  Activations are NHWC; conv operands are "split32" bf16 (see include/wgs_b200.h)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+MAX_TAPS = 64
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ('inp', ctypes.c_void_p),
+        ('in_n', ctypes.c_int), ('in_h', ctypes.c_int), ('in_w', ctypes.c_int), ('c_chunks', ctypes.c_int),
+        ('w', ctypes.c_void_p),
+        ('w_taps', ctypes.c_int), ('w_cout', ctypes.c_int),
+        ('out_n', ctypes.c_int), ('grid_h', ctypes.c_int), ('grid_w', ctypes.c_int), ('in_stride', ctypes.c_int),
+        ('num_taps', ctypes.c_int),
+        ('tap_dy', ctypes.c_int * MAX_TAPS), ('tap_dx', ctypes.c_int * MAX_TAPS), ('tap_w', ctypes.c_int * MAX_TAPS),
+        ('out', ctypes.c_void_p),
+        ('out_sn', ctypes.c_longlong), ('out_sy', ctypes.c_longlong), ('out_sx', ctypes.c_longlong),
+        ('out_y0', ctypes.c_int), ('out_x0', ctypes.c_int), ('out_ystep', ctypes.c_int), ('out_xstep', ctypes.c_int),
+        ('cout', ctypes.c_int),
+        ('alpha', ctypes.c_void_p), ('beta', ctypes.c_void_p),
+        ('act', ctypes.c_int), ('accumulate', ctypes.c_int), ('force_bn', ctypes.c_int),
+    ]
+
+
+def _check_layout():
+    lib = _lib.load()
+    if lib.wgs_conv_desc_size() != ctypes.sizeof(ConvDesc):
+        raise RuntimeError('wgs_conv_desc layout mismatch: C %d vs ctypes %d'
+                           % (lib.wgs_conv_desc_size(), ctypes.sizeof(ConvDesc)))
+
+
+def chunks_of(c):
+    return (c + 31) // 32
+
+
+def pack_split32(x, scale=None, rows_per_group=1, out=None):
+    """x: fp32 [..., C] with contiguous rows (last-dim stride 1; a uniform row stride is allowed).
+    Returns bf16 [..., ceil(C/32), 64].  scale: fp32 [groups, C]; row r uses group r // rows_per_group."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if not x.is_contiguous():
+        x = x.contiguous()
+    ld = C
+    if out is None:
+        out = torch.empty(*x.shape[:-1], chunks_of(C), 64, dtype=torch.bfloat16, device=x.device)
+    _lib.call('wgs_pack_split32', _lib.ptr(x), rows, C, ld, _lib.ptr(scale), int(rows_per_group),
+              _lib.ptr(out), _lib.stream())
+    return out
+
+
+def pack_weights(w):
+    """w: fp32 [Co, Ci, kh, kw] (torch conv layout) -> split32 [kh*kw, Co, ceil(Ci/32), 64]; tap = ky*kw+kx."""
+    co, ci, kh, kw = w.shape
+    wt = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+    return pack_split32(wt)
+
+
+def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
+              alpha=None, beta=None, act=0, accumulate=False, force_bn=0):
+    """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
+    taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
+    grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
+    _check_layout()
+    n, h, w_, chunks, _ = x_split.shape
+    assert w_split.shape[2] == chunks, (w_split.shape, x_split.shape)
+    d = ConvDesc()
+    d.inp = x_split.data_ptr()
+    d.in_n, d.in_h, d.in_w, d.c_chunks = n, h, w_, chunks
+    d.w = w_split.data_ptr()
+    d.w_taps, d.w_cout = w_split.shape[0], w_split.shape[1]
+    d.out_n, d.grid_h, d.grid_w, d.in_stride = out.shape[0], grid[0], grid[1], in_stride
+    d.num_taps = len(taps)
+    for i, (dy, dx, tw) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i], d.tap_w[i] = dy, dx, tw
+    assert out.dtype == torch.float32 and out.stride(3) == 1
+    d.out = out.data_ptr()
+    d.out_sn, d.out_sy, d.out_sx = out.stride(0), out.stride(1), out.stride(2)
+    d.out_y0, d.out_x0 = out_origin
+    d.out_ystep, d.out_xstep = out_step
+    d.cout = cout if cout is not None else w_split.shape[1]
+    d.alpha = alpha.data_ptr() if alpha is not None else None
+    d.beta = beta.data_ptr() if beta is not None else None
+    d.act, d.accumulate, d.force_bn = act, int(accumulate), force_bn
+    for t in (x_split, w_split, out):
+        if not t.is_cuda:
+            raise RuntimeError('conv needs CUDA tensors; there is no CPU fallback')
+    _lib.check(_lib.load().wgs_conv_split32(ctypes.byref(d), _lib.stream()))
+    return out
+
+
+def conv2d(x_split, w_split, kh, kw, *, stride=1, padding=0, out=None, **kw_args):
+    """Plain cross-correlation (F.conv2d semantics) on split32 operands -> fp32 NHWC."""
+    n, h, w_, _, _ = x_split.shape
+    oh = (h + 2 * padding - kh) // stride + 1
+    ow = (w_ + 2 * padding - kw) // stride + 1
+    co = kw_args.get('cout') or w_split.shape[1]
+    if out is None:
+        out = torch.empty(n, oh, ow, co, dtype=torch.float32, device=x_split.device)
+    taps = [(ky - padding, kx - padding, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
+    return conv_taps(x_split, w_split, taps, out, grid=(oh, ow), in_stride=stride, **kw_args)
+
+
+def conv_transpose2d_s2(x_split, w_split, k, *, out=None, crop=0, **kw_args):
+    """F.conv_transpose2d(stride=2, padding=crop) semantics for a k x k kernel, as 4 output-phase convs.
+    w_split holds taps in (ky*k + kx) order of the *transposed-conv* weight [Ci, Co, k, k] packed as
+    [k*k, Co, Ci]:  out[2*iy + ky - crop, 2*ix + kx - crop] += x[iy, ix] * w[ky, kx]."""
+    n, h, w_, _, _ = x_split.shape
+    full = 2 * (h - 1) + k
+    oh = full - 2 * crop
+    fullw = 2 * (w_ - 1) + k
+    ow = fullw - 2 * crop
+    co = kw_args.get('cout') or w_split.shape[1]
+    if out is None:
+        out = torch.empty(n, oh, ow, co, dtype=torch.float32, device=x_split.device)
+    for py in range(2):
+        for px in range(2):
+            # output Y = 2*q + py (in cropped coords); uncropped Yf = Y + crop = 2*iy + ky
+            kys = [ky for ky in range(k) if (ky - py - crop) % 2 == 0]
+            kxs = [kx for kx in range(k) if (kx - px - crop) % 2 == 0]
+            gh = (oh - py + 1) // 2
+            gw = (ow - px + 1) // 2
+            if gh <= 0 or gw <= 0 or not kys or not kxs:
+                continue
+            taps = [((py + crop - ky) // 2, (px + crop - kx) // 2, ky * k + kx) for ky in kys for kx in kxs]
+            conv_taps(x_split, w_split, taps, out, grid=(gh, gw), out_origin=(py, px), out_step=(2, 2), **kw_args)
+    return out

@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, 'libwgs_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v', '-I', os.path.join(os.path.dirname(PKG), 'include')]
 
 
 def sources():
@@ -21,7 +21,8 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(HERE, '*.cuh')) + [os.path.abspath(__file__)]
+    deps = (sources() + glob.glob(os.path.join(HERE, '*.cuh')) + [os.path.abspath(__file__)] +
+            glob.glob(os.path.join(os.path.dirname(PKG), 'include', '*.h')))
     return any(os.path.getmtime(p) > t for p in deps)
 
 
@@ -35,7 +36,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(HERE, 'build', os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
-                and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in glob.glob(os.path.join(HERE, '*.cuh')))):
+                and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in glob.glob(os.path.join(HERE, '*.cuh')) +
+                        glob.glob(os.path.join(os.path.dirname(PKG), 'include', '*.h')))):
             continue
         cmd = [NVCC] + FLAGS + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

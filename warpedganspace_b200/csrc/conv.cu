@@ -1,0 +1,333 @@
+// Tap-list implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// One kernel family serves every dense contraction on the hot path: StyleGAN2's modulated 3x3 convs
+// (restated as  d[b,o] * conv(W, s[b,i]*x) — no per-sample weights, no grouped conv; reference
+// models/StyleGAN2/model.py:187-228), its stride-2 transposed convs (four output phases, each a short
+// tap list; :201-212), ProgGAN / BigGAN / SNGAN 3x3 and 1x1 convs, the Reconstructor's ResNet-18 convs
+// (7x7/2, 3x3/1, 3x3/2, 1x1/2) and all of their data-gradients (same kernel, flipped/transposed taps).
+//
+//   out[n, oy*ystep+y0, ox*xstep+x0, co] = act( alpha[n,co] * sum_{t,ci} W[t][co][ci] *
+//                                           in[n, oy*stride+dy_t, ox*stride+dx_t, ci] + beta[co] )
+//
+// Operands are "split32" bf16: every 32 fp32 channels are stored as one 128-byte row
+// [hi(32) | lo(32)] with x = hi + lo to 2^-17; the product is formed as hi*hi + hi*lo + lo*hi with fp32
+// accumulation in TMEM (3 MMAs per logical MAC, error ~1e-5 instead of bf16's ~1e-2).
+//
+// Structure (one 128-pixel x BN-channel output tile per CTA):
+//   warp 0    TMA producer: per (tap, 32-channel chunk) one 5-D box load of the shifted input patch
+//             (out-of-bounds = zero fill = conv padding; elementStrides = conv stride) and one 4-D box
+//             of the weight slice, both 128B-swizzled, into an N-stage mbarrier ring;
+//   warp 1    TMEM allocation + single-thread tcgen05.mma issue (6 MMAs of K=16 per stage);
+//   warps 2-5 epilogue: tcgen05.ld of the fp32 accumulators, alpha/beta/activation, NHWC stores.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "wgs_b200.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace wgs {
+
+constexpr int CONV_THREADS = 192;
+constexpr int A_STAGE_BYTES = 128 * 128;
+
+struct ConvKernelParams {
+    int out_n, grid_h, grid_w;
+    int bh, bw, bn;
+    int tiles_x, tiles_y, tiles_n, n_tiles_co;
+    int in_stride;
+    int c_chunks, cout, BN, stages, tmem_cols;
+    int num_taps;
+    float* out;
+    long long out_sn, out_sy, out_sx;
+    int out_y0, out_x0, out_ystep, out_xstep;
+    const float* alpha;
+    const float* beta;
+    int act, accumulate;
+    signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
+    unsigned char tap_w[WGS_MAX_TAPS];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return v > 0.f ? v : 0.f;
+    if (act == 2) return v > 0.f ? v : 0.2f * v;
+    return v;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ ConvKernelParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_stage_bytes = p.BN * 128;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.stages * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* acc_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    // tile coordinates: co tile fastest so CTAs sharing an input patch are co-scheduled (L2 reuse)
+    int t = blockIdx.x;
+    const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    const int tn = t;
+    const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = tn * p.bn, co0 = co_tile * p.BN;
+    const int k_blocks = p.num_taps * p.c_chunks;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(full_bar + s, 1);
+            ptx::mbar_init(empty_bar + s, 1);
+        }
+        ptx::mbar_init(acc_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+                const int ix = ox0 * p.in_stride + p.tap_dx[tap];
+                const int iy = oy0 * p.in_stride + p.tap_dy[tap];
+                const int wt = p.tap_w[tap];
+                for (int ch = 0; ch < p.c_chunks; ++ch) {
+                    ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+                    ptx::mbar_expect_tx(full_bar + stage, (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+                    ptx::tma_load_5d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, full_bar + stage, 0, ch, ix, iy, n0);
+                    ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, ch, co0, wt);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                ptx::mbar_wait(full_bar + stage, phase);
+                ptx::tc_fence_after();
+                const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES));
+                const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + (size_t)stage * b_stage_bytes));
+                // 128-byte row = [hi k0 | hi k1 | lo k0 | lo k1], 32 B each -> descriptor address +2 per slot
+                ptx::mma_f16(tmem_base, da + 0, db + 0, idesc, kb > 0 ? 1u : 0u);   // hi*hi
+                ptx::mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
+                ptx::mma_f16(tmem_base, da + 0, db + 4, idesc, 1u);                 // hi*lo
+                ptx::mma_f16(tmem_base, da + 2, db + 6, idesc, 1u);
+                ptx::mma_f16(tmem_base, da + 4, db + 0, idesc, 1u);                 // lo*hi
+                ptx::mma_f16(tmem_base, da + 6, db + 2, idesc, 1u);
+                ptx::mma_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            ptx::mma_commit(acc_bar);                         // accumulator complete
+        }
+    } else {
+        // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
+        const int n = n0 + nl, oy = oy0 + yl, ox = ox0 + xl;
+        const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
+        float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
+                     (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
+        const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
+        ptx::mbar_wait(acc_bar, 0);
+        ptx::tc_fence_after();
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        for (int c = 0; c < p.BN; c += 16) {
+            float v[16];
+            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            const int co = co0 + c;
+            if (!valid || co >= p.cout) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int cc = co + i;
+                if (cc < p.cout) {
+                    float r = v[i];
+                    if (alpha) r *= __ldg(alpha + cc);
+                    if (p.beta) r += __ldg(p.beta + cc);
+                    if (p.accumulate) r += dst[cc];
+                    v[i] = apply_act(r, p.act);
+                }
+            }
+            if (vec_ok && co + 16 <= p.cout) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+                for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// Same contract on CUDA cores (debug / cross-check path; selected with WGS_CONV_IMPL=simt).
+__global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
+                                 int in_n, int in_h, int in_w, int w_cout, const ConvKernelParams p) {
+    const long long total = (long long)p.out_n * p.grid_h * p.grid_w * p.cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % p.cout);
+        long long r = i / p.cout;
+        const int ox = (int)(r % p.grid_w); r /= p.grid_w;
+        const int oy = (int)(r % p.grid_h);
+        const int n = (int)(r / p.grid_h);
+        float acc = 0.f;
+        for (int tp = 0; tp < p.num_taps; ++tp) {
+            const int iy = oy * p.in_stride + p.tap_dy[tp], ix = ox * p.in_stride + p.tap_dx[tp];
+            if (iy < 0 || iy >= in_h || ix < 0 || ix >= in_w) continue;
+            const __nv_bfloat16* a = in + (((size_t)n * in_h + iy) * in_w + ix) * p.c_chunks * 64;
+            const __nv_bfloat16* b = w + ((size_t)p.tap_w[tp] * w_cout + co) * p.c_chunks * 64;
+            for (int ch = 0; ch < p.c_chunks; ++ch)
+                for (int c = 0; c < 32; ++c) {
+                    const float ah = __bfloat162float(a[ch * 64 + c]), al = __bfloat162float(a[ch * 64 + 32 + c]);
+                    const float bh = __bfloat162float(b[ch * 64 + c]), bl = __bfloat162float(b[ch * 64 + 32 + c]);
+                    acc += ah * bh + ah * bl + al * bh;
+                }
+        }
+        float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
+                     (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx + co;
+        if (p.alpha) acc *= p.alpha[(size_t)n * p.cout + co];
+        if (p.beta) acc += p.beta[co];
+        if (p.accumulate) acc += *dst;
+        *dst = apply_act(acc, p.act);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+static int conv_impl_is_simt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("WGS_CONV_IMPL");
+        v = (e && std::string(e) == "simt") ? 1 : 0;
+    }
+    return v;
+}
+
+}  // namespace wgs
+
+using namespace wgs;
+
+extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
+    WGS_REQUIRE(d != nullptr, "conv: null descriptor");
+    WGS_REQUIRE(d->num_taps >= 1 && d->num_taps <= WGS_MAX_TAPS, "conv: bad tap count");
+    WGS_REQUIRE(d->c_chunks >= 1 && d->cout >= 1, "conv: bad channel counts");
+    WGS_REQUIRE(d->in_stride >= 1 && d->in_stride <= 8, "conv: bad input stride");
+    WGS_REQUIRE(d->out_n >= 1 && d->grid_h >= 1 && d->grid_w >= 1, "conv: empty output grid");
+    WGS_REQUIRE((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0,
+                "conv: operands must be 16-byte aligned");
+    ConvKernelParams p;
+    memset(&p, 0, sizeof(p));
+    p.out_n = d->out_n; p.grid_h = d->grid_h; p.grid_w = d->grid_w;
+    p.bw = std::min(16, next_pow2(d->grid_w));
+    p.bh = std::min(128 / p.bw, next_pow2(d->grid_h));
+    p.bn = 128 / (p.bw * p.bh);
+    p.tiles_x = ceil_div(d->grid_w, p.bw);
+    p.tiles_y = ceil_div(d->grid_h, p.bh);
+    p.tiles_n = ceil_div(d->out_n, p.bn);
+    p.in_stride = d->in_stride;
+    p.c_chunks = d->c_chunks; p.cout = d->cout; p.num_taps = d->num_taps;
+    p.out = d->out; p.out_sn = d->out_sn; p.out_sy = d->out_sy; p.out_sx = d->out_sx;
+    p.out_y0 = d->out_y0; p.out_x0 = d->out_x0; p.out_ystep = d->out_ystep; p.out_xstep = d->out_xstep;
+    p.alpha = d->alpha; p.beta = d->beta; p.act = d->act; p.accumulate = d->accumulate;
+    for (int i = 0; i < d->num_taps; ++i) {
+        WGS_REQUIRE(d->tap_dy[i] >= -64 && d->tap_dy[i] <= 64 && d->tap_dx[i] >= -64 && d->tap_dx[i] <= 64,
+                    "conv: tap offset out of range");
+        WGS_REQUIRE(d->tap_w[i] >= 0 && d->tap_w[i] < d->w_taps && d->tap_w[i] < 256, "conv: bad weight tap index");
+        p.tap_dy[i] = (signed char)d->tap_dy[i]; p.tap_dx[i] = (signed char)d->tap_dx[i];
+        p.tap_w[i] = (unsigned char)d->tap_w[i];
+    }
+    // N tile: as wide as possible (fewer re-reads of the input patch) but keep >= ~1 wave of CTAs
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    int BN = std::min(256, (d->cout + 15) / 16 * 16);
+    while (BN > 64 && m_tiles * ceil_div(d->cout, BN) < num_sms() && BN % 32 == 0) BN /= 2;
+    if (d->force_bn > 0) BN = d->force_bn;
+    WGS_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "conv: bad N tile");
+    p.BN = BN;
+    p.n_tiles_co = ceil_div(d->cout, BN);
+    p.tmem_cols = std::max(32, next_pow2(BN));
+    const int stage_bytes = A_STAGE_BYTES + BN * 128;
+    p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+    const cudaStream_t st = (cudaStream_t)stream;
+
+    if (conv_impl_is_simt()) {
+        const long long total = (long long)p.out_n * p.grid_h * p.grid_w * p.cout;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        conv_simt_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)d->in, (const __nv_bfloat16*)d->w, d->in_n,
+                                                 d->in_h, d->in_w, d->w_cout, p);
+        count_launch();
+        WGS_LAUNCH_CHECK();
+        return 0;
+    }
+
+    auto encode = get_encode();
+    WGS_REQUIRE(encode != nullptr, "conv: cuTensorMapEncodeTiled entry point not available");
+    alignas(64) CUtensorMap tmap_a, tmap_b;
+    {
+        const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
+                                    (cuuint64_t)d->in_n};
+        const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->in_w, s4 = s3 * d->in_h;
+        const cuuint64_t strides[4] = {s1, s2, s3, s4};
+        const cuuint32_t box[5] = {64, 1, (cuuint32_t)(p.bw * d->in_stride), (cuuint32_t)(p.bh * d->in_stride),
+                                   (cuuint32_t)p.bn};
+        const cuuint32_t estr[5] = {1, 1, (cuuint32_t)d->in_stride, (cuuint32_t)d->in_stride, 1};
+        CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->in), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        WGS_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(input) failed with code " + std::to_string((int)r));
+    }
+    {
+        const cuuint64_t dims[4] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_cout, (cuuint64_t)d->w_taps};
+        const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->w_cout;
+        const cuuint64_t strides[3] = {s1, s2, s3};
+        const cuuint32_t box[4] = {64, 1, (cuuint32_t)BN, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->w), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        WGS_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
+    }
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        smem_set = 227 * 1024;
+    }
+    const int grid = m_tiles * p.n_tiles_co;
+    conv_tc_kernel<<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_conv_desc_size(void) { return (int)sizeof(wgs_conv_desc); }

@@ -1,0 +1,60 @@
+// fp32 -> split32 (bf16 hi|lo per 32-channel chunk) packing, with optional per-group channel scale.
+#include "common.cuh"
+#include "wgs_b200.h"
+
+namespace wgs {
+
+// one thread per (row, chunk, 4-channel group): reads a float4 (or a guarded tail), writes 4 hi + 4 lo
+__global__ void pack_split32_kernel(const float* __restrict__ src, long long rows, int C, long long ld,
+                                    const float* __restrict__ scale, long long rows_per_group,
+                                    __nv_bfloat16* __restrict__ dst, int chunks) {
+    const long long total = rows * chunks * 8;
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i & 7);
+        const long long rc = i >> 3;
+        const int ch = (int)(rc % chunks);
+        const long long r = rc / chunks;
+        const int c0 = ch * 32 + g * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* s = src + r * ld + c0;
+        if (vec && c0 + 4 <= C) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(s));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (c0 + k < C) v[k] = __ldg(s + k);
+        }
+        if (scale) {
+            const float* sc = scale + (r / rows_per_group) * C + c0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (c0 + k < C) v[k] *= __ldg(sc + k);
+        }
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16(v[k], hi[k], lo[k]);
+        __nv_bfloat16* d = dst + rc * 64 + g * 4;
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(hi);
+        *reinterpret_cast<uint2*>(d + 32) = *reinterpret_cast<uint2*>(lo);
+    }
+}
+
+}  // namespace wgs
+
+using namespace wgs;
+
+extern "C" int wgs_pack_split32(const float* src, long long rows, int C, long long ld, const float* scale,
+                                long long rows_per_group, void* dst, void* stream) {
+    WGS_REQUIRE(rows >= 0 && C >= 1 && ld >= C, "pack_split32: bad sizes");
+    WGS_REQUIRE(!scale || rows_per_group >= 1, "pack_split32: rows_per_group must be >= 1 with a scale");
+    if (rows == 0) return 0;
+    const int chunks = (C + 31) / 32;
+    const long long total = rows * chunks * 8;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+    pack_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, C, ld, scale, rows_per_group,
+                                                                  (__nv_bfloat16*)dst, chunks);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
