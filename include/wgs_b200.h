@@ -56,11 +56,11 @@ int wgs_rbf_traverse(const float* support_sets, const float* alphas, const float
  * [..., C/32, 64] bf16 and has the same byte size as its fp32 source.
  *
  * wgs_pack_split32: rows x C fp32 (row stride `ld` floats) -> [rows, ceil(C/32), 64] split32, each
- * element optionally multiplied by scale[(row / rows_per_group) * C + c] (per-sample per-channel
+ * element optionally multiplied by scale[(row / rows_per_group) * scale_ld + c] (per-sample per-channel
  * modulation; scale may be NULL) — replaces `weight = scale * W * style` of
  * models/StyleGAN2/model.py:190-191 by scaling the activations instead of the weights.            */
 int wgs_pack_split32(const float* src, long long rows, int C, long long ld, const float* scale,
-                     long long rows_per_group, void* dst, void* stream);
+                     long long scale_ld, long long rows_per_group, void* dst, void* stream);
 
 #define WGS_MAX_TAPS 64
 typedef struct wgs_conv_desc {
@@ -81,9 +81,12 @@ typedef struct wgs_conv_desc {
     int cout;
     const float* alpha;      /* [out_n, cout] per-sample per-channel scale (demodulation) or NULL */
     const float* beta;       /* [cout] bias or NULL */
-    int act;                 /* 0 none, 1 relu, 2 leaky relu 0.2 */
+    int act;                 /* 0 none, 1 relu, 2 leaky relu 0.2, 3 sqrt(2)*leaky relu 0.2 (FusedLeakyReLU) */
     int accumulate;          /* add to the existing output instead of overwriting */
     int force_bn;            /* 0 = choose the channel tile automatically */
+    const float* noise;      /* per-pixel noise plane indexed by OUTPUT pixel [y*noise_ld + x], or NULL  */
+    float noise_w;           /* NoiseInjection weight (models/StyleGAN2/model.py:231-241)                */
+    int noise_ld;
 } wgs_conv_desc;
 
 /* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls
@@ -92,6 +95,27 @@ typedef struct wgs_conv_desc {
  * torchvision resnet18 (lib/reconstructor.py:54), forward and data-gradient.                       */
 int wgs_conv_split32(const wgs_conv_desc* desc, void* stream);
 int wgs_conv_desc_size(void);
+
+/* ---- StyleGAN2 glue (CUDA cores, HBM/latency-bound) --------------------------------------------- *
+ * wgs_linear_small: out[b,o] = epi(wscale * sum_i f(x[b,i]) * W[o,i] + bscale * bias[o]); f = square when
+ * in_square; epi 0 linear, 1 sqrt(2)*lrelu(0.2) (EqualLinear 'fused_lrelu', models/StyleGAN2/model.py:110-131),
+ * 2 rsqrt(wscale*sum + eps) (demodulation :194-195 restated on squared styles). Row strides in floats.   */
+int wgs_linear_small(const float* x, long long x_ld, const float* W, long long w_ld, const float* bias,
+                     float* out, long long out_ld, int B, int I, int O, float wscale, float bscale,
+                     int in_square, int epi, float eps, int accumulate, void* stream);
+/* PixelNorm over latent rows (model.py:9-15). */
+int wgs_pixelnorm_rows(const float* x, float* out, int B, int d, void* stream);
+/* Separable 4-tap FIR (upfirdn2d up=down=1: Blur, model.py:66-81; op/upfirdn2d_kernel.cu:52-137) fused with
+ * demodulation scale alpha[n,c], NoiseInjection (:231-241) and FusedLeakyReLU (op/fused_bias_act_kernel.cu).
+ * y [N,Hin,Win,C] -> out [N,Hout,Wout,C]; h_taps4 is a HOST pointer to the four 1-D taps.               */
+int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win, int Hout, int Wout, int C, int pad0,
+                 const float* h_taps4, const float* alpha, const float* beta, const float* noise,
+                 float noise_w, int act, void* stream);
+/* ToRGB (model.py:270-282): 1x1 modulated conv (no demod) + bias + FIR-upsampled skip (Upsample :29-45).
+ * a [N,H,W,C], s [N,C] (row stride s_ld), W [3,C], bias [3], prev [N,H/2,W/2,3] or NULL, rgb [N,H,W,3].  */
+int wgs_sg2_torgb(const float* a, const float* s, long long s_ld, const float* W, const float* bias,
+                  const float* prev, float* rgb, int N, int H, int Wd, int C, float wscale,
+                  const float* h_taps4, void* stream);
 
 #ifdef __cplusplus
 }

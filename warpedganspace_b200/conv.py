@@ -24,6 +24,7 @@ class ConvDesc(ctypes.Structure):
         ('cout', ctypes.c_int),
         ('alpha', ctypes.c_void_p), ('beta', ctypes.c_void_p),
         ('act', ctypes.c_int), ('accumulate', ctypes.c_int), ('force_bn', ctypes.c_int),
+        ('noise', ctypes.c_void_p), ('noise_w', ctypes.c_float), ('noise_ld', ctypes.c_int),
     ]
 
 
@@ -48,7 +49,11 @@ def pack_split32(x, scale=None, rows_per_group=1, out=None):
     ld = C
     if out is None:
         out = torch.empty(*x.shape[:-1], chunks_of(C), 64, dtype=torch.bfloat16, device=x.device)
-    _lib.call('wgs_pack_split32', _lib.ptr(x), rows, C, ld, _lib.ptr(scale), int(rows_per_group),
+    scale_ld = scale.stride(0) if scale is not None else 0
+    if scale is not None:
+        assert scale.stride(1) == 1 and scale.shape[1] == C
+    _lib.call('wgs_pack_split32', _lib.ptr(x), rows, C, ld,
+              ctypes.c_void_p(scale.data_ptr()) if scale is not None else None, scale_ld, int(rows_per_group),
               _lib.ptr(out), _lib.stream())
     return out
 
@@ -61,7 +66,7 @@ def pack_weights(w):
 
 
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
-              alpha=None, beta=None, act=0, accumulate=False, force_bn=0):
+              alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -86,6 +91,9 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
     d.alpha = alpha.data_ptr() if alpha is not None else None
     d.beta = beta.data_ptr() if beta is not None else None
     d.act, d.accumulate, d.force_bn = act, int(accumulate), force_bn
+    if noise is not None:
+        assert noise.is_contiguous() and noise.dim() == 2
+        d.noise, d.noise_w, d.noise_ld = noise.data_ptr(), float(noise_w), noise.shape[1]
     for t in (x_split, w_split, out):
         if not t.is_cuda:
             raise RuntimeError('conv needs CUDA tensors; there is no CPU fallback')

@@ -42,6 +42,9 @@ struct ConvKernelParams {
     int out_y0, out_x0, out_ystep, out_xstep;
     const float* alpha;
     const float* beta;
+    const float* noise;      // [grid plane in output coords: out_h x out_w] or null
+    float noise_w;
+    int noise_ld;
     int act, accumulate;
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
@@ -50,6 +53,7 @@ struct ConvKernelParams {
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 1) return v > 0.f ? v : 0.f;
     if (act == 2) return v > 0.f ? v : 0.2f * v;
+    if (act == 3) return 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);      // FusedLeakyReLU
     return v;
 }
 
@@ -141,6 +145,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
                      (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
         const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
+        const float nz = (p.noise && valid)
+            ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
+            : 0.f;
         ptx::mbar_wait(acc_bar, 0);
         ptx::tc_fence_after();
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
@@ -155,6 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (cc < p.cout) {
                     float r = v[i];
                     if (alpha) r *= __ldg(alpha + cc);
+                    r += nz;
                     if (p.beta) r += __ldg(p.beta + cc);
                     if (p.accumulate) r += dst[cc];
                     v[i] = apply_act(r, p.act);
@@ -204,6 +212,8 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ in, const __n
         float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
                      (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx + co;
         if (p.alpha) acc *= p.alpha[(size_t)n * p.cout + co];
+        if (p.noise)
+            acc += p.noise_w * p.noise[(size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0)];
         if (p.beta) acc += p.beta[co];
         if (p.accumulate) acc += *dst;
         *dst = apply_act(acc, p.act);
@@ -260,6 +270,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.out = d->out; p.out_sn = d->out_sn; p.out_sy = d->out_sy; p.out_sx = d->out_sx;
     p.out_y0 = d->out_y0; p.out_x0 = d->out_x0; p.out_ystep = d->out_ystep; p.out_xstep = d->out_xstep;
     p.alpha = d->alpha; p.beta = d->beta; p.act = d->act; p.accumulate = d->accumulate;
+    p.noise = d->noise; p.noise_w = d->noise_w; p.noise_ld = d->noise_ld;
     for (int i = 0; i < d->num_taps; ++i) {
         WGS_REQUIRE(d->tap_dy[i] >= -64 && d->tap_dy[i] <= 64 && d->tap_dx[i] >= -64 && d->tap_dx[i] <= 64,
                     "conv: tap offset out of range");

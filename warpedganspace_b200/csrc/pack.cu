@@ -6,7 +6,7 @@ namespace wgs {
 
 // one thread per (row, chunk, 4-channel group): reads a float4 (or a guarded tail), writes 4 hi + 4 lo
 __global__ void pack_split32_kernel(const float* __restrict__ src, long long rows, int C, long long ld,
-                                    const float* __restrict__ scale, long long rows_per_group,
+                                    const float* __restrict__ scale, long long scale_ld, long long rows_per_group,
                                     __nv_bfloat16* __restrict__ dst, int chunks) {
     const long long total = rows * chunks * 8;
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -27,7 +27,7 @@ __global__ void pack_split32_kernel(const float* __restrict__ src, long long row
             for (int k = 0; k < 4; ++k) if (c0 + k < C) v[k] = __ldg(s + k);
         }
         if (scale) {
-            const float* sc = scale + (r / rows_per_group) * C + c0;
+            const float* sc = scale + (r / rows_per_group) * scale_ld + c0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) if (c0 + k < C) v[k] *= __ldg(sc + k);
         }
@@ -45,14 +45,14 @@ __global__ void pack_split32_kernel(const float* __restrict__ src, long long row
 using namespace wgs;
 
 extern "C" int wgs_pack_split32(const float* src, long long rows, int C, long long ld, const float* scale,
-                                long long rows_per_group, void* dst, void* stream) {
+                                long long scale_ld, long long rows_per_group, void* dst, void* stream) {
     WGS_REQUIRE(rows >= 0 && C >= 1 && ld >= C, "pack_split32: bad sizes");
     WGS_REQUIRE(!scale || rows_per_group >= 1, "pack_split32: rows_per_group must be >= 1 with a scale");
     if (rows == 0) return 0;
     const int chunks = (C + 31) / 32;
     const long long total = rows * chunks * 8;
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
-    pack_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, C, ld, scale, rows_per_group,
+    pack_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, C, ld, scale, scale_ld, rows_per_group,
                                                                   (__nv_bfloat16*)dst, chunks);
     count_launch();
     WGS_LAUNCH_CHECK();

@@ -1,0 +1,252 @@
+// StyleGAN2 glue kernels around the tensor-core convs: small-batch linears (mapping network,
+// per-layer modulation, demodulation coefficients), FIR blur + noise + bias + activation, ToRGB with
+// the FIR-upsampled skip.  All HBM/latency-bound CUDA-core work.
+#include "common.cuh"
+#include "wgs_b200.h"
+
+namespace wgs {
+
+// ------------------------------------------------------------------------------------------------
+// out[b, o] = epi( wscale * sum_i f(x[b, i]) * W[o, i]  (+ bscale * bias[o]) )       B small, I % 4 == 0
+//   f = identity or square;  epi: 0 linear, 1 sqrt(2)*lrelu(0.2), 2 rsqrt(. + eps)
+// One warp per output feature: the weight row is streamed once with float4 loads and reused for every
+// batch row (EqualLinear, models/StyleGAN2/model.py:110-131; demod :194-195 restated as a linear on s^2).
+constexpr int LIN_BT = 8;
+
+__global__ void __launch_bounds__(256)
+linear_small_kernel(const float* __restrict__ x, long long x_ld, const float* __restrict__ W, long long w_ld,
+                    const float* __restrict__ bias, float* __restrict__ out, long long out_ld, int B, int I, int O,
+                    float wscale, float bscale, int in_square, int epi, float eps, int accumulate) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + warp;
+    if (o >= O) return;
+    const float* wrow = W + (size_t)o * w_ld;
+    for (int b0 = 0; b0 < B; b0 += LIN_BT) {
+        float acc[LIN_BT];
+#pragma unroll
+        for (int t = 0; t < LIN_BT; ++t) acc[t] = 0.f;
+        for (int i = lane * 4; i < I; i += 128) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + i));
+#pragma unroll
+            for (int t = 0; t < LIN_BT; ++t) {
+                if (b0 + t < B) {
+                    float4 x4 = __ldg(reinterpret_cast<const float4*>(x + (size_t)(b0 + t) * x_ld + i));
+                    if (in_square) { x4.x *= x4.x; x4.y *= x4.y; x4.z *= x4.z; x4.w *= x4.w; }
+                    acc[t] += w4.x * x4.x + w4.y * x4.y + w4.z * x4.z + w4.w * x4.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < LIN_BT; ++t) acc[t] = warp_sum(acc[t]);
+        if (lane < LIN_BT && b0 + lane < B) {
+            float v = 0.f;
+#pragma unroll
+            for (int t = 0; t < LIN_BT; ++t) if (t == lane) v = acc[t];
+            v *= wscale;
+            if (epi == 2) {
+                v = rsqrtf(v + eps);
+            } else {
+                if (bias) v += bscale * __ldg(bias + o);
+                if (epi == 1) v = 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);
+            }
+            float* dst = out + (size_t)(b0 + lane) * out_ld + o;
+            *dst = accumulate ? (*dst + v) : v;
+        }
+    }
+}
+
+// x * rsqrt(mean(x^2) + 1e-8) per row (PixelNorm on latents, model.py:9-15)
+__global__ void pixelnorm_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int d) {
+    __shared__ float red[32];
+    const float* r = x + (size_t)blockIdx.x * d;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) s += r[i] * r[i];
+    s = block_sum(s, red);
+    const float k = rsqrtf(s / d + 1e-8f);
+    for (int i = threadIdx.x; i < d; i += blockDim.x) out[(size_t)blockIdx.x * d + i] = r[i] * k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Separable 4-tap FIR (upfirdn2d with up = down = 1, op/upfirdn2d_kernel.cu:52-137) fused with the
+// StyledConv tail: out = act(alpha[n,c] * fir(y)[Y,X,c] + noise_w * noise[Y,X] + beta[c]).
+// y: [N, Hin, Win, C] NHWC, out: [N, Hout, Wout, C]; fir(y)[Y,X] = sum_ij kf[i] kf[j] y[Y+i-pad0, X+j-pad0].
+__global__ void __launch_bounds__(256)
+fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int Hin, int Win, int Hout, int Wout,
+                int C, int pad0, float k0, float k1, float k2, float k3, const float* __restrict__ alpha,
+                const float* __restrict__ beta, const float* __restrict__ noise, float noise_w, int act) {
+    const int c4n = C >> 2;
+    const long long total = (long long)N * Hout * Wout * c4n;
+    const float kf[4] = {k3, k2, k1, k0};                       // correlation with the flipped kernel
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4;
+        long long r = i / c4n;
+        const int X = (int)(r % Wout); r /= Wout;
+        const int Y = (int)(r % Hout);
+        const int n = (int)(r / Hout);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = Y + a - pad0;
+            if (yy < 0 || yy >= Hin) continue;
+            float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int xx = X + b - pad0;
+                if (xx < 0 || xx >= Win) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(y + (((size_t)n * Hin + yy) * Win + xx) * C + c));
+                row.x += kf[b] * v.x; row.y += kf[b] * v.y; row.z += kf[b] * v.z; row.w += kf[b] * v.w;
+            }
+            acc.x += kf[a] * row.x; acc.y += kf[a] * row.y; acc.z += kf[a] * row.z; acc.w += kf[a] * row.w;
+        }
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        const float nz = noise ? noise_w * __ldg(noise + (size_t)Y * Wout + X) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float t = v[k];
+            if (alpha) t *= __ldg(alpha + (size_t)n * C + c + k);
+            t += nz;
+            if (beta) t += __ldg(beta + c + k);
+            if (act == 3) t = 1.41421356237309515f * (t > 0.f ? t : 0.2f * t);
+            else if (act == 2) t = t > 0.f ? t : 0.2f * t;
+            else if (act == 1) t = t > 0.f ? t : 0.f;
+            v[k] = t;
+        }
+        *reinterpret_cast<float4*>(out + (((size_t)n * Hout + Y) * Wout + X) * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ToRGB (model.py:270-282): 1x1 modulated conv without demodulation + bias + FIR-upsampled skip.
+//   rgb[n,y,x,o] = sum_c a[n,y,x,c] * (wscale * W[o,c] * s[n,c]) + bias[o] + up2(prev)[n,y,x,o]
+// a: [N,H,W,C]; s: [N, C] (row stride s_ld); W: [3, C]; prev: [N,H/2,W/2,3] or NULL; rgb: [N,H,W,3].
+// up2 = upfirdn2d(up=2, taps*2 per axis, pad (2,1)) -> per axis: even y: k3*p[y/2-1] + k1*p[y/2];
+// odd y: k2*p[(y-1)/2] + k0*p[(y+1)/2]  (taps (k0..k3) already include the factor 2).
+// LPP lanes cooperate on one pixel (LPP = min(32, C/4)); 32/LPP pixels per warp.
+__global__ void __launch_bounds__(256)
+torgb_kernel(const float* __restrict__ a, const float* __restrict__ s, long long s_ld, const float* __restrict__ W,
+             const float* __restrict__ bias, const float* __restrict__ prev, float* __restrict__ rgb, int N, int H,
+             int Wd, int C, float wscale, float k0, float k1, float k2, float k3, int lpp) {
+    extern __shared__ float wm[];                               // [3][C] modulated weights of image n
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+        const int c = i % C;
+        wm[i] = wscale * __ldg(W + i) * __ldg(s + (size_t)n * s_ld + c);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % lpp, pix_in_warp = lane / lpp, ppw = 32 / lpp;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp_id = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long npix = (long long)H * Wd;
+    const int h2 = H >> 1, w2 = Wd >> 1;
+    for (long long p0 = warp_id * ppw; p0 < npix; p0 += warps_total * ppw) {
+        const long long pix = p0 + pix_in_warp;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        if (pix < npix) {
+            const float* ap = a + ((size_t)n * npix + pix) * C;
+            for (int c = sub * 4; c < C; c += lpp * 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(ap + c));
+                const float4 w0 = *reinterpret_cast<const float4*>(wm + c);
+                const float4 w1 = *reinterpret_cast<const float4*>(wm + C + c);
+                const float4 w2v = *reinterpret_cast<const float4*>(wm + 2 * C + c);
+                r0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+                r1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+                r2 += v.x * w2v.x + v.y * w2v.y + v.z * w2v.z + v.w * w2v.w;
+            }
+        }
+        for (int o = lpp >> 1; o > 0; o >>= 1) {
+            r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+            r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+            r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        }
+        if (sub == 0 && pix < npix) {
+            float o3[3] = {r0 + __ldg(bias), r1 + __ldg(bias + 1), r2 + __ldg(bias + 2)};
+            if (prev) {
+                const int yy = (int)(pix / Wd), xx = (int)(pix % Wd);
+                int ya, yb, xa, xb;
+                float wya, wyb, wxa, wxb;
+                if (yy & 1) { ya = (yy - 1) >> 1; yb = (yy + 1) >> 1; wya = k2; wyb = k0; }
+                else        { ya = (yy >> 1) - 1; yb = yy >> 1;       wya = k3; wyb = k1; }
+                if (xx & 1) { xa = (xx - 1) >> 1; xb = (xx + 1) >> 1; wxa = k2; wxb = k0; }
+                else        { xa = (xx >> 1) - 1; xb = xx >> 1;       wxa = k3; wxb = k1; }
+                const int ys[2] = {ya, yb}, xs[2] = {xa, xb};
+                const float wy[2] = {wya, wyb}, wx[2] = {wxa, wxb};
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (ys[i] < 0 || ys[i] >= h2) continue;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (xs[j] < 0 || xs[j] >= w2) continue;
+                        const float* pp = prev + (((size_t)n * h2 + ys[i]) * w2 + xs[j]) * 3;
+                        const float wgt = wy[i] * wx[j];
+                        o3[0] += wgt * __ldg(pp); o3[1] += wgt * __ldg(pp + 1); o3[2] += wgt * __ldg(pp + 2);
+                    }
+                }
+            }
+            float* dst = rgb + ((size_t)n * npix + pix) * 3;
+            dst[0] = o3[0]; dst[1] = o3[1]; dst[2] = o3[2];
+        }
+    }
+}
+
+}  // namespace wgs
+
+using namespace wgs;
+
+extern "C" int wgs_linear_small(const float* x, long long x_ld, const float* W, long long w_ld, const float* bias,
+                                float* out, long long out_ld, int B, int I, int O, float wscale, float bscale,
+                                int in_square, int epi, float eps, int accumulate, void* stream) {
+    WGS_REQUIRE(B >= 0 && I > 0 && O > 0, "linear_small: bad sizes");
+    WGS_REQUIRE(I % 4 == 0 && x_ld % 4 == 0 && w_ld % 4 == 0, "linear_small: I, x_ld, w_ld must be multiples of 4");
+    WGS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)W & 15) == 0, "linear_small: operands must be 16-byte aligned");
+    if (B == 0) return 0;
+    linear_small_kernel<<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x, x_ld, W, w_ld, bias, out, out_ld, B, I, O,
+                                                                         wscale, bscale, in_square, epi, eps, accumulate);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_pixelnorm_rows(const float* x, float* out, int B, int d, void* stream) {
+    WGS_REQUIRE(B >= 0 && d > 0, "pixelnorm_rows: bad sizes");
+    if (B == 0) return 0;
+    pixelnorm_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(x, out, d);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win, int Hout, int Wout, int C, int pad0,
+                            const float* taps4, const float* alpha, const float* beta, const float* noise,
+                            float noise_w, int act, void* stream) {
+    WGS_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "fir4_act: channels must be a multiple of 4");
+    WGS_REQUIRE(taps4 != nullptr, "fir4_act: taps4 is a HOST pointer to 4 floats");
+    const long long total = (long long)N * Hout * Wout * (C / 4);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 32);
+    fir4_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1],
+                                                              taps4[2], taps4[3], alpha, beta, noise, noise_w, act);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_sg2_torgb(const float* a, const float* s, long long s_ld, const float* W, const float* bias,
+                             const float* prev, float* rgb, int N, int H, int Wd, int C, float wscale,
+                             const float* taps4, void* stream) {
+    WGS_REQUIRE(N > 0 && C >= 4 && C % 4 == 0, "torgb: channels must be a multiple of 4");
+    WGS_REQUIRE(!prev || (H % 2 == 0 && Wd % 2 == 0), "torgb: skip needs even output size");
+    int lpp = 32;
+    while (lpp > 1 && lpp * 4 > C) lpp >>= 1;
+    const long long npix = (long long)H * Wd;
+    const int ppw = 32 / lpp;
+    const long long warps = (npix + ppw - 1) / ppw;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((warps + 7) / 8, (long long)num_sms() * 8 / std::max(1, N) + 1));
+    const float k0 = taps4 ? taps4[0] : 0.25f, k1 = taps4 ? taps4[1] : 0.75f, k2 = taps4 ? taps4[2] : 0.75f,
+                k3 = taps4 ? taps4[3] : 0.25f;
+    torgb_kernel<<<dim3(blocks, N), 256, (size_t)3 * C * sizeof(float), (cudaStream_t)stream>>>(
+        a, s, s_ld, W, bias, prev, rgb, N, H, Wd, C, wscale, k0, k1, k2, k3, lpp);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}

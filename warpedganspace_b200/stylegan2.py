@@ -1,0 +1,284 @@
+"""StyleGAN2 generator on the libwgs_b200 kernels.
+
+Mirrors the reference ``models.StyleGAN2.model.Generator`` (models/StyleGAN2/model.py:285-408): same
+constructor arguments, attributes (``size``, ``style_dim``, ``n_latent``, ``num_layers``, ``channels``),
+``get_latent`` / ``forward(styles, input_is_latent=...) -> (image, None)`` and the same 171 state-dict
+keys, so a reference ``g_ema`` checkpoint loads with ``load_state_dict``.
+
+B200-first restatement of the math (verified to 1e-15 in fp64):
+  * modulated conv  y[b,o] = d[b,o] * conv(W, s[b,i] * x[b,i])  with  d = rsqrt(scale^2 * sum_i s^2 * Wsq[o,i]
+    + 1e-8), Wsq = sum_k W^2 — the per-sample [B,Co,Ci,k,k] weight tensor and the groups=B conv of
+    model.py:190-226 disappear; the whole batch is one dense implicit GEMM on tensor cores;
+  * the stride-2 transposed conv (:201-206) is four output-phase tap lists of the same kernel;
+  * blur + demod + noise + bias + sqrt(2)*lrelu is one FIR kernel; same-resolution layers fuse
+    demod + noise + bias + activation into the conv epilogue; ToRGB + skip upsample is one kernel.
+The frozen generator receives no weight gradients; backward only carries the data gradient to the styles.
+"""
+import ctypes
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+from . import conv as C
+
+
+def default_channels(channel_multiplier=2):
+    c = {4: 512, 8: 512, 16: 512, 32: 512}
+    for res, base in ((64, 256), (128, 128), (256, 64), (512, 32), (1024, 16)):
+        c[res] = base * channel_multiplier
+    return c
+
+
+def _fir2d(taps=(1, 3, 3, 1), gain=1.0):
+    k = torch.tensor(taps, dtype=torch.float32)
+    k = torch.outer(k, k)
+    return k / k.sum() * gain
+
+
+class _Node(nn.Module):
+    """Bare container used to reproduce the reference module tree (and therefore its state-dict keys)."""
+
+
+def _equal_linear(in_dim, out_dim, bias_init=0.0, lr_mul=1.0):
+    m = _Node()
+    m.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+    m.bias = nn.Parameter(torch.full((out_dim,), float(bias_init)))
+    return m
+
+
+def _mod_conv(ci, co, k, style_dim, upsample=False):
+    m = _Node()
+    m.weight = nn.Parameter(torch.randn(1, co, ci, k, k))
+    m.modulation = _equal_linear(style_dim, ci, bias_init=1.0)
+    if upsample:
+        m.blur = _Node()
+        m.blur.register_buffer('kernel', _fir2d(gain=4.0))
+    return m
+
+
+def _styled_conv(ci, co, style_dim, upsample=False):
+    m = _Node()
+    m.conv = _mod_conv(ci, co, 3, style_dim, upsample)
+    m.noise = _Node()
+    m.noise.weight = nn.Parameter(torch.zeros(1))
+    m.activate = _Node()
+    m.activate.bias = nn.Parameter(torch.zeros(co))
+    return m
+
+
+def _to_rgb(ci, style_dim, upsample=True):
+    m = _Node()
+    if upsample:
+        m.upsample = _Node()
+        m.upsample.register_buffer('kernel', _fir2d(gain=4.0))
+    m.conv = _mod_conv(ci, 3, 1, style_dim)
+    m.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+    return m
+
+
+_TAPS = (ctypes.c_float * 4)(0.25, 0.75, 0.75, 0.25)          # [1,3,3,1]/8 * 2 per axis (kernel * 4 overall)
+
+
+class Generator(nn.Module):
+    def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=(1, 3, 3, 1), lr_mlp=0.01,
+                 channels=None):
+        super().__init__()
+        if tuple(blur_kernel) != (1, 3, 3, 1):
+            raise NotImplementedError('only the [1,3,3,1] FIR of the released models is implemented')
+        self.size, self.style_dim, self.n_mlp, self.lr_mlp = size, style_dim, n_mlp, lr_mlp
+        self.channels = dict(channels) if channels else default_channels(channel_multiplier)
+        self.log_size = int(math.log2(size))
+        self.num_layers = (self.log_size - 2) * 2 + 1
+        self.n_latent = self.log_size * 2 - 2
+        self.style = nn.ModuleList([_Node()] + [_equal_linear(style_dim, style_dim, lr_mul=lr_mlp)
+                                                for _ in range(n_mlp)])
+        self.input = _Node()
+        self.input.input = nn.Parameter(torch.randn(1, self.channels[4], 4, 4))
+        self.conv1 = _styled_conv(self.channels[4], self.channels[4], style_dim)
+        self.to_rgb1 = _to_rgb(self.channels[4], style_dim, upsample=False)
+        self.convs, self.to_rgbs = nn.ModuleList(), nn.ModuleList()
+        self.upsamples = nn.ModuleList()
+        self.noises = _Node()
+        for layer in range(self.num_layers):
+            res = (layer + 5) // 2
+            self.noises.register_buffer('noise_%d' % layer, torch.randn(1, 1, 2 ** res, 2 ** res))
+        cin = self.channels[4]
+        for i in range(3, self.log_size + 1):
+            co = self.channels[2 ** i]
+            self.convs.append(_styled_conv(cin, co, style_dim, upsample=True))
+            self.convs.append(_styled_conv(co, co, style_dim))
+            self.to_rgbs.append(_to_rgb(co, style_dim))
+            cin = co
+        self._plan = None
+
+    # ------------------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._plan = None                       # packed weights live on the old device
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def plan(self):
+        """Kernel-ready (frozen) weights: split32 packs, squared-weight sums, concatenated modulation."""
+        if self._plan is not None:
+            return self._plan
+        dev = self.input.input.device
+        if dev.type != 'cuda':
+            raise RuntimeError('StyleGAN2 Generator runs on CUDA only (no CPU fallback); call .cuda() first')
+        P = {}
+        layers = [('conv1', self.conv1, False)]
+        for i in range(self.log_size - 2):
+            layers.append(('convs.%d' % (2 * i), self.convs[2 * i], True))
+            layers.append(('convs.%d' % (2 * i + 1), self.convs[2 * i + 1], False))
+        rgbs = [self.to_rgb1] + list(self.to_rgbs)
+        mod_w, mod_b, offs = [], [], []
+        off = 0
+        with torch.no_grad():
+            P['styled'] = []
+            for name, m, up in layers:
+                w = m.conv.weight[0].float()                                  # [Co, Ci, 3, 3]
+                co, ci = w.shape[:2]
+                ent = dict(name=name, up=up, ci=ci, co=co, scale=1.0 / math.sqrt(ci * 9), s_off=off,
+                           w_fwd=C.pack_weights(w),
+                           wsq=w.pow(2).sum(dim=[2, 3]).contiguous(),          # [Co, Ci]
+                           noise_w=float(m.noise.weight.item()), bias=m.activate.bias.detach().float().contiguous())
+                # data-gradient weights: dx[ci] = sum_{taps,co} dy[co] * W[co,ci,tap]
+                if up:
+                    ent['w_bwd'] = C.pack_weights(w.permute(1, 0, 2, 3).contiguous())          # strided conv, same taps
+                else:
+                    ent['w_bwd'] = C.pack_weights(torch.flip(w, [2, 3]).permute(1, 0, 2, 3).contiguous())
+                ent['wsq_t'] = ent['wsq'].t().contiguous()                    # [Ci, Co]
+                mod_w.append(m.conv.modulation.weight.detach().float())
+                mod_b.append(m.conv.modulation.bias.detach().float())
+                off += ci
+                P['styled'].append(ent)
+            P['rgb'] = []
+            for m in rgbs:
+                w = m.conv.weight[0, :, :, 0, 0].float().contiguous()          # [3, C]
+                ci = w.shape[1]
+                P['rgb'].append(dict(ci=ci, scale=1.0 / math.sqrt(ci), s_off=off, w=w,
+                                     bias=m.bias.detach().float().reshape(3).contiguous()))
+                mod_w.append(m.conv.modulation.weight.detach().float())
+                mod_b.append(m.conv.modulation.bias.detach().float())
+                off += ci
+            P['mod_w'] = torch.cat(mod_w, 0).contiguous()                     # [sumC, style_dim]
+            P['mod_b'] = torch.cat(mod_b, 0).contiguous()
+            P['mod_w_t'] = P['mod_w'].t().contiguous()                        # [style_dim, sumC]
+            P['sum_c'] = off
+            P['map_w'] = [self.style[i].weight.detach().float().contiguous() for i in range(1, self.n_mlp + 1)]
+            P['map_b'] = [self.style[i].bias.detach().float().contiguous() for i in range(1, self.n_mlp + 1)]
+            P['map_w_t'] = [w.t().contiguous() for w in P['map_w']]
+            P['const'] = self.input.input[0].detach().float().permute(1, 2, 0).contiguous()   # [4,4,C] NHWC
+            P['noise'] = [getattr(self.noises, 'noise_%d' % i)[0, 0].detach().float().contiguous()
+                          for i in range(self.num_layers)]
+            d_total = sum(e['co'] for e in P['styled'])
+            P['d_total'] = d_total
+        self._plan = P
+        return P
+
+    # ------------------------------------------------------------------------------------------
+    def get_latent(self, z):
+        """Mapping network: PixelNorm + n_mlp x (EqualLinear, lr_mul, fused lrelu) (model.py:291-295)."""
+        return _mapping_forward(self, z.float().contiguous())[-1]
+
+    def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
+                input_is_latent=False, noise=None, randomize_noise=False):
+        if len(styles) != 1 or styles[0].dim() != 2 or truncation != 1 or noise is not None or randomize_noise:
+            raise NotImplementedError('hot path only: one [B, style_dim] latent, fixed noise buffers, no truncation')
+        x = styles[0].float().contiguous()
+        w = x if input_is_latent else self.get_latent(x)
+        img = synthesis(self, w)                                              # NHWC
+        image = img.permute(0, 3, 1, 2)                                       # logical NCHW, channels-last memory
+        if return_latents:
+            return image, w.unsqueeze(1).repeat(1, self.n_latent, 1)
+        return image, None
+
+
+# ----------------------------------------------------------------------------------------------
+def _linear(x, W, bias, out, *, wscale=1.0, bscale=1.0, in_square=0, epi=0, eps=0.0, accumulate=0):
+    B, I = x.shape
+    O = W.shape[0]
+    assert x.stride(1) == 1 and W.stride(1) == 1 and out.stride(1) == 1
+    _lib.call('wgs_linear_small', ctypes.c_void_p(x.data_ptr()), x.stride(0), ctypes.c_void_p(W.data_ptr()), W.stride(0),
+              _lib.ptr(bias), ctypes.c_void_p(out.data_ptr()), out.stride(0), B, I, O, float(wscale), float(bscale),
+              int(in_square), int(epi), float(eps), int(accumulate), _lib.stream())
+    return out
+
+
+def _mapping_forward(G, z):
+    """Returns the list [pixelnorm(z), h1, ..., h8 = w] (all kept for the backward pass)."""
+    P = G.plan()
+    B, d = z.shape
+    acts = [torch.empty_like(z)]
+    _lib.call('wgs_pixelnorm_rows', _lib.ptr(z), _lib.ptr(acts[0]), B, d, _lib.stream())
+    wscale = (1.0 / math.sqrt(d)) * G.lr_mlp
+    for i in range(G.n_mlp):
+        out = torch.empty(B, G.style_dim, device=z.device, dtype=torch.float32)
+        _linear(acts[-1], P['map_w'][i], P['map_b'][i], out, wscale=wscale, bscale=G.lr_mlp, epi=1)
+        acts.append(out)
+    return acts
+
+
+def styles_and_demod(G, w):
+    """All 26 per-layer styles in one launch, then the 17 demodulation vectors."""
+    P = G.plan()
+    B = w.shape[0]
+    s_all = torch.empty(B, P['sum_c'], device=w.device, dtype=torch.float32)
+    _linear(w, P['mod_w'], P['mod_b'], s_all, wscale=1.0 / math.sqrt(G.style_dim), bscale=1.0)
+    demod = []
+    for e in P['styled']:
+        d = torch.empty(B, e['co'], device=w.device, dtype=torch.float32)
+        s = s_all[:, e['s_off']: e['s_off'] + e['ci']]
+        _linear(s, e['wsq'], None, d, wscale=e['scale'] ** 2, in_square=1, epi=2, eps=1e-8)
+        demod.append(d)
+    return s_all, demod
+
+
+def synthesis(G, w, tape=None):
+    """w [B, style_dim] -> image NHWC [B, size, size, 3].  When `tape` is a dict, everything the
+    data-gradient pass needs is recorded in it."""
+    P = G.plan()
+    B = w.shape[0]
+    dev = w.device
+    s_all, demod = styles_and_demod(G, w)
+    if tape is not None:
+        tape.update(s_all=s_all, demod=demod, acts=[], rgb=[], w=w)
+
+    def style_of(e):
+        return s_all[:, e['s_off']: e['s_off'] + e['ci']]
+
+    def torgb(a, idx, prev):
+        r = P['rgb'][idx]
+        n, h, wd, c = a.shape
+        out = torch.empty(n, h, wd, 3, device=dev, dtype=torch.float32)
+        s = style_of(r)
+        _lib.call('wgs_sg2_torgb', _lib.ptr(a), ctypes.c_void_p(s.data_ptr()), s.stride(0), _lib.ptr(r['w']),
+                  _lib.ptr(r['bias']), _lib.ptr(prev), _lib.ptr(out), n, h, wd, c, r['scale'], _TAPS, _lib.stream())
+        return out
+
+    a = P['const'].unsqueeze(0).expand(B, -1, -1, -1).contiguous()             # [B,4,4,C]
+    skip = None
+    for li, e in enumerate(P['styled']):
+        n, h, wd, _ = a.shape
+        xs = C.pack_split32(a, scale=style_of(e), rows_per_group=h * wd)
+        if tape is not None:
+            tape['acts'].append(a)                                             # input activation of layer li
+        noise = P['noise'][li]
+        if e['up']:
+            y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3)                       # [B, 2h+1, 2w+1, Co] raw
+            a = torch.empty(n, 2 * h, 2 * wd, e['co'], device=dev, dtype=torch.float32)
+            _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(a), n, 2 * h + 1, 2 * wd + 1, 2 * h, 2 * wd, e['co'], 1,
+                      _TAPS, _lib.ptr(demod[li]), _lib.ptr(e['bias']), _lib.ptr(noise), e['noise_w'], 3, _lib.stream())
+        else:
+            a = C.conv2d(xs, e['w_fwd'], 3, 3, padding=1, alpha=demod[li], beta=e['bias'], noise=noise,
+                         noise_w=e['noise_w'], act=3)
+            skip = torgb(a, li // 2, skip)
+            if tape is not None:
+                tape['rgb'].append(skip)
+    if tape is not None:
+        tape['acts'].append(a)
+    return skip
