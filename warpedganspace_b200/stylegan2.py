@@ -142,15 +142,17 @@ class Generator(nn.Module):
             for name, m, up in layers:
                 w = m.conv.weight[0].float()                                  # [Co, Ci, 3, 3]
                 co, ci = w.shape[:2]
-                ent = dict(name=name, up=up, ci=ci, co=co, scale=1.0 / math.sqrt(ci * 9), s_off=off,
-                           w_fwd=C.pack_weights(w),
+                scale = 1.0 / math.sqrt(ci * 9)
+                ws = w * scale                                                # equalised-lr scale folded in
+                ent = dict(name=name, up=up, ci=ci, co=co, scale=scale, s_off=off,
+                           w_fwd=C.pack_weights(ws),
                            wsq=w.pow(2).sum(dim=[2, 3]).contiguous(),          # [Co, Ci]
                            noise_w=float(m.noise.weight.item()), bias=m.activate.bias.detach().float().contiguous())
                 # data-gradient weights: dx[ci] = sum_{taps,co} dy[co] * W[co,ci,tap]
                 if up:
-                    ent['w_bwd'] = C.pack_weights(w.permute(1, 0, 2, 3).contiguous())          # strided conv, same taps
+                    ent['w_bwd'] = C.pack_weights(ws.permute(1, 0, 2, 3).contiguous())         # strided conv, same taps
                 else:
-                    ent['w_bwd'] = C.pack_weights(torch.flip(w, [2, 3]).permute(1, 0, 2, 3).contiguous())
+                    ent['w_bwd'] = C.pack_weights(torch.flip(ws, [2, 3]).permute(1, 0, 2, 3).contiguous())
                 ent['wsq_t'] = ent['wsq'].t().contiguous()                    # [Ci, Co]
                 mod_w.append(m.conv.modulation.weight.detach().float())
                 mod_b.append(m.conv.modulation.bias.detach().float())
