@@ -117,6 +117,14 @@ int wgs_sg2_torgb(const float* a, const float* s, long long s_ld, const float* W
                   const float* prev, float* rgb, int N, int H, int Wd, int C, float wscale,
                   const float* h_taps4, void* stream);
 
+/* Weight gradient of F.conv2d(x, w, stride, padding) on tensor cores (csrc/wgrad.cu):
+ * xs split32 [n,h,w,ci_chunks,64], dys split32 [n,oh,ow,co_chunks,64] ->
+ * dw fp32 [kh*kw][co_chunks*32][ci_chunks*32], ACCUMULATED (zero it first).  Replaces the cuDNN wgrad
+ * reached from loss.backward(), lib/trainer.py:250.                                                */
+int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int ci_chunks, const void* dys, int oh,
+                           int ow, int co_chunks, int kh, int kw, int stride, int pad, float* dw,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

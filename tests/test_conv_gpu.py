@@ -133,3 +133,36 @@ def test_simt_twin_matches(monkeypatch):
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0, out.stderr[-2000:]
     assert float(out.stdout.strip().splitlines()[-1]) < 2e-5
+
+
+WG_CASES = [
+    # N, Ci, H, W, Co, k, stride, pad
+    (2, 32, 16, 16, 32, 3, 1, 1),
+    (4, 64, 32, 32, 64, 3, 1, 1),
+    (2, 64, 16, 16, 128, 3, 2, 1),
+    (2, 6, 32, 32, 64, 7, 2, 3),
+    (3, 128, 8, 8, 256, 3, 1, 1),
+    (2, 64, 16, 16, 128, 1, 2, 0),
+    (4, 2, 32, 32, 6, 5, 1, 0),
+    (4, 16, 5, 5, 120, 5, 1, 0),
+    (1, 160, 12, 20, 96, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize('case', WG_CASES)
+def test_wgrad_and_dgrad_match_torch(case):
+    from warpedganspace_b200 import reconstructor as R
+    N, Ci, H, W, Co, k, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Co, Ci, k, k, generator=g).cuda() / (Ci * k * k) ** 0.5).requires_grad_(True)
+    b = torch.randn(Co, generator=g).cuda().requires_grad_(True)
+    y_ref = F.conv2d(x, w, b, stride=stride, padding=pad)
+    cot = torch.randn(y_ref.shape, generator=g).cuda()
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad((y_ref * cot).sum(), (x, w, b))
+    y = R.conv2d(x.contiguous(memory_format=torch.channels_last), w, b, stride, pad)
+    assert rel(y, y_ref) < 2e-5
+    gx, gw, gb = torch.autograd.grad((y * cot).sum(), (x, w, b))
+    assert rel(gx, gx_ref) < 2e-5
+    assert rel(gw, gw_ref) < 3e-5
+    assert rel(gb, gb_ref) < 1e-5

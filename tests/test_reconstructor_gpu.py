@@ -1,0 +1,49 @@
+"""GPU parity: Reconstructor (ResNet-18 / LeNet, train-mode BN) against the reference fixtures."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle.reconstructor as o_rec
+
+pytestmark = pytest.mark.gpu
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+@pytest.mark.parametrize('name', ['resnet', 'lenet'])
+def test_reconstructor_fixture(golden, name):
+    from warpedganspace_b200.reconstructor import Reconstructor
+    torch.backends.cudnn.allow_tf32 = False
+    fx = golden('reconstructor_%s.pt' % name)
+    sd = o_rec.init_state(fx['type'], fx['dim'], fx['channels'], generator=gen(fx['seed']))
+    R = Reconstructor(fx['type'], fx['dim'], fx['channels'])
+    R.load_state_dict(sd, strict=True)
+    R.cuda().train()
+    x1 = fx['x1'].cuda().requires_grad_(True)
+    x2 = fx['x2'].cuda().requires_grad_(True)
+    logits, mag = R(x1, x2)
+    assert rel(logits, fx['logits']) < 2e-4 and rel(mag, fx['mag']) < 2e-4
+    assert torch.equal(logits.argmax(1).cpu(), fx['logits'].argmax(1))          # path-index argmax bit-exact
+    loss = F.cross_entropy(logits, fx['idx'].cuda()) + 0.25 * (mag - fx['tgt'].cuda()).abs().mean()
+    assert rel(loss, fx['loss']) < 1e-5
+    loss.backward()
+    assert rel(x1.grad, fx['dx1']) < 1e-3 and rel(x2.grad, fx['dx2']) < 1e-3
+    params = dict(R.named_parameters())
+    for k, n in fx['grad_norms'].items():
+        assert abs(float(params[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
+    first = 'features_extractor.conv1.weight' if name == 'resnet' else 'feature_extractor.0.weight'
+    assert rel(params[first].grad, fx['d_first_conv']) < 1e-3
+    head = 'path_indices.weight' if name == 'resnet' else 'path_indices.3.weight'
+    assert rel(params[head].grad, fx['d_head_w']) < 1e-3
+    sd_after = R.state_dict()
+    for k, v in fx['running'].items():
+        assert rel(sd_after[k], v) < 1e-4, k
+    if name == 'resnet':
+        assert params['features_extractor.fc.weight'].grad is None             # the dead fc stays untouched
