@@ -125,6 +125,21 @@ int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int ci_chunks, c
                            int ow, int co_chunks, int kh, int kw, int stride, int pad, float* dw,
                            void* stream);
 
+/* ---- StyleGAN2 data-gradient glue (csrc/sg2_bwd.cu) — replaces autograd through
+ * models/StyleGAN2/model.py:187-282 for the frozen generator (no weight gradients are formed).
+ * P = pixels per image, tensors [N, P, C]; reductions are accumulated (zero the outputs first).     */
+int wgs_sg2_act_bwd(const float* da, const float* a, const float* demod, const float* bias,
+                    const float* noise, float noise_w, float* dpre, float* dd, int N, long long P, int C,
+                    void* stream);
+int wgs_sg2_mod_bwd(const float* dx, const float* a_prev, int a_bcast, const float* s, long long s_ld,
+                    float* da_prev, int accumulate, float* ds, long long ds_ld, int N, long long P, int C,
+                    void* stream);
+int wgs_sg2_torgb_bwd(const float* drgb, const float* a, const float* s, long long s_ld, const float* W,
+                      float wscale, float* da, int accumulate, float* ds, long long ds_ld, int N,
+                      long long P, int C, void* stream);
+int wgs_sg2_rgb_up_bwd(const float* drgb, float* dprev, int N, int H, int W, const float* h_taps4,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

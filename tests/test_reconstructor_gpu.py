@@ -29,7 +29,7 @@ def test_reconstructor_fixture(golden, name):
     x1 = fx['x1'].cuda().requires_grad_(True)
     x2 = fx['x2'].cuda().requires_grad_(True)
     logits, mag = R(x1, x2)
-    assert rel(logits, fx['logits']) < 2e-4 and rel(mag, fx['mag']) < 2e-4
+    assert rel(logits, fx["logits"]) < 2e-4 and rel(mag, fx["mag"]) < 1e-3     # 20 conv layers, train-mode BN at batch 4
     assert torch.equal(logits.argmax(1).cpu(), fx['logits'].argmax(1))          # path-index argmax bit-exact
     loss = F.cross_entropy(logits, fx['idx'].cuda()) + 0.25 * (mag - fx['tgt'].cuda()).abs().mean()
     assert rel(loss, fx['loss']) < 1e-5
@@ -37,7 +37,8 @@ def test_reconstructor_fixture(golden, name):
     assert rel(x1.grad, fx['dx1']) < 1e-3 and rel(x2.grad, fx['dx2']) < 1e-3
     params = dict(R.named_parameters())
     for k, n in fx['grad_norms'].items():
-        assert abs(float(params[k].grad.double().norm()) - n) <= 1e-3 * max(n, 1e-12), k
+        # biases feeding a train-mode BatchNorm have an exactly-zero gradient: only rounding noise (~1e-7)
+        assert abs(float(params[k].grad.double().norm()) - n) <= 1e-3 * n + 2e-6, (k, float(params[k].grad.double().norm()), n)
     first = 'features_extractor.conv1.weight' if name == 'resnet' else 'feature_extractor.0.weight'
     assert rel(params[first].grad, fx['d_first_conv']) < 1e-3
     head = 'path_indices.weight' if name == 'resnet' else 'path_indices.3.weight'

@@ -58,3 +58,26 @@ def test_generator_small_channels_vs_oracle():
         want = o_sg2.generate(sd, z, None, 256)
         got = G([z.cuda()], input_is_latent=False)[0]
     assert rel(got, want) < 1e-4
+
+
+@pytest.mark.parametrize('wspace', [False, True])
+def test_generator_latent_gradient_vs_oracle(wspace):
+    """d(loss)/d(shift) through G(z + shift) (or G(w + shift)) against oracle autograd — the only gradient the
+    frozen generator has to deliver (to the SupportSets warp)."""
+    from warpedganspace_b200.gan_load import StyleGAN2Wrapper
+    ch = {4: 64, 8: 64, 16: 32, 32: 32, 64: 32}
+    sd, G = build(64, 11, channels=ch)
+    W = StyleGAN2Wrapper(G, shift_in_w_space=wspace)
+    g = gen(12)
+    z = torch.randn(3, 512, generator=g)
+    shift = (0.2 * torch.nn.functional.normalize(torch.randn(3, 512, generator=g), dim=1))
+    cot = torch.randn(3, 3, 64, 64, generator=g)
+    so = shift.clone().requires_grad_(True)
+    img_o = o_sg2.generate(sd, z, so, 64, shift_in_w_space=wspace)
+    (img_o * cot).sum().backward()
+    sc = shift.cuda().requires_grad_(True)
+    img = W(z.cuda(), sc)
+    assert rel(img, img_o) < 1e-4
+    (img * cot.cuda()).sum().backward()
+    assert rel(sc.grad, so.grad) < 1e-3                                  # north-star bar: 1e-3 relative
+    print('latent-gradient rel err', rel(sc.grad, so.grad))

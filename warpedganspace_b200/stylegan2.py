@@ -185,7 +185,7 @@ class Generator(nn.Module):
     # ------------------------------------------------------------------------------------------
     def get_latent(self, z):
         """Mapping network: PixelNorm + n_mlp x (EqualLinear, lr_mul, fused lrelu) (model.py:291-295)."""
-        return _mapping_forward(self, z.float().contiguous())[-1]
+        return _MappingFn.apply(self, z.float().contiguous())
 
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 input_is_latent=False, noise=None, randomize_noise=False):
@@ -193,7 +193,7 @@ class Generator(nn.Module):
             raise NotImplementedError('hot path only: one [B, style_dim] latent, fixed noise buffers, no truncation')
         x = styles[0].float().contiguous()
         w = x if input_is_latent else self.get_latent(x)
-        img = synthesis(self, w)                                              # NHWC
+        img = _SynthesisFn.apply(self, w)                                     # NHWC
         image = img.permute(0, 3, 1, 2)                                       # logical NCHW, channels-last memory
         if return_latents:
             return image, w.unsqueeze(1).repeat(1, self.n_latent, 1)
@@ -284,3 +284,125 @@ def synthesis(G, w, tape=None):
     if tape is not None:
         tape['acts'].append(a)
     return skip
+
+
+# ----------------------------------------------------------------------------------------------
+# backward (data gradient only)
+def synthesis_backward(G, tape, dimg):
+    """dimg [B, size, size, 3] NHWC -> d(loss)/dw [B, style_dim] using the activations recorded in `tape`."""
+    P = G.plan()
+    s_all, demod, acts = tape['s_all'], tape['demod'], tape['acts']
+    B = s_all.shape[0]
+    dev = s_all.device
+    ds_all = torch.zeros_like(s_all)
+    drgb = dimg.contiguous()
+    da = None
+    st = _lib.stream
+
+    def sl(t, e):
+        return t[:, e['s_off']: e['s_off'] + e['ci']]
+
+    for li in range(len(P['styled']) - 1, -1, -1):
+        e = P['styled'][li]
+        a, a_prev = acts[li + 1], acts[li]
+        n, h, wd, co = a.shape
+        npix = h * wd
+        if not e['up']:
+            # this activation also feeds ToRGB number li // 2
+            r = P['rgb'][li // 2]
+            s_r, ds_r = sl(s_all, r), sl(ds_all, r)
+            acc = da is not None
+            if da is None:
+                da = torch.empty_like(a)
+            _lib.call('wgs_sg2_torgb_bwd', _lib.ptr(drgb), _lib.ptr(a), ctypes.c_void_p(s_r.data_ptr()), s_r.stride(0),
+                      _lib.ptr(r['w']), r['scale'], _lib.ptr(da), int(acc), ctypes.c_void_p(ds_r.data_ptr()),
+                      ds_r.stride(0), n, npix, co, st())
+            if li > 0:
+                dprev = torch.empty(n, h // 2, wd // 2, 3, device=dev, dtype=torch.float32)
+                _lib.call('wgs_sg2_rgb_up_bwd', _lib.ptr(drgb), _lib.ptr(dprev), n, h, wd, _TAPS, st())
+                drgb = dprev
+        dd = torch.zeros(n, co, device=dev, dtype=torch.float32)
+        _lib.call('wgs_sg2_act_bwd', _lib.ptr(da), _lib.ptr(a), _lib.ptr(demod[li]), _lib.ptr(e['bias']),
+                  _lib.ptr(P['noise'][li]), e['noise_w'], _lib.ptr(da), _lib.ptr(dd), n, npix, co, st())
+        dpre = da
+        if e['up']:
+            hi, wi = h // 2, wd // 2
+            dyup = torch.empty(n, h + 1, wd + 1, co, device=dev, dtype=torch.float32)
+            _lib.call('wgs_fir4_act', _lib.ptr(dpre), _lib.ptr(dyup), n, h, wd, h + 1, wd + 1, co, 2, _TAPS,
+                      _lib.ptr(demod[li]), None, None, 0.0, 0, st())
+            gs = C.pack_split32(dyup)
+            dx = C.conv2d(gs, e['w_bwd'], 3, 3, stride=2, padding=0, cout=e['ci'])       # [n, hi, wi, ci]
+            assert dx.shape[1] == hi and dx.shape[2] == wi
+        else:
+            gs = C.pack_split32(dpre, scale=demod[li], rows_per_group=npix)
+            dx = C.conv2d(gs, e['w_bwd'], 3, 3, padding=1, cout=e['ci'])
+        s_e, ds_e = sl(s_all, e), sl(ds_all, e)
+        pin = dx.shape[1] * dx.shape[2]
+        if li == 0:
+            _lib.call('wgs_sg2_mod_bwd', _lib.ptr(dx), _lib.ptr(P['const']), 1, ctypes.c_void_p(s_e.data_ptr()),
+                      s_e.stride(0), None, 0, ctypes.c_void_p(ds_e.data_ptr()), ds_e.stride(0), n, pin, e['ci'], st())
+            da = None
+        else:
+            da = torch.empty_like(a_prev)
+            _lib.call('wgs_sg2_mod_bwd', _lib.ptr(dx), _lib.ptr(a_prev), 0, ctypes.c_void_p(s_e.data_ptr()),
+                      s_e.stride(0), _lib.ptr(da), 0, ctypes.c_void_p(ds_e.data_ptr()), ds_e.stride(0), n, pin,
+                      e['ci'], st())
+        # demodulation: d = rsqrt(scale^2 sum_i s_i^2 Wsq[o,i] + eps)  ->  ds_i += s_i * sum_o (-dd_o d_o^3 scale^2) Wsq[o,i]
+        t = (dd * demod[li].pow(3)).mul_(-(e['scale'] ** 2))
+        u = torch.empty(n, e['ci'], device=dev, dtype=torch.float32)
+        _linear(t, e['wsq_t'], None, u)
+        ds_e.add_(u * s_e)
+    dw = torch.empty(B, G.style_dim, device=dev, dtype=torch.float32)
+    _linear(ds_all, P['mod_w_t'], None, dw, wscale=1.0 / math.sqrt(G.style_dim))
+    return dw
+
+
+def _mapping_backward(G, acts, dw):
+    """Backward of PixelNorm + n_mlp fused-lrelu EqualLinears; acts = [pixelnorm(z), h1..hn]."""
+    P = G.plan()
+    wscale = (1.0 / math.sqrt(G.style_dim)) * G.lr_mlp
+    g = dw
+    for i in range(G.n_mlp - 1, -1, -1):
+        h = acts[i + 1]
+        dpre = g * torch.where(h > 0, math.sqrt(2.0), 0.2 * math.sqrt(2.0))
+        out = torch.empty_like(acts[i])
+        _linear(dpre.contiguous(), P['map_w_t'][i], None, out, wscale=wscale)
+        g = out
+    return g
+
+
+class _MappingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, G, z):
+        acts = _mapping_forward(G, z)
+        ctx.G = G
+        ctx.acts = acts
+        ctx.save_for_backward(z)
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, dw):
+        (z,) = ctx.saved_tensors
+        g = _mapping_backward(ctx.G, ctx.acts, dw.contiguous())
+        # PixelNorm: y = z * r, r = rsqrt(mean(z^2) + 1e-8)  ->  dz = r*g - z * r^3 * mean(z*g)
+        r = torch.rsqrt(z.pow(2).mean(dim=1, keepdim=True) + 1e-8)
+        dz = r * g - z * r.pow(3) * (z * g).mean(dim=1, keepdim=True)
+        return None, dz
+
+
+class _SynthesisFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, G, w):
+        need = ctx.needs_input_grad[1]
+        tape = {} if need else None
+        img = synthesis(G, w.detach().contiguous(), tape)
+        ctx.G, ctx.tape = G, tape
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        if ctx.tape is None:
+            return None, None
+        dw = synthesis_backward(ctx.G, ctx.tape, dimg)
+        ctx.tape = None
+        return None, dw
