@@ -140,6 +140,11 @@ int wgs_sg2_torgb_bwd(const float* drgb, const float* a, const float* s, long lo
 int wgs_sg2_rgb_up_bwd(const float* drgb, float* dprev, int N, int H, int W, const float* h_taps4,
                        void* stream);
 
+/* Fused Adam over a flat fp32 buffer, torch.optim.Adam defaults semantics (lib/trainer.py:153-156,253-254);
+ * the gradient is multiplied by grad_scale first (1/world_size after the NCCL sum).                  */
+int wgs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                  float eps, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,132 @@
+"""GPU parity of the whole paired training step (PairedTrainer) against the oracle step, plus
+size-independent properties at the full StyleGAN2-1024 / K=128 benchmark shape."""
+import pytest
+import torch
+
+import oracle.support_sets as o_ss
+import oracle.stylegan2 as o_sg2
+import oracle.reconstructor as o_rec
+import oracle.step as o_step
+
+pytestmark = pytest.mark.gpu
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def build(size, channels, K, D, seed, wspace=False):
+    from warpedganspace_b200 import SupportSets
+    from warpedganspace_b200.stylegan2 import Generator
+    from warpedganspace_b200.gan_load import StyleGAN2Wrapper
+    from warpedganspace_b200.reconstructor import Reconstructor
+    g_sd = o_sg2.init_state(size=size, generator=gen(seed), channels=channels)
+    s_sd = o_ss.init_state(K, D, 512, generator=gen(seed + 1))
+    r_sd = o_rec.init_state('ResNet', K, 3, generator=gen(seed + 2))
+    G = Generator(size, 512, 8, channels=channels)
+    G.load_state_dict(g_sd, strict=False)
+    S = SupportSets(K, D, 512, learn_gammas=True, gamma=1.0 / 512)
+    S.load_state_dict(s_sd)
+    R = Reconstructor('ResNet', K, 3)
+    R.load_state_dict(r_sd)
+    W = StyleGAN2Wrapper(G, shift_in_w_space=wspace).cuda()
+    return (g_sd, s_sd, r_sd), (W, S.cuda(), R.cuda())
+
+
+@pytest.mark.parametrize('wspace', [False, True])
+def test_step_matches_oracle(wspace):
+    from warpedganspace_b200.trainer import PairedTrainer
+    torch.backends.cudnn.allow_tf32 = False
+    ch = {4: 64, 8: 64, 16: 32, 32: 32}
+    K, D, B, size = 16, 4, 4, 32
+    (g_sd, s_sd, r_sd), (W, S, R) = build(size, ch, K, D, 20, wspace)
+    g = gen(30)
+    z = torch.randn(B, 512, generator=g)
+    idx = torch.randint(0, K, (B,), generator=g)
+    mag = o_step.sample_shift_magnitudes(B, 0.1, 0.2, generator=g)
+    gen_fn, get_w = o_step.make_generator('StyleGAN2', g_sd, size=size, shift_in_w_space=wspace)
+    want = o_step.paired_step(gen_fn, s_sd, r_sd, z, idx, mag, reconstructor_type='ResNet',
+                              get_w=get_w if wspace else None)
+    T = PairedTrainer(W, S, R, shift_in_w_space=wspace)
+    s_before = S.SUPPORT_SETS.detach().clone()
+    got = T.forward_backward(z.cuda(), idx.cuda(), mag.cuda())
+    assert rel(got['shift'], want['shift']) < 1e-5
+    assert rel(got['img'], want['img']) < 1e-4 and rel(got['img_shifted'], want['img_shifted']) < 1e-4
+    assert rel(got['logits'], want['logits']) < 1e-3
+    assert torch.equal(got['logits'].argmax(1).cpu(), want['logits'].argmax(1))
+    assert rel(got['loss'], want['loss']) < 1e-4
+    # gradients: ReLU / leaky-ReLU / max-pool kinks make fp32 gradients of ANY two implementations differ at the
+    # 1e-3..1e-2 level (the fp32 and fp64 oracles differ by 1e-3 on this graph); direction must agree
+    rows = torch.unique(idx)
+    gs, ws = S.SUPPORT_SETS.grad[rows.cuda()].cpu(), want['grads']['S']['SUPPORT_SETS'][rows]
+    cos = float(torch.nn.functional.cosine_similarity(gs.flatten().double(), ws.flatten().double(), dim=0))
+    print('dSUPPORT_SETS rel err %.2e cos %.6f' % (rel(gs, ws), cos))
+    assert cos > 0.999 and rel(gs, ws) < 5e-2
+    untouched = torch.ones(K, dtype=torch.bool)
+    untouched[rows] = False
+    assert float(S.SUPPORT_SETS.grad[untouched.cuda()].abs().max()) == 0.0
+    params = dict(R.named_parameters())
+    for k in ('path_indices.weight', 'shift_magnitudes.weight', 'features_extractor.conv1.weight',
+              'features_extractor.layer4.1.conv2.weight'):
+        e = rel(params[k].grad, want['grads']['R'][k])
+        print('dR %s rel err %.2e' % (k, e))
+        assert e < 5e-2, k
+    # optimiser: Adam from the oracle gradients must land where the fused kernel lands
+    T.optimizer_step()
+    p = s_sd['SUPPORT_SETS'].clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    o_step.adam_update(p, want['grads']['S']['SUPPORT_SETS'], m, v, 1)
+    assert rel((S.SUPPORT_SETS.detach().cpu() - s_before.cpu())[rows], (p - s_sd['SUPPORT_SETS'])[rows]) < 5e-2
+    assert float((S.SUPPORT_SETS.detach().cpu() - s_before.cpu())[untouched].abs().max()) == 0.0
+
+
+def test_adam_kernel_matches_oracle():
+    from warpedganspace_b200 import _lib
+    g = gen(1)
+    n = 1003
+    p0 = torch.randn(n, generator=g)
+    p = p0.clone().cuda()
+    m = torch.zeros(n).cuda()
+    v = torch.zeros(n).cuda()
+    po, mo, vo = p0.clone(), torch.zeros(n), torch.zeros(n)
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))
+        _lib.call('wgs_adam_step', _lib.ptr(p), _lib.ptr(gr.cuda()), _lib.ptr(m), _lib.ptr(v), n, 1e-4, 0.9, 0.999, 1e-8,
+                  step, 1.0, _lib.stream())
+        o_step.adam_update(po, gr, mo, vo, step)
+    assert rel(p.cpu() - p0, po - p0) < 1e-5
+
+
+def test_full_size_properties():
+    """StyleGAN2-1024, K=128, D=32, B=2 (benchmark shape, reduced batch): size-independent invariants."""
+    from warpedganspace_b200.trainer import PairedTrainer
+    from warpedganspace_b200 import _lib
+    K, D, B = 128, 32, 2
+    (_, s_sd, _), (W, S, R) = build(1024, None, K, D, 40)
+    T = PairedTrainer(W, S, R)
+    g = gen(41)
+    z = torch.randn(B, 512, generator=g).cuda()
+    idx = torch.tensor([5, 77]).cuda()
+    mag = torch.tensor([0.15, -0.12]).cuda()
+    _lib.reset_launch_count()
+    out = T.step(z, idx, mag)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() > 100
+    assert tuple(out['img'].shape) == (B, 3, 1024, 1024) and tuple(out['logits'].shape) == (B, K)
+    assert torch.isfinite(out['loss']) and torch.isfinite(out['img_shifted']).all()
+    # the warp moves each latent by exactly |magnitude| (unit-norm direction, lib/support_sets.py:101)
+    assert torch.allclose(out['shift'].norm(dim=1), mag.abs(), rtol=1e-5)
+    grad = T.flat_s.grad[: K * 2 * D * 512].view(K, -1)
+    nz = (grad.abs().sum(dim=1) > 0).nonzero().flatten().cpu().tolist()
+    assert nz == [5, 77]
+    # G(z) of the pair equals a stand-alone G(z) (batched pass == two reference calls)
+    with torch.no_grad():
+        alone = W(z)
+    assert rel(out['img'], alone) < 1e-6
+    delta = (S.SUPPORT_SETS.detach().cpu() - s_sd['SUPPORT_SETS']).abs().sum(dim=1)
+    assert set(delta.nonzero().flatten().tolist()) == {5, 77}

@@ -29,6 +29,15 @@ class StyleGAN2Wrapper(nn.Module):
             return self.G([w if shift is None else w + shift], input_is_latent=True)[0]
         return self.G([z if shift is None else z + shift], input_is_latent=False)[0]
 
+    def forward_pair(self, z, shift):
+        """(G(z), G(z, shift)) in one batched pass (fast path of lib/trainer.py:200,239)."""
+        if self.shift_in_w_space:
+            w = self.G.get_latent(z)
+            return self.G.synthesize_pair(w, w + shift)
+        lat = self.G.get_latent(torch.cat([z, z + shift], dim=0))
+        b = z.shape[0]
+        return self.G.synthesize_pair(lat[:b], lat[b:])
+
 
 def build_stylegan2(pretrained_gan_weights, resolution, shift_in_w_space=False):
     """models/gan_load.py:182-188: ``torch.load(path)['g_ema']`` with strict=False."""

@@ -187,6 +187,14 @@ class Generator(nn.Module):
         """Mapping network: PixelNorm + n_mlp x (EqualLinear, lr_mul, fused lrelu) (model.py:291-295)."""
         return _MappingFn.apply(self, z.float().contiguous())
 
+    def synthesize_pair(self, w_plain, w_shifted):
+        """Both images of a training pair in ONE batched pass: rows [w_plain; w_shifted]; only the shifted
+        rows are taped / back-propagated.  Returns (img_plain, img_shifted) as logical NCHW."""
+        b = w_plain.shape[0]
+        w_all = torch.cat([w_plain.detach().float(), w_shifted.float()], dim=0).contiguous()
+        img = _PairFn.apply(self, w_all, b).permute(0, 3, 1, 2)
+        return img[:b], img[b:]
+
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 input_is_latent=False, noise=None, randomize_noise=False):
         if len(styles) != 1 or styles[0].dim() != 2 or truncation != 1 or noise is not None or randomize_noise:
@@ -240,15 +248,17 @@ def styles_and_demod(G, w):
     return s_all, demod
 
 
-def synthesis(G, w, tape=None):
+def synthesis(G, w, tape=None, grad_from=0):
     """w [B, style_dim] -> image NHWC [B, size, size, 3].  When `tape` is a dict, everything the
-    data-gradient pass needs is recorded in it."""
+    data-gradient pass needs is recorded in it — for batch rows >= grad_from only (the un-shifted half of a
+    paired batch needs no gradient: lib/trainer.py:200 feeds G(z) with a z that has no grad)."""
     P = G.plan()
     B = w.shape[0]
     dev = w.device
     s_all, demod = styles_and_demod(G, w)
     if tape is not None:
-        tape.update(s_all=s_all, demod=demod, acts=[], rgb=[], w=w)
+        g0 = grad_from
+        tape.update(s_all=s_all[g0:], demod=[d[g0:] for d in demod], acts=[], rgb=[], w=w[g0:])
 
     def style_of(e):
         return s_all[:, e['s_off']: e['s_off'] + e['ci']]
@@ -268,7 +278,7 @@ def synthesis(G, w, tape=None):
         n, h, wd, _ = a.shape
         xs = C.pack_split32(a, scale=style_of(e), rows_per_group=h * wd)
         if tape is not None:
-            tape['acts'].append(a)                                             # input activation of layer li
+            tape['acts'].append(a[grad_from:])                                 # input activation of layer li
         noise = P['noise'][li]
         if e['up']:
             y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3)                       # [B, 2h+1, 2w+1, Co] raw
@@ -280,9 +290,9 @@ def synthesis(G, w, tape=None):
                          noise_w=e['noise_w'], act=3)
             skip = torgb(a, li // 2, skip)
             if tape is not None:
-                tape['rgb'].append(skip)
+                tape['rgb'].append(skip[grad_from:])
     if tape is not None:
-        tape['acts'].append(a)
+        tape['acts'].append(a[grad_from:])
     return skip
 
 
@@ -406,3 +416,23 @@ class _SynthesisFn(torch.autograd.Function):
         dw = synthesis_backward(ctx.G, ctx.tape, dimg)
         ctx.tape = None
         return None, dw
+
+
+class _PairFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, G, w_all, n_plain):
+        need = ctx.needs_input_grad[1]
+        tape = {} if need else None
+        img = synthesis(G, w_all.detach(), tape, grad_from=n_plain)
+        ctx.G, ctx.tape, ctx.n_plain, ctx.rows = G, tape, n_plain, w_all.shape[0]
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        if ctx.tape is None:
+            return None, None, None
+        dw = synthesis_backward(ctx.G, ctx.tape, dimg[ctx.n_plain:])
+        ctx.tape = None
+        full = dw.new_zeros(ctx.rows, dw.shape[1])
+        full[ctx.n_plain:] = dw
+        return None, full, None
