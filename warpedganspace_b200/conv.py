@@ -8,6 +8,26 @@ from . import _lib
 
 MAX_TAPS = 64
 
+# Optional per-launch profiling (bench.py): when PROFILE is a list, every tensor-core launch appends
+# (kind, algorithmic_flops, start_event, end_event) recorded on the launching stream.
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, kind, flops):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.append((kind, flops, e0, e1))
+
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [
@@ -66,7 +86,7 @@ def pack_weights(w):
 
 
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
-              alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0):
+              alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -97,7 +117,9 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
     for t in (x_split, w_split, out):
         if not t.is_cuda:
             raise RuntimeError('conv needs CUDA tensors; there is no CPU fallback')
+    e0 = _prof_begin()
     _lib.check(_lib.load().wgs_conv_split32(ctypes.byref(d), _lib.stream()))
+    _prof_end(e0, 'conv', 2.0 * out.shape[0] * grid[0] * grid[1] * d.cout * (cin or chunks * 32) * len(taps))
     return out
 
 

@@ -30,7 +30,8 @@ class _ConvFn(torch.autograd.Function):
         x_nhwc = x.permute(0, 2, 3, 1).contiguous()
         xs = C.pack_split32(x_nhwc)
         ws = C.pack_weights(w.detach())
-        out = C.conv2d(xs, ws, kh, kw, stride=stride, padding=padding, beta=bias.detach() if bias is not None else None)
+        out = C.conv2d(xs, ws, kh, kw, stride=stride, padding=padding, cin=ci,
+                       beta=bias.detach() if bias is not None else None)
         ctx.save_for_backward(xs, w)
         ctx.geom = (x.shape, stride, padding, bias is not None)
         return out.permute(0, 3, 1, 2)
@@ -73,7 +74,7 @@ def conv_dgrad(dys, w, in_hw, stride, padding):
                 continue
             taps = [((py + padding - ky) // stride, (px + padding - kx) // stride, ky * kw + kx)
                     for ky in kys for kx in kxs]
-            C.conv_taps(dys, wt, taps, dx, grid=(gh, gw), out_origin=(py, px), out_step=(stride, stride), cout=ci)
+            C.conv_taps(dys, wt, taps, dx, grid=(gh, gw), out_origin=(py, px), out_step=(stride, stride), cout=ci, cin=co)
     return dx
 
 
