@@ -288,7 +288,16 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.n_tiles_co = ceil_div(d->cout, BN);
     p.tmem_cols = std::max(32, next_pow2(BN));
     const int stage_bytes = A_STAGE_BYTES + BN * 128;
-    p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+    // Short contractions (few taps x chunks) are latency-bound per tile: keep the ring shallow so that several
+    // CTAs fit on one SM (smem and TMEM columns permitting) and overlap each other's prologue / epilogue.
+    const int k_blocks = d->num_taps * d->c_chunks;
+    int ctas_per_sm = 1;
+    if (k_blocks <= 12) ctas_per_sm = 4;
+    else if (k_blocks <= 24) ctas_per_sm = 3;
+    else if (k_blocks <= 48) ctas_per_sm = 2;
+    ctas_per_sm = std::max(1, std::min(ctas_per_sm, 512 / p.tmem_cols));
+    const int smem_budget = (220 * 1024) / ctas_per_sm - 2048;
+    p.stages = std::max(2, std::min(std::min(8, k_blocks), smem_budget / stage_bytes));
     const cudaStream_t st = (cudaStream_t)stream;
 
     if (conv_impl_is_simt()) {
