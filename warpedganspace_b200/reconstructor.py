@@ -18,6 +18,23 @@ from . import conv as C
 from . import wgrad as WG
 
 
+_FROZEN_PACKS = {}
+
+
+def _packed(w, transposed):
+    """split32 pack of a conv weight; cached for frozen (requires_grad=False) weights, which never change."""
+    if w.requires_grad:
+        return C.pack_weights(w.detach().permute(1, 0, 2, 3).contiguous() if transposed else w.detach())
+    key = (w.data_ptr(), tuple(w.shape), w._version, transposed)
+    hit = _FROZEN_PACKS.get(key)
+    if hit is None:
+        if len(_FROZEN_PACKS) > 512:
+            _FROZEN_PACKS.clear()
+        hit = C.pack_weights(w.detach().permute(1, 0, 2, 3).contiguous() if transposed else w.detach())
+        _FROZEN_PACKS[key] = hit
+    return hit
+
+
 class _ConvFn(torch.autograd.Function):
     """F.conv2d(x, w, bias, stride, padding) on the tensor-core kernel; x, out are logical NCHW with
     channels-last memory."""
@@ -29,7 +46,7 @@ class _ConvFn(torch.autograd.Function):
         co, ci, kh, kw = w.shape
         x_nhwc = x.permute(0, 2, 3, 1).contiguous()
         xs = C.pack_split32(x_nhwc)
-        ws = C.pack_weights(w.detach())
+        ws = _packed(w, False)
         out = C.conv2d(xs, ws, kh, kw, stride=stride, padding=padding, cin=ci,
                        beta=bias.detach() if bias is not None else None)
         ctx.save_for_backward(xs, w)
@@ -45,7 +62,7 @@ class _ConvFn(torch.autograd.Function):
         dys = C.pack_split32(dy_nhwc)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad(dys, w.detach(), (h, wd), stride, padding).permute(0, 3, 1, 2)
+            dx = conv_dgrad(dys, w, (h, wd), stride, padding).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             dw = WG.conv_wgrad(xs, dys, (co, ci, kh, kw), stride, padding)
         if has_bias and ctx.needs_input_grad[2]:
@@ -59,7 +76,7 @@ def conv_dgrad(dys, w, in_hw, stride, padding):
     co, ci, kh, kw = w.shape
     h, wd = in_hw
     n, oh, ow = dys.shape[0], dys.shape[1], dys.shape[2]
-    wt = C.pack_weights(w.permute(1, 0, 2, 3).contiguous())                 # [kh*kw, Ci, Co]
+    wt = _packed(w, True)                                                   # [kh*kw, Ci, Co]
     dx = torch.empty(n, h, wd, ci, device=dys.device, dtype=torch.float32)
     for py in range(stride):
         for px in range(stride):
