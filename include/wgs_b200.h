@@ -145,6 +145,11 @@ int wgs_sg2_rgb_up_bwd(const float* drgb, float* dprev, int N, int H, int W, con
 int wgs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                   float eps, int step, float grad_scale, void* stream);
 
+/* im2col into split32 for few-input-channel convs (ResNet stem 7x7/2 on 6 channels, lib/reconstructor.py:56-60):
+ * x fp32 NHWC [N,H,W,C] -> out split32 [N,OH,OW,ceil(kh*kw*C/32),64], K index = (ky*kw+kx)*C + c.             */
+int wgs_im2col_split32(const float* x, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
+                       int OH, int OW, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

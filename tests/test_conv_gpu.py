@@ -166,3 +166,45 @@ def test_wgrad_and_dgrad_match_torch(case):
     assert rel(gx, gx_ref) < 2e-5
     assert rel(gw, gw_ref) < 3e-5
     assert rel(gb, gb_ref) < 1e-5
+
+
+@pytest.mark.parametrize('case', [(2, 6, 32, 32, 64, 7, 2, 3), (3, 6, 64, 48, 64, 7, 2, 3), (4, 2, 32, 32, 6, 5, 1, 0)])
+def test_stem_im2col_path(case):
+    """Few-input-channel convs go through im2col -> 1-tap GEMM (forward and weight gradient)."""
+    from warpedganspace_b200 import reconstructor as R
+    N, Ci, H, W, Co, k, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case) + 7)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Co, Ci, k, k, generator=g).cuda() / (Ci * k * k) ** 0.5).requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, stride=stride, padding=pad)
+    cot = torch.randn(y_ref.shape, generator=g).cuda()
+    gx_ref, gw_ref = torch.autograd.grad((y_ref * cot).sum(), (x, w))
+    y = R.conv2d(x.contiguous(memory_format=torch.channels_last), w, None, stride, pad)
+    assert y.grad_fn.__class__.__name__.startswith('_StemConvFn')
+    assert rel(y, y_ref) < 2e-5
+    gx, gw = torch.autograd.grad((y * cot).sum(), (x, w))
+    assert rel(gx, gx_ref) < 2e-5 and rel(gw, gw_ref) < 3e-5
+
+
+@pytest.mark.parametrize('N,H,W,C,pad0,Ho,Wo', [(2, 9, 9, 32, 1, 8, 8), (1, 17, 33, 64, 1, 16, 32), (3, 8, 8, 16, 2, 9, 9),
+                                                (1, 6, 10, 8, 2, 7, 11), (2, 5, 7, 4, 1, 4, 6)])
+def test_fir4_act_matches_torch(N, H, W, C, pad0, Ho, Wo):
+    """Separable 4-tap FIR + per-sample scale + noise + bias + sqrt2*lrelu against upfirdn2d-style torch code."""
+    import ctypes
+    from warpedganspace_b200 import _lib
+    g = torch.Generator().manual_seed(N + H + W + C)
+    y = torch.randn(N, H, W, C, generator=g).cuda()
+    alpha = (torch.rand(N, C, generator=g) + 0.5).cuda()
+    beta = torch.randn(C, generator=g).cuda()
+    noise = torch.randn(Ho, Wo, generator=g).cuda()
+    taps = (ctypes.c_float * 4)(0.25, 0.75, 0.75, 0.25)
+    out = torch.empty(N, Ho, Wo, C, device='cuda')
+    _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(out), N, H, W, Ho, Wo, C, pad0, taps, _lib.ptr(alpha), _lib.ptr(beta),
+              _lib.ptr(noise), 0.3, 3, _lib.stream())
+    k1 = torch.tensor([0.25, 0.75, 0.75, 0.25], device='cuda')
+    k2 = torch.outer(k1, k1)
+    yp = F.pad(y.permute(0, 3, 1, 2), [pad0, Wo + 3 - W - pad0, pad0, Ho + 3 - H - pad0])
+    f = F.conv2d(yp, torch.flip(k2, [0, 1]).view(1, 1, 4, 4).expand(C, 1, 4, 4), groups=C)
+    want = f * alpha[:, :, None, None] + 0.3 * noise[None, None] + beta[None, :, None, None]
+    want = 2 ** 0.5 * F.leaky_relu(want, 0.2)
+    assert rel(out, want.permute(0, 2, 3, 1)) < 1e-6

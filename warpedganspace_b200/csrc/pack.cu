@@ -58,3 +58,53 @@ extern "C" int wgs_pack_split32(const float* src, long long rows, int C, long lo
     WGS_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// im2col straight into split32 for convolutions with very few input channels (the Reconstructor's
+// 7x7/2 stem on 6 channels, lib/reconstructor.py:56-60): K = kh*kw*C gathered per output pixel, so the
+// stem becomes a 1-tap GEMM with K = 294 (10 chunks) instead of 49 taps x one 6/32-full chunk.
+namespace wgs {
+
+__global__ void __launch_bounds__(256)
+im2col_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
+                      int OH, int OW, __nv_bfloat16* __restrict__ out, int chunks) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long npix = (long long)N * OH * OW;
+    const int K = kh * kw * C;
+    for (long long pix = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += warps) {
+        const int ox = (int)(pix % OW);
+        const int oy = (int)((pix / OW) % OH);
+        const int n = (int)(pix / ((long long)OW * OH));
+        const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+        __nv_bfloat16* dst = out + pix * chunks * 64;
+        for (int j = 0; j < chunks; ++j) {
+            const int k = j * 32 + lane;
+            float v = 0.f;
+            if (k < K) {
+                const int c = k % C, tap = k / C;
+                const int iy = iy0 + tap / kw, ix = ix0 + tap % kw;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((size_t)n * H + iy) * W + ix) * C + c);
+            }
+            __nv_bfloat16 hi, lo;
+            split_bf16(v, hi, lo);
+            dst[j * 64 + lane] = hi;
+            dst[j * 64 + 32 + lane] = lo;
+        }
+    }
+}
+
+}  // namespace wgs
+
+extern "C" int wgs_im2col_split32(const float* x, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
+                                  int OH, int OW, void* out, void* stream) {
+    WGS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && OH > 0 && OW > 0, "im2col: bad sizes");
+    const int chunks = (kh * kw * C + 31) / 32;
+    const long long npix = (long long)N * OH * OW;
+    const int blocks = (int)std::min<long long>((npix + 7) / 8, (long long)wgs::num_sms() * 32);
+    wgs::im2col_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW,
+                                                                       (__nv_bfloat16*)out, chunks);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}

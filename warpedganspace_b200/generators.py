@@ -15,6 +15,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from . import _tree
+from . import reconstructor as _rec
 from .reconstructor import conv2d
 
 # ------------------------------------------------------------------------------------------------
@@ -39,13 +40,16 @@ class _Frozen(nn.Module):
     def __init__(self):
         super().__init__()
         self._plan = None
+        _rec._FROZEN_PACKS.clear()              # the pack cache is keyed by address: a new model may reuse freed memory
 
     def _apply(self, fn, *a, **k):
         self._plan = None
+        _rec._FROZEN_PACKS.clear()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
         self._plan = None
+        _rec._FROZEN_PACKS.clear()
         return super().load_state_dict(*a, **k)
 
     def _require_cuda(self, x):

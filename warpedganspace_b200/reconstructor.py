@@ -14,6 +14,7 @@ import torch
 from torch import nn
 import torch.nn.functional as F
 
+from . import _lib
 from . import conv as C
 from . import wgrad as WG
 
@@ -70,6 +71,45 @@ class _ConvFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class _StemConvFn(torch.autograd.Function):
+    """Few-input-channel convolution (the 7x7/2 stem on 6 channels) as im2col -> one 1-tap GEMM on the tensor
+    cores: K = kh*kw*Ci packed densely instead of kh*kw taps of a mostly-empty 32-channel chunk.  The data
+    gradient (needed: it carries d loss / d image back into the generator) stays on the phase tap-list path."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding):
+        if not x.is_cuda:
+            raise RuntimeError('Reconstructor runs on CUDA tensors only (no CPU fallback); got %s' % x.device)
+        co, ci, kh, kw = w.shape
+        n, _, h, wd = x.shape
+        oh = (h + 2 * padding - kh) // stride + 1
+        ow = (wd + 2 * padding - kw) // stride + 1
+        x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+        chunks = (kh * kw * ci + 31) // 32
+        xcol = torch.empty(n, oh, ow, chunks, 64, device=x.device, dtype=torch.bfloat16)
+        _lib.call('wgs_im2col_split32', _lib.ptr(x_nhwc), n, h, wd, ci, kh, kw, stride, padding, oh, ow,
+                  _lib.ptr(xcol), _lib.stream())
+        wmat = w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci, 1, 1)        # K order (ky, kx, c)
+        out = C.conv2d(xcol, C.pack_weights(wmat), 1, 1, cin=kh * kw * ci)
+        ctx.save_for_backward(xcol, w)
+        ctx.geom = (x.shape, stride, padding)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xcol, w = ctx.saved_tensors
+        (n, ci, h, wd), stride, padding = ctx.geom
+        co, _, kh, kw = w.shape
+        dys = C.pack_split32(dy.permute(0, 2, 3, 1).contiguous())
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad(dys, w, (h, wd), stride, padding).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            dwm = WG.conv_wgrad(xcol, dys, (co, kh * kw * ci, 1, 1), 1, 0)           # [Co, K, 1, 1]
+            dw = dwm.reshape(co, kh, kw, ci).permute(0, 3, 1, 2).contiguous()
+        return dx, dw, None, None
+
+
 def conv_dgrad(dys, w, in_hw, stride, padding):
     """Data gradient of F.conv2d: dx[iy,ix,ci] = sum_{ky,kx,co} dy[(iy+p-ky)/s, (ix+p-kx)/s, co] * w[co,ci,ky,kx]
     (terms with non-integer quotients vanish).  stride 1: one flipped-tap conv; stride s: s*s output phases."""
@@ -96,6 +136,8 @@ def conv_dgrad(dys, w, in_hw, stride, padding):
 
 
 def conv2d(x, w, bias=None, stride=1, padding=0):
+    if bias is None and w.shape[1] < 16 and w.shape[2] * w.shape[3] >= 9:
+        return _StemConvFn.apply(x, w, stride, padding)
     return _ConvFn.apply(x, w, bias, stride, padding)
 
 
