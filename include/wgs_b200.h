@@ -87,6 +87,13 @@ typedef struct wgs_conv_desc {
     const float* noise;      /* per-pixel noise plane indexed by OUTPUT pixel [y*noise_ld + x], or NULL  */
     float noise_w;           /* NoiseInjection weight (models/StyleGAN2/model.py:231-241)                */
     int noise_ld;
+    /* fused consumers of the activation (identity output mapping only; `out` may then be NULL):            */
+    void* out_split;         /* split32 [out_n][grid_h][grid_w][cout/32][64] of act * split_scale[n,co]     */
+    const float* split_scale;/* [out_n, cout] with row stride split_scale_ld, or NULL (next layer's style)  */
+    long long split_scale_ld;
+    int out_from_n;          /* fp32 `out` only for images n >= out_from_n (the half that is back-propagated) */
+    const float* rgb_w;      /* [out_n][3][cout] modulated ToRGB weights (model.py:270-282) or NULL          */
+    float* rgb_out;          /* [out_n][grid_h][grid_w][3] += act . rgb_w  (pre-initialised: bias + skip)    */
 } wgs_conv_desc;
 
 /* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls
@@ -107,10 +114,17 @@ int wgs_linear_small(const float* x, long long x_ld, const float* W, long long w
 int wgs_pixelnorm_rows(const float* x, float* out, int B, int d, void* stream);
 /* Separable 4-tap FIR (upfirdn2d up=down=1: Blur, model.py:66-81; op/upfirdn2d_kernel.cu:52-137) fused with
  * demodulation scale alpha[n,c], NoiseInjection (:231-241) and FusedLeakyReLU (op/fused_bias_act_kernel.cu).
- * y [N,Hin,Win,C] -> out [N,Hout,Wout,C]; h_taps4 is a HOST pointer to the four 1-D taps.               */
+ * y [N,Hin,Win,C] -> out [N,Hout,Wout,C] (fp32, images n >= out_from_n only; may be NULL) and/or out_split
+ * (split32 of the result times split_scale[n,c]); h_taps4 is a HOST pointer to the four 1-D taps.           */
 int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win, int Hout, int Wout, int C, int pad0,
                  const float* h_taps4, const float* alpha, const float* beta, const float* noise,
-                 float noise_w, int act, void* stream);
+                 float noise_w, int act, void* out_split, const float* split_scale, long long split_scale_ld,
+                 int out_from_n, void* stream);
+/* ToRGB accumulator init (bias + FIR-upsampled skip) and modulated ToRGB weights for the fused conv epilogue. */
+int wgs_sg2_rgb_init(const float* bias, const float* prev, float* rgb, int N, int H, int W,
+                     const float* h_taps4, void* stream);
+int wgs_sg2_rgb_weights(const float* W, const float* s, long long s_ld, float* wm, int N, int C, float wscale,
+                        void* stream);
 /* ToRGB (model.py:270-282): 1x1 modulated conv (no demod) + bias + FIR-upsampled skip (Upsample :29-45).
  * a [N,H,W,C], s [N,C] (row stride s_ld), W [3,C], bias [3], prev [N,H/2,W/2,3] or NULL, rgb [N,H,W,3].  */
 int wgs_sg2_torgb(const float* a, const float* s, long long s_ld, const float* W, const float* bias,
@@ -129,8 +143,8 @@ int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int ci_chunks, c
  * models/StyleGAN2/model.py:187-282 for the frozen generator (no weight gradients are formed).
  * P = pixels per image, tensors [N, P, C]; reductions are accumulated (zero the outputs first).     */
 int wgs_sg2_act_bwd(const float* da, const float* a, const float* demod, const float* bias,
-                    const float* noise, float noise_w, float* dpre, float* dd, int N, long long P, int C,
-                    void* stream);
+                    const float* noise, float noise_w, float* dpre, float* dd, void* g_split, int N,
+                    long long P, int C, void* stream);
 int wgs_sg2_mod_bwd(const float* dx, const float* a_prev, int a_bcast, const float* s, long long s_ld,
                     float* da_prev, int accumulate, float* ds, long long ds_ld, int N, long long P, int C,
                     void* stream);

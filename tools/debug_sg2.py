@@ -33,12 +33,11 @@ x = sd['input.input'].repeat(2, 1, 1, 1)
 x = o.styled_conv(sd, 'conv1', x, w, sd['noises.noise_0'])
 print('conv1 act', rel(tape['acts'][1].permute(0, 3, 1, 2), x))
 skip = o.to_rgb(sd, 'to_rgb1', x, w)
-print('rgb1', rel(tape['rgb'][0].permute(0, 3, 1, 2), skip))
+
 for i in range(G.log_size - 2):
     x = o.styled_conv(sd, 'convs.%d' % (2 * i), x, w, sd['noises.noise_%d' % (2 * i + 1)], upsample=True)
     print('convs.%d act' % (2 * i), rel(tape['acts'][2 * i + 2].permute(0, 3, 1, 2), x))
     x = o.styled_conv(sd, 'convs.%d' % (2 * i + 1), x, w, sd['noises.noise_%d' % (2 * i + 2)])
     print('convs.%d act' % (2 * i + 1), rel(tape['acts'][2 * i + 3].permute(0, 3, 1, 2), x))
     skip = o.to_rgb(sd, 'to_rgbs.%d' % i, x, w, skip)
-    print('rgb', rel(tape['rgb'][i + 1].permute(0, 3, 1, 2), skip))
 print('image', rel(img.permute(0, 3, 1, 2), skip))

@@ -45,6 +45,8 @@ class ConvDesc(ctypes.Structure):
         ('alpha', ctypes.c_void_p), ('beta', ctypes.c_void_p),
         ('act', ctypes.c_int), ('accumulate', ctypes.c_int), ('force_bn', ctypes.c_int),
         ('noise', ctypes.c_void_p), ('noise_w', ctypes.c_float), ('noise_ld', ctypes.c_int),
+        ('out_split', ctypes.c_void_p), ('split_scale', ctypes.c_void_p), ('split_scale_ld', ctypes.c_longlong),
+        ('out_from_n', ctypes.c_int), ('rgb_w', ctypes.c_void_p), ('rgb_out', ctypes.c_void_p),
     ]
 
 
@@ -86,7 +88,8 @@ def pack_weights(w):
 
 
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
-              alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None):
+              alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None,
+              out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -98,13 +101,24 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
     d.in_n, d.in_h, d.in_w, d.c_chunks = n, h, w_, chunks
     d.w = w_split.data_ptr()
     d.w_taps, d.w_cout = w_split.shape[0], w_split.shape[1]
-    d.out_n, d.grid_h, d.grid_w, d.in_stride = out.shape[0], grid[0], grid[1], in_stride
+    d.out_n, d.grid_h, d.grid_w, d.in_stride = (out.shape[0] if out is not None else out_n), grid[0], grid[1], in_stride
     d.num_taps = len(taps)
     for i, (dy, dx, tw) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i], d.tap_w[i] = dy, dx, tw
-    assert out.dtype == torch.float32 and out.stride(3) == 1
-    d.out = out.data_ptr()
-    d.out_sn, d.out_sy, d.out_sx = out.stride(0), out.stride(1), out.stride(2)
+    if out is not None:
+        assert out.dtype == torch.float32 and out.stride(3) == 1
+        d.out = out.data_ptr()
+        d.out_sn, d.out_sy, d.out_sx = out.stride(0), out.stride(1), out.stride(2)
+    if out_split is not None:
+        assert out_split.is_contiguous() and out_split.dtype == torch.bfloat16
+        d.out_split = out_split.data_ptr()
+        if split_scale is not None:
+            assert split_scale.stride(1) == 1
+            d.split_scale, d.split_scale_ld = split_scale.data_ptr(), split_scale.stride(0)
+    d.out_from_n = out_from_n
+    if rgb_out is not None:
+        assert rgb_w.is_contiguous() and rgb_out.is_contiguous()
+        d.rgb_w, d.rgb_out = rgb_w.data_ptr(), rgb_out.data_ptr()
     d.out_y0, d.out_x0 = out_origin
     d.out_ystep, d.out_xstep = out_step
     d.cout = cout if cout is not None else w_split.shape[1]
@@ -114,12 +128,12 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
     if noise is not None:
         assert noise.is_contiguous() and noise.dim() == 2
         d.noise, d.noise_w, d.noise_ld = noise.data_ptr(), float(noise_w), noise.shape[1]
-    for t in (x_split, w_split, out):
+    for t in (x_split, w_split):
         if not t.is_cuda:
             raise RuntimeError('conv needs CUDA tensors; there is no CPU fallback')
     e0 = _prof_begin()
     _lib.check(_lib.load().wgs_conv_split32(ctypes.byref(d), _lib.stream()))
-    _prof_end(e0, 'conv', 2.0 * out.shape[0] * grid[0] * grid[1] * d.cout * (cin or chunks * 32) * len(taps))
+    _prof_end(e0, 'conv', 2.0 * d.out_n * grid[0] * grid[1] * d.cout * (cin or chunks * 32) * len(taps))
     return out
 
 
@@ -129,10 +143,11 @@ def conv2d(x_split, w_split, kh, kw, *, stride=1, padding=0, out=None, **kw_args
     oh = (h + 2 * padding - kh) // stride + 1
     ow = (w_ + 2 * padding - kw) // stride + 1
     co = kw_args.get('cout') or w_split.shape[1]
-    if out is None:
+    no_f32 = kw_args.pop('no_f32', False)
+    if out is None and not no_f32:
         out = torch.empty(n, oh, ow, co, dtype=torch.float32, device=x_split.device)
     taps = [(ky - padding, kx - padding, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
-    return conv_taps(x_split, w_split, taps, out, grid=(oh, ow), in_stride=stride, **kw_args)
+    return conv_taps(x_split, w_split, taps, out, grid=(oh, ow), in_stride=stride, out_n=n, **kw_args)
 
 
 def conv_transpose2d_s2(x_split, w_split, k, *, out=None, crop=0, **kw_args):

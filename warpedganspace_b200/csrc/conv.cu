@@ -46,6 +46,13 @@ struct ConvKernelParams {
     float noise_w;
     int noise_ld;
     int act, accumulate;
+    // fused consumers of the activation (all optional)
+    void* out_split;             // split32 [out_n][grid_h][grid_w][cout/32][64] of act * split_scale[n, co]
+    const float* split_scale;    // [out_n, cout] (row stride split_scale_ld) or null (= 1)
+    long long split_scale_ld;
+    int out_from_n;              // fp32 `out` is written only for images n >= out_from_n
+    const float* rgb_w;          // [out_n][3][cout] modulated ToRGB weights; rgb_out += act . rgb_w
+    float* rgb_out;              // [out_n][grid_h][grid_w][3], pre-initialised with bias + upsampled skip
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -57,7 +64,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 4)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -150,7 +157,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             : 0.f;
         ptx::mbar_wait(acc_bar, 0);
         ptx::tc_fence_after();
+        const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
+        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
         for (int c = 0; c < p.BN; c += 16) {
             float v[16];
             ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
@@ -166,15 +176,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (p.beta) r += __ldg(p.beta + cc);
                     if (p.accumulate) r += dst[cc];
                     v[i] = apply_act(r, p.act);
+                } else {
+                    v[i] = 0.f;
                 }
             }
-            if (vec_ok && co + 16 <= p.cout) {
+            if (p.rgb_w) {
+                const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-                for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+                for (int i = 0; i < 16; ++i) {
+                    if (co + i < p.cout) {
+                        rgb0 += v[i] * __ldg(wm + i);
+                        rgb1 += v[i] * __ldg(wm + p.cout + i);
+                        rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
+                    }
+                }
             }
+            if (p.out_split) {
+                __align__(16) __nv_bfloat16 hi[16], lo[16];
+                const float* sc = p.split_scale ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split_bf16(sc ? v[i] * __ldg(sc + i) : v[i], hi[i], lo[i]);
+                __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
+                                    (size_t)(co >> 5) * 64 + (co & 16);
+                reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
+                reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
+                reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
+                reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
+            }
+            if (write_f32) {
+                if (vec_ok && co + 16 <= p.cout) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+                    for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+                }
+            }
+        }
+        if (p.rgb_out && valid) {
+            float* ro = p.rgb_out + pix * 3;
+            atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
         }
     }
     ptx::tc_fence_before();
@@ -216,7 +257,17 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ in, const __n
             acc += p.noise_w * p.noise[(size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0)];
         if (p.beta) acc += p.beta[co];
         if (p.accumulate) acc += *dst;
-        *dst = apply_act(acc, p.act);
+        acc = apply_act(acc, p.act);
+        if (p.out && n >= p.out_from_n) *dst = acc;
+        const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
+        if (p.rgb_w)
+            for (int o = 0; o < 3; ++o) atomicAdd(p.rgb_out + pix * 3 + o, acc * p.rgb_w[((size_t)n * 3 + o) * p.cout + co]);
+        if (p.out_split) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(p.split_scale ? acc * p.split_scale[(size_t)n * p.split_scale_ld + co] : acc, hi, lo);
+            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) + (size_t)(co >> 5) * 64 + (co & 31);
+            sp[0] = hi; sp[32] = lo;
+        }
     }
 }
 
@@ -271,6 +322,13 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.out_y0 = d->out_y0; p.out_x0 = d->out_x0; p.out_ystep = d->out_ystep; p.out_xstep = d->out_xstep;
     p.alpha = d->alpha; p.beta = d->beta; p.act = d->act; p.accumulate = d->accumulate;
     p.noise = d->noise; p.noise_w = d->noise_w; p.noise_ld = d->noise_ld;
+    p.out_split = d->out_split; p.split_scale = d->split_scale; p.split_scale_ld = d->split_scale_ld;
+    p.out_from_n = d->out_from_n; p.rgb_w = d->rgb_w; p.rgb_out = d->rgb_out;
+    WGS_REQUIRE(d->out != nullptr || d->out_split != nullptr || d->rgb_out != nullptr, "conv: no output requested");
+    WGS_REQUIRE((!d->out_split && !d->rgb_out) || (d->out_ystep == 1 && d->out_xstep == 1 && d->out_y0 == 0 && d->out_x0 == 0),
+                "conv: fused split32 / ToRGB outputs need the identity output mapping");
+    WGS_REQUIRE(!d->out_split || d->cout % 32 == 0, "conv: split32 output needs cout % 32 == 0");
+    WGS_REQUIRE(!d->accumulate || d->out != nullptr, "conv: accumulate needs an fp32 output");
     for (int i = 0; i < d->num_taps; ++i) {
         WGS_REQUIRE(d->tap_dy[i] >= -64 && d->tap_dy[i] <= 64 && d->tap_dx[i] >= -64 && d->tap_dx[i] <= 64,
                     "conv: tap offset out of range");

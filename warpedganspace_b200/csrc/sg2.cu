@@ -73,7 +73,9 @@ __global__ void pixelnorm_rows_kernel(const float* __restrict__ x, float* __rest
 __global__ void __launch_bounds__(256)
 fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int Hin, int Win, int Hout, int Wout,
                 int C, int pad0, float k0, float k1, float k2, float k3, const float* __restrict__ alpha,
-                const float* __restrict__ beta, const float* __restrict__ noise, float noise_w, int act) {
+                const float* __restrict__ beta, const float* __restrict__ noise, float noise_w, int act,
+                __nv_bfloat16* __restrict__ out_split, const float* __restrict__ split_scale, long long split_scale_ld,
+                int out_from_n) {
     // each thread produces a 4 (rows) x 2 (cols) patch of one channel quad: 7 x 5 float4 loads for 8 outputs
     // (4.4 loads per output instead of 16), horizontal pass first, then the vertical combination in registers.
     const int c4n = C >> 2;
@@ -140,10 +142,68 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
                     else if (act == 1) t = t > 0.f ? t : 0.f;
                     v4[k] = t;
                 }
-                *reinterpret_cast<float4*>(out + (((size_t)n * Hout + Y) * Wout + X) * C + c) =
-                    make_float4(v4[0], v4[1], v4[2], v4[3]);
+                const size_t pix = ((size_t)n * Hout + Y) * Wout + X;
+                if (out && n >= out_from_n)
+                    *reinterpret_cast<float4*>(out + pix * C + c) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                if (out_split) {
+                    __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        split_bf16(split_scale ? v4[k] * __ldg(split_scale + (size_t)n * split_scale_ld + c + k) : v4[k],
+                                   hi[k], lo[k]);
+                    __nv_bfloat16* sp = out_split + pix * (size_t)(((C + 31) >> 5) * 64) + (size_t)(c >> 5) * 64 + (c & 31);
+                    *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+                    *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+                }
             }
         }
+    }
+}
+
+// rgb[n,y,x,:] = bias + up2(prev)[n,y,x,:]  — initialises the ToRGB accumulator that the conv epilogue adds into
+__global__ void rgb_init_kernel(const float* __restrict__ bias, const float* __restrict__ prev, float* __restrict__ rgb,
+                                int N, int H, int W, float k0, float k1, float k2, float k3) {
+    const long long total = (long long)N * H * W;
+    const int h2 = H >> 1, w2 = W >> 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W);
+        const int yy = (int)((i / W) % H);
+        const int n = (int)(i / ((long long)W * H));
+        float o3[3] = {__ldg(bias), __ldg(bias + 1), __ldg(bias + 2)};
+        if (prev) {
+            int ya, yb, xa, xb;
+            float wya, wyb, wxa, wxb;
+            if (yy & 1) { ya = (yy - 1) >> 1; yb = (yy + 1) >> 1; wya = k2; wyb = k0; }
+            else        { ya = (yy >> 1) - 1; yb = yy >> 1;       wya = k3; wyb = k1; }
+            if (xx & 1) { xa = (xx - 1) >> 1; xb = (xx + 1) >> 1; wxa = k2; wxb = k0; }
+            else        { xa = (xx >> 1) - 1; xb = xx >> 1;       wxa = k3; wxb = k1; }
+            const int ys[2] = {ya, yb}, xs[2] = {xa, xb};
+            const float wy[2] = {wya, wyb}, wx[2] = {wxa, wxb};
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                if (ys[a] < 0 || ys[a] >= h2) continue;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    if (xs[b] < 0 || xs[b] >= w2) continue;
+                    const float* pp = prev + (((size_t)n * h2 + ys[a]) * w2 + xs[b]) * 3;
+                    const float wgt = wy[a] * wx[b];
+                    o3[0] += wgt * __ldg(pp); o3[1] += wgt * __ldg(pp + 1); o3[2] += wgt * __ldg(pp + 2);
+                }
+            }
+        }
+        float* d = rgb + i * 3;
+        d[0] = o3[0]; d[1] = o3[1]; d[2] = o3[2];
+    }
+}
+
+// wm[n][o][c] = wscale * W[o][c] * s[n][c]   (modulated ToRGB weights consumed by the conv epilogue)
+__global__ void rgb_weights_kernel(const float* __restrict__ W, const float* __restrict__ s, long long s_ld,
+                                   float* __restrict__ wm, int N, int C, float wscale) {
+    const int total = N * 3 * C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % C, o = (i / C) % 3, n = i / (3 * C);
+        wm[i] = wscale * __ldg(W + o * C + c) * __ldg(s + (size_t)n * s_ld + c);
     }
 }
 
@@ -250,13 +310,15 @@ extern "C" int wgs_pixelnorm_rows(const float* x, float* out, int B, int d, void
 
 extern "C" int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win, int Hout, int Wout, int C, int pad0,
                             const float* taps4, const float* alpha, const float* beta, const float* noise,
-                            float noise_w, int act, void* stream) {
+                            float noise_w, int act, void* out_split, const float* split_scale, long long split_scale_ld,
+                            int out_from_n, void* stream) {
     WGS_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "fir4_act: channels must be a multiple of 4");
     WGS_REQUIRE(taps4 != nullptr, "fir4_act: taps4 is a HOST pointer to 4 floats");
     const long long total = (long long)N * ((Hout + 3) / 4) * ((Wout + 1) / 2) * (C / 4);
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 32);
     fir4_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1],
-                                                              taps4[2], taps4[3], alpha, beta, noise, noise_w, act);
+                                                              taps4[2], taps4[3], alpha, beta, noise, noise_w, act,
+                                                              (__nv_bfloat16*)out_split, split_scale, split_scale_ld, out_from_n);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
@@ -277,6 +339,29 @@ extern "C" int wgs_sg2_torgb(const float* a, const float* s, long long s_ld, con
                 k3 = taps4 ? taps4[3] : 0.25f;
     torgb_kernel<<<dim3(blocks, N), 256, (size_t)3 * C * sizeof(float), (cudaStream_t)stream>>>(
         a, s, s_ld, W, bias, prev, rgb, N, H, Wd, C, wscale, k0, k1, k2, k3, lpp);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_sg2_rgb_init(const float* bias, const float* prev, float* rgb, int N, int H, int W,
+                                const float* h_taps4, void* stream) {
+    WGS_REQUIRE(N > 0 && H > 0 && W > 0, "rgb_init: bad sizes");
+    WGS_REQUIRE(!prev || (H % 2 == 0 && W % 2 == 0), "rgb_init: skip needs even output size");
+    const float k0 = h_taps4 ? h_taps4[0] : 0.25f, k1 = h_taps4 ? h_taps4[1] : 0.75f, k2 = h_taps4 ? h_taps4[2] : 0.75f,
+                k3 = h_taps4 ? h_taps4[3] : 0.25f;
+    const long long total = (long long)N * H * W;
+    rgb_init_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16), 256, 0, (cudaStream_t)stream>>>(
+        bias, prev, rgb, N, H, W, k0, k1, k2, k3);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_sg2_rgb_weights(const float* W, const float* s, long long s_ld, float* wm, int N, int C, float wscale,
+                                   void* stream) {
+    WGS_REQUIRE(N > 0 && C > 0, "rgb_weights: bad sizes");
+    rgb_weights_kernel<<<ceil_div(N * 3 * C, 256), 256, 0, (cudaStream_t)stream>>>(W, s, s_ld, wm, N, C, wscale);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

@@ -33,7 +33,8 @@ __device__ __forceinline__ void reduce_quads_to_global(const float acc[4], float
 __global__ void __launch_bounds__(RED_THREADS)
 sg2_act_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a, const float* __restrict__ demod,
                    const float* __restrict__ bias, const float* __restrict__ noise, float noise_w,
-                   float* __restrict__ dpre, float* __restrict__ dd, long long P, int C) {
+                   float* __restrict__ dpre, float* __restrict__ dd, __nv_bfloat16* __restrict__ g_split, long long P,
+                   int C) {
     extern __shared__ float sm[];
     const int n = blockIdx.y;
     const int C4 = C >> 2, PL = RED_THREADS / C4;
@@ -58,7 +59,15 @@ sg2_act_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a, co
             o[k] = gv[k] * (pos ? SQRT2 : 0.2f * SQRT2);
             acc[k] += o[k] * (pre - nz - bv[k]) / dv[k];
         }
-        *reinterpret_cast<float4*>(dpre + off) = make_float4(o[0], o[1], o[2], o[3]);
+        if (dpre) *reinterpret_cast<float4*>(dpre + off) = make_float4(o[0], o[1], o[2], o[3]);
+        if (g_split) {                                   // operand of the data-gradient conv: d[n,c] * dpre, split32
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(o[k] * dv[k], hi[k], lo[k]);
+            __nv_bfloat16* sp = g_split + ((size_t)n * P + p) * (size_t)(C * 2) + (size_t)(q >> 3) * 64 + ((q & 7) << 2);
+            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+        }
     }
     reduce_quads_to_global(acc, sm, C, C4, PL, dd + (size_t)n * C);
 }
@@ -180,12 +189,13 @@ static bool red_ok(int C) { return C >= 4 && C % 4 == 0 && (C / 4) <= RED_THREAD
 using namespace wgs;
 
 extern "C" int wgs_sg2_act_bwd(const float* da, const float* a, const float* demod, const float* bias,
-                               const float* noise, float noise_w, float* dpre, float* dd, int N, long long P, int C,
-                               void* stream) {
+                               const float* noise, float noise_w, float* dpre, float* dd, void* g_split, int N,
+                               long long P, int C, void* stream) {
+    WGS_REQUIRE(!g_split || C % 32 == 0, "sg2_act_bwd: split32 output needs C % 32 == 0");
     WGS_REQUIRE(red_ok(C), "sg2_act_bwd: channel count must be a power of two in [4, 1024]");
     const size_t smem = (size_t)(RED_THREADS / (C / 4)) * C * sizeof(float);
     sg2_act_bwd_kernel<<<dim3(red_blocks(P, N), N), RED_THREADS, smem, (cudaStream_t)stream>>>(
-        da, a, demod, bias, noise, noise_w, dpre, dd, P, C);
+        da, a, demod, bias, noise, noise_w, dpre, dd, (__nv_bfloat16*)g_split, P, C);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

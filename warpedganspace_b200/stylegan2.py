@@ -251,48 +251,57 @@ def styles_and_demod(G, w):
 def synthesis(G, w, tape=None, grad_from=0):
     """w [B, style_dim] -> image NHWC [B, size, size, 3].  When `tape` is a dict, everything the
     data-gradient pass needs is recorded in it — for batch rows >= grad_from only (the un-shifted half of a
-    paired batch needs no gradient: lib/trainer.py:200 feeds G(z) with a z that has no grad)."""
+    paired batch needs no gradient: lib/trainer.py:200 feeds G(z) with a z that has no grad).
+
+    Per layer: ONE tensor-core launch (4 for an up-sampling layer + the FIR kernel) whose epilogue writes the
+    next layer's modulated split32 operand, accumulates ToRGB, and stores the fp32 activation only for the rows
+    that will be back-propagated."""
     P = G.plan()
     B = w.shape[0]
     dev = w.device
+    st = _lib.stream
     s_all, demod = styles_and_demod(G, w)
+    g0 = grad_from
     if tape is not None:
-        g0 = grad_from
-        tape.update(s_all=s_all[g0:], demod=[d[g0:] for d in demod], acts=[], rgb=[], w=w[g0:])
+        tape.update(s_all=s_all[g0:], demod=[d[g0:] for d in demod], acts=[], w=w[g0:])
+    layers = P['styled']
 
     def style_of(e):
         return s_all[:, e['s_off']: e['s_off'] + e['ci']]
 
-    def torgb(a, idx, prev):
-        r = P['rgb'][idx]
-        n, h, wd, c = a.shape
-        out = torch.empty(n, h, wd, 3, device=dev, dtype=torch.float32)
-        s = style_of(r)
-        _lib.call('wgs_sg2_torgb', _lib.ptr(a), ctypes.c_void_p(s.data_ptr()), s.stride(0), _lib.ptr(r['w']),
-                  _lib.ptr(r['bias']), _lib.ptr(prev), _lib.ptr(out), n, h, wd, c, r['scale'], _TAPS, _lib.stream())
-        return out
-
     a = P['const'].unsqueeze(0).expand(B, -1, -1, -1).contiguous()             # [B,4,4,C]
+    xs = C.pack_split32(a, scale=style_of(layers[0]), rows_per_group=16)
+    if tape is not None:
+        tape['acts'].append(a[g0:])
     skip = None
-    for li, e in enumerate(P['styled']):
-        n, h, wd, _ = a.shape
-        xs = C.pack_split32(a, scale=style_of(e), rows_per_group=h * wd)
-        if tape is not None:
-            tape['acts'].append(a[grad_from:])                                 # input activation of layer li
+    for li, e in enumerate(layers):
+        n, h, wd = xs.shape[0], xs.shape[1], xs.shape[2]
+        nxt = layers[li + 1] if li + 1 < len(layers) else None
         noise = P['noise'][li]
+        oh, ow = (2 * h, 2 * wd) if e['up'] else (h, wd)
+        a = torch.empty(n, oh, ow, e['co'], device=dev, dtype=torch.float32) if tape is not None else None
+        xs_next = torch.empty(n, oh, ow, e['co'] // 32, 64, device=dev, dtype=torch.bfloat16) if nxt else None
+        s_next = style_of(nxt) if nxt else None
         if e['up']:
             y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3)                       # [B, 2h+1, 2w+1, Co] raw
-            a = torch.empty(n, 2 * h, 2 * wd, e['co'], device=dev, dtype=torch.float32)
-            _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(a), n, 2 * h + 1, 2 * wd + 1, 2 * h, 2 * wd, e['co'], 1,
-                      _TAPS, _lib.ptr(demod[li]), _lib.ptr(e['bias']), _lib.ptr(noise), e['noise_w'], 3, _lib.stream())
+            _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(a), n, 2 * h + 1, 2 * wd + 1, oh, ow, e['co'], 1,
+                      _TAPS, _lib.ptr(demod[li]), _lib.ptr(e['bias']), _lib.ptr(noise), e['noise_w'], 3,
+                      _lib.ptr(xs_next), ctypes.c_void_p(s_next.data_ptr()), s_next.stride(0), g0, st())
         else:
-            a = C.conv2d(xs, e['w_fwd'], 3, 3, padding=1, alpha=demod[li], beta=e['bias'], noise=noise,
-                         noise_w=e['noise_w'], act=3)
-            skip = torgb(a, li // 2, skip)
-            if tape is not None:
-                tape['rgb'].append(skip[grad_from:])
-    if tape is not None:
-        tape['acts'].append(a[grad_from:])
+            r = P['rgb'][li // 2]
+            s_r = style_of(r)
+            rgb = torch.empty(n, oh, ow, 3, device=dev, dtype=torch.float32)
+            _lib.call('wgs_sg2_rgb_init', _lib.ptr(r['bias']), _lib.ptr(skip), _lib.ptr(rgb), n, oh, ow, _TAPS, st())
+            wm = torch.empty(n, 3, e['co'], device=dev, dtype=torch.float32)
+            _lib.call('wgs_sg2_rgb_weights', _lib.ptr(r['w']), ctypes.c_void_p(s_r.data_ptr()), s_r.stride(0),
+                      _lib.ptr(wm), n, e['co'], r['scale'], st())
+            C.conv2d(xs, e['w_fwd'], 3, 3, padding=1, out=a, no_f32=a is None, alpha=demod[li], beta=e['bias'],
+                     noise=noise, noise_w=e['noise_w'], act=3, out_split=xs_next, split_scale=s_next, out_from_n=g0,
+                     rgb_w=wm, rgb_out=rgb)
+            skip = rgb
+        if tape is not None:
+            tape['acts'].append(a[g0:])
+        xs = xs_next
     return skip
 
 
@@ -332,19 +341,20 @@ def synthesis_backward(G, tape, dimg):
                 _lib.call('wgs_sg2_rgb_up_bwd', _lib.ptr(drgb), _lib.ptr(dprev), n, h, wd, _TAPS, st())
                 drgb = dprev
         dd = torch.zeros(n, co, device=dev, dtype=torch.float32)
-        _lib.call('wgs_sg2_act_bwd', _lib.ptr(da), _lib.ptr(a), _lib.ptr(demod[li]), _lib.ptr(e['bias']),
-                  _lib.ptr(P['noise'][li]), e['noise_w'], _lib.ptr(da), _lib.ptr(dd), n, npix, co, st())
-        dpre = da
         if e['up']:
+            # dpre (fp32, in place) -> transposed blur * demod written straight as the split32 conv operand
+            _lib.call('wgs_sg2_act_bwd', _lib.ptr(da), _lib.ptr(a), _lib.ptr(demod[li]), _lib.ptr(e['bias']),
+                      _lib.ptr(P['noise'][li]), e['noise_w'], _lib.ptr(da), _lib.ptr(dd), None, n, npix, co, st())
             hi, wi = h // 2, wd // 2
-            dyup = torch.empty(n, h + 1, wd + 1, co, device=dev, dtype=torch.float32)
-            _lib.call('wgs_fir4_act', _lib.ptr(dpre), _lib.ptr(dyup), n, h, wd, h + 1, wd + 1, co, 2, _TAPS,
-                      _lib.ptr(demod[li]), None, None, 0.0, 0, st())
-            gs = C.pack_split32(dyup)
+            gs = torch.empty(n, h + 1, wd + 1, co // 32, 64, device=dev, dtype=torch.bfloat16)
+            _lib.call('wgs_fir4_act', _lib.ptr(da), None, n, h, wd, h + 1, wd + 1, co, 2, _TAPS,
+                      _lib.ptr(demod[li]), None, None, 0.0, 0, _lib.ptr(gs), None, 0, 0, st())
             dx = C.conv2d(gs, e['w_bwd'], 3, 3, stride=2, padding=0, cout=e['ci'])       # [n, hi, wi, ci]
             assert dx.shape[1] == hi and dx.shape[2] == wi
         else:
-            gs = C.pack_split32(dpre, scale=demod[li], rows_per_group=npix)
+            gs = torch.empty(n, h, wd, co // 32, 64, device=dev, dtype=torch.bfloat16)
+            _lib.call('wgs_sg2_act_bwd', _lib.ptr(da), _lib.ptr(a), _lib.ptr(demod[li]), _lib.ptr(e['bias']),
+                      _lib.ptr(P['noise'][li]), e['noise_w'], None, _lib.ptr(dd), _lib.ptr(gs), n, npix, co, st())
             dx = C.conv2d(gs, e['w_bwd'], 3, 3, padding=1, cout=e['ci'])
         s_e, ds_e = sl(s_all, e), sl(ds_all, e)
         pin = dx.shape[1] * dx.shape[2]
