@@ -200,7 +200,7 @@ def test_fir4_act_matches_torch(N, H, W, C, pad0, Ho, Wo):
     taps = (ctypes.c_float * 4)(0.25, 0.75, 0.75, 0.25)
     out = torch.empty(N, Ho, Wo, C, device='cuda')
     _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(out), N, H, W, Ho, Wo, C, pad0, taps, _lib.ptr(alpha), _lib.ptr(beta),
-              _lib.ptr(noise), 0.3, 3, _lib.stream())
+              _lib.ptr(noise), 0.3, 3, None, None, 0, 0, _lib.stream())
     k1 = torch.tensor([0.25, 0.75, 0.75, 0.25], device='cuda')
     k2 = torch.outer(k1, k1)
     yp = F.pad(y.permute(0, 3, 1, 2), [pad0, Wo + 3 - W - pad0, pad0, Ho + 3 - H - pad0])

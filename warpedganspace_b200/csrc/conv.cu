@@ -77,6 +77,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    float* ep = reinterpret_cast<float*>(tmem_slot + 4);     // [6][BN] per-channel epilogue constants
 
     // tile coordinates: co tile fastest so CTAs sharing an input patch are co-scheduled (L2 reuse)
     int t = blockIdx.x;
@@ -155,13 +156,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const float nz = (p.noise && valid)
             ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
             : 0.f;
+        // One image per tile (the common case): stage alpha / beta / next-layer style / ToRGB weights of this
+        // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
+        const bool cs = (p.bn == 1);
+        const int BN = p.BN;
+        if (cs) {
+            const bool n_ok = n0 < p.out_n;
+            for (int i = threadIdx.x - 64; i < BN; i += 128) {
+                const int cc = co0 + i;
+                const bool ok = n_ok && cc < p.cout;
+                ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
+                ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
+                ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
+#pragma unroll
+                for (int o = 0; o < 3; ++o)
+                    ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         ptx::mbar_wait(acc_bar, 0);
         ptx::tc_fence_after();
         const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
         const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-        for (int c = 0; c < p.BN; c += 16) {
+        for (int c = 0; c < BN; c += 16) {
             float v[16];
             ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
             const int co = co0 + c;
@@ -171,9 +190,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int cc = co + i;
                 if (cc < p.cout) {
                     float r = v[i];
-                    if (alpha) r *= __ldg(alpha + cc);
-                    r += nz;
-                    if (p.beta) r += __ldg(p.beta + cc);
+                    if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
+                    else {
+                        if (alpha) r *= __ldg(alpha + cc);
+                        r += nz;
+                        if (p.beta) r += __ldg(p.beta + cc);
+                    }
                     if (p.accumulate) r += dst[cc];
                     v[i] = apply_act(r, p.act);
                 } else {
@@ -181,21 +203,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
             if (p.rgb_w) {
-                const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
+                if (cs) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (co + i < p.cout) {
-                        rgb0 += v[i] * __ldg(wm + i);
-                        rgb1 += v[i] * __ldg(wm + p.cout + i);
-                        rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
+                    for (int i = 0; i < 16; ++i) {
+                        rgb0 += v[i] * ep[3 * BN + c + i];
+                        rgb1 += v[i] * ep[4 * BN + c + i];
+                        rgb2 += v[i] * ep[5 * BN + c + i];
+                    }
+                } else {
+                    const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (co + i < p.cout) {
+                            rgb0 += v[i] * __ldg(wm + i);
+                            rgb1 += v[i] * __ldg(wm + p.cout + i);
+                            rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
+                        }
                     }
                 }
             }
             if (p.out_split) {
                 __align__(16) __nv_bfloat16 hi[16], lo[16];
-                const float* sc = p.split_scale ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+                const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) split_bf16(sc ? v[i] * __ldg(sc + i) : v[i], hi[i], lo[i]);
+                for (int i = 0; i < 16; ++i)
+                    split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
                 __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
                                     (size_t)(co >> 5) * 64 + (co & 16);
                 reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
@@ -354,7 +386,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     else if (k_blocks <= 24) ctas_per_sm = 3;
     else if (k_blocks <= 48) ctas_per_sm = 2;
     ctas_per_sm = std::max(1, std::min(ctas_per_sm, 512 / p.tmem_cols));
-    const int smem_budget = (220 * 1024) / ctas_per_sm - 2048;
+    const int smem_budget = (220 * 1024) / ctas_per_sm - 2048 - 6 * BN * 4;
     p.stages = std::max(2, std::min(std::min(8, k_blocks), smem_budget / stage_bytes));
     const cudaStream_t st = (cudaStream_t)stream;
 
@@ -395,7 +427,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         WGS_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 6 * BN * 4 + 1024;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));

@@ -65,32 +65,48 @@ extern "C" int wgs_pack_split32(const float* src, long long rows, int C, long lo
 // stem becomes a 1-tap GEMM with K = 294 (10 chunks) instead of 49 taps x one 6/32-full chunk.
 namespace wgs {
 
+// One thread per (output pixel, 8 consecutive K entries): the (ky, kx, c) decomposition of every K index comes
+// from a per-block shared table, values are gathered with scalar loads (neighbouring K = neighbouring c / kx =
+// contiguous bytes) and written as one 16-byte hi and one 16-byte lo store.
 __global__ void __launch_bounds__(256)
 im2col_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
                       int OH, int OW, __nv_bfloat16* __restrict__ out, int chunks) {
-    const int lane = threadIdx.x & 31;
-    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long npix = (long long)N * OH * OW;
-    const int K = kh * kw * C;
-    for (long long pix = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += warps) {
+    extern __shared__ int tab[];                                 // tab[k] = (ky << 20) | (kx << 10) | c, or -1
+    const int K = kh * kw * C, Kp = chunks * 32;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        if (k < K) {
+            const int c = k % C, tap = k / C;
+            tab[k] = ((tap / kw) << 20) | ((tap % kw) << 10) | c;
+        } else {
+            tab[k] = -1;
+        }
+    }
+    __syncthreads();
+    const int groups = chunks * 4;
+    const long long total = (long long)N * OH * OW * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long long pix = i / groups;
         const int ox = (int)(pix % OW);
         const int oy = (int)((pix / OW) % OH);
         const int n = (int)(pix / ((long long)OW * OH));
         const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
-        __nv_bfloat16* dst = out + pix * chunks * 64;
-        for (int j = 0; j < chunks; ++j) {
-            const int k = j * 32 + lane;
+        const float* img = x + (size_t)n * H * W * C;
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = tab[g * 8 + j];
             float v = 0.f;
-            if (k < K) {
-                const int c = k % C, tap = k / C;
-                const int iy = iy0 + tap / kw, ix = ix0 + tap % kw;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((size_t)n * H + iy) * W + ix) * C + c);
+            if (e >= 0) {
+                const int iy = iy0 + (e >> 20), ix = ix0 + ((e >> 10) & 1023);
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((size_t)iy * W + ix) * C + (e & 1023));
             }
-            __nv_bfloat16 hi, lo;
-            split_bf16(v, hi, lo);
-            dst[j * 64 + lane] = hi;
-            dst[j * 64 + 32 + lane] = lo;
+            split_bf16(v, hi[j], lo[j]);
         }
+        __nv_bfloat16* dst = out + pix * (size_t)chunks * 64 + (size_t)(g >> 2) * 64 + (g & 3) * 8;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(dst + 32) = *reinterpret_cast<const uint4*>(lo);
     }
 }
 
@@ -100,9 +116,10 @@ extern "C" int wgs_im2col_split32(const float* x, int N, int H, int W, int C, in
                                   int OH, int OW, void* out, void* stream) {
     WGS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && OH > 0 && OW > 0, "im2col: bad sizes");
     const int chunks = (kh * kw * C + 31) / 32;
-    const long long npix = (long long)N * OH * OW;
-    const int blocks = (int)std::min<long long>((npix + 7) / 8, (long long)wgs::num_sms() * 32);
-    wgs::im2col_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW,
+    WGS_REQUIRE(kh < 1024 && kw < 1024 && C < 1024, "im2col: kernel / channel counts must be < 1024");
+    const long long total = (long long)N * OH * OW * chunks * 4;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)wgs::num_sms() * 32);
+    wgs::im2col_split32_kernel<<<blocks, 256, (size_t)chunks * 32 * sizeof(int), (cudaStream_t)stream>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW,
                                                                        (__nv_bfloat16*)out, chunks);
     wgs::count_launch();
     WGS_LAUNCH_CHECK();

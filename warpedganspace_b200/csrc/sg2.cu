@@ -70,91 +70,78 @@ __global__ void pixelnorm_rows_kernel(const float* __restrict__ x, float* __rest
 // Separable 4-tap FIR (upfirdn2d with up = down = 1, op/upfirdn2d_kernel.cu:52-137) fused with the
 // StyledConv tail: out = act(alpha[n,c] * fir(y)[Y,X,c] + noise_w * noise[Y,X] + beta[c]).
 // y: [N, Hin, Win, C] NHWC, out: [N, Hout, Wout, C]; fir(y)[Y,X] = sum_ij kf[i] kf[j] y[Y+i-pad0, X+j-pad0].
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int Hin, int Win, int Hout, int Wout,
                 int C, int pad0, float k0, float k1, float k2, float k3, const float* __restrict__ alpha,
                 const float* __restrict__ beta, const float* __restrict__ noise, float noise_w, int act,
                 __nv_bfloat16* __restrict__ out_split, const float* __restrict__ split_scale, long long split_scale_ld,
                 int out_from_n) {
-    // each thread produces a 4 (rows) x 2 (cols) patch of one channel quad: 7 x 5 float4 loads for 8 outputs
-    // (4.4 loads per output instead of 16), horizontal pass first, then the vertical combination in registers.
+    // each thread produces a 4-row strip of one channel quad: 7 x 4 float4 loads for 4 outputs (7 loads per output
+    // instead of 16); horizontal pass first, then the vertical combination in registers.
     const int c4n = C >> 2;
-    const int yb_n = (Hout + 3) >> 2, xb_n = (Wout + 1) >> 1;
-    const long long total = (long long)N * yb_n * xb_n * c4n;
+    const int yb_n = (Hout + 3) >> 2;
+    const long long total = (long long)N * yb_n * Wout * c4n;
     const float kf[4] = {k3, k2, k1, k0};                       // correlation with the flipped kernel
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4n) * 4;
         long long r = i / c4n;
-        const int X0 = (int)(r % xb_n) * 2; r /= xb_n;
+        const int X = (int)(r % Wout); r /= Wout;
         const int Y0 = (int)(r % yb_n) * 4;
         const int n = (int)(r / yb_n);
-        float4 h[7][2];
+        float4 h[7];
 #pragma unroll
         for (int a = 0; a < 7; ++a) {
             const int yy = Y0 + a - pad0;
-            float4 v[5];
-#pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                const int xx = X0 + b - pad0;
-                v[b] = (yy >= 0 && yy < Hin && xx >= 0 && xx < Win)
-                           ? __ldg(reinterpret_cast<const float4*>(y + (((size_t)n * Hin + yy) * Win + xx) * C + c))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < Hin) {
+                const float* row = y + (((size_t)n * Hin + yy) * Win) * C + c;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    t.x += kf[b] * v[b + o].x; t.y += kf[b] * v[b + o].y;
-                    t.z += kf[b] * v[b + o].z; t.w += kf[b] * v[b + o].w;
+                    const int xx = X + b - pad0;
+                    if (xx >= 0 && xx < Win) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(row + (size_t)xx * C));
+                        t.x += kf[b] * v.x; t.y += kf[b] * v.y; t.z += kf[b] * v.z; t.w += kf[b] * v.w;
+                    }
                 }
-                h[a][o] = t;
             }
+            h[a] = t;
         }
-        float al[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+        float al[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (alpha) al[k] = __ldg(alpha + (size_t)n * C + c + k);
             if (beta) be[k] = __ldg(beta + c + k);
+            if (split_scale) sc[k] = __ldg(split_scale + (size_t)n * split_scale_ld + c + k);
         }
+        const bool f32 = out && n >= out_from_n;
 #pragma unroll
         for (int oy = 0; oy < 4; ++oy) {
             const int Y = Y0 + oy;
             if (Y >= Hout) break;
+            float v4[4];
+            v4[0] = kf[0] * h[oy].x + kf[1] * h[oy + 1].x + kf[2] * h[oy + 2].x + kf[3] * h[oy + 3].x;
+            v4[1] = kf[0] * h[oy].y + kf[1] * h[oy + 1].y + kf[2] * h[oy + 2].y + kf[3] * h[oy + 3].y;
+            v4[2] = kf[0] * h[oy].z + kf[1] * h[oy + 1].z + kf[2] * h[oy + 2].z + kf[3] * h[oy + 3].z;
+            v4[3] = kf[0] * h[oy].w + kf[1] * h[oy + 1].w + kf[2] * h[oy + 2].w + kf[3] * h[oy + 3].w;
+            const float nz = noise ? noise_w * __ldg(noise + (size_t)Y * Wout + X) : 0.f;
 #pragma unroll
-            for (int ox = 0; ox < 2; ++ox) {
-                const int X = X0 + ox;
-                if (X >= Wout) continue;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 4; ++k) {
+                float t = v4[k] * al[k] + nz + be[k];
+                if (act == 3) t = 1.41421356237309515f * (t > 0.f ? t : 0.2f * t);
+                else if (act == 2) t = t > 0.f ? t : 0.2f * t;
+                else if (act == 1) t = t > 0.f ? t : 0.f;
+                v4[k] = t;
+            }
+            const size_t pix = ((size_t)n * Hout + Y) * Wout + X;
+            if (f32) *reinterpret_cast<float4*>(out + pix * C + c) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+            if (out_split) {
+                __align__(8) __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    acc.x += kf[a] * h[oy + a][ox].x; acc.y += kf[a] * h[oy + a][ox].y;
-                    acc.z += kf[a] * h[oy + a][ox].z; acc.w += kf[a] * h[oy + a][ox].w;
-                }
-                float v4[4] = {acc.x, acc.y, acc.z, acc.w};
-                const float nz = noise ? noise_w * __ldg(noise + (size_t)Y * Wout + X) : 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float t = v4[k] * al[k] + nz + be[k];
-                    if (act == 3) t = 1.41421356237309515f * (t > 0.f ? t : 0.2f * t);
-                    else if (act == 2) t = t > 0.f ? t : 0.2f * t;
-                    else if (act == 1) t = t > 0.f ? t : 0.f;
-                    v4[k] = t;
-                }
-                const size_t pix = ((size_t)n * Hout + Y) * Wout + X;
-                if (out && n >= out_from_n)
-                    *reinterpret_cast<float4*>(out + pix * C + c) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-                if (out_split) {
-                    __align__(8) __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        split_bf16(split_scale ? v4[k] * __ldg(split_scale + (size_t)n * split_scale_ld + c + k) : v4[k],
-                                   hi[k], lo[k]);
-                    __nv_bfloat16* sp = out_split + pix * (size_t)(((C + 31) >> 5) * 64) + (size_t)(c >> 5) * 64 + (c & 31);
-                    *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
-                    *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
-                }
+                for (int k = 0; k < 4; ++k) split_bf16(v4[k] * sc[k], hi[k], lo[k]);
+                __nv_bfloat16* sp = out_split + pix * (size_t)(((C + 31) >> 5) * 64) + (size_t)(c >> 5) * 64 + (c & 31);
+                *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+                *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
             }
         }
     }
@@ -314,8 +301,8 @@ extern "C" int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win,
                             int out_from_n, void* stream) {
     WGS_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "fir4_act: channels must be a multiple of 4");
     WGS_REQUIRE(taps4 != nullptr, "fir4_act: taps4 is a HOST pointer to 4 floats");
-    const long long total = (long long)N * ((Hout + 3) / 4) * ((Wout + 1) / 2) * (C / 4);
-    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 32);
+    const long long total = (long long)N * ((Hout + 3) / 4) * Wout * (C / 4);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 48);
     fir4_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1],
                                                               taps4[2], taps4[3], alpha, beta, noise, noise_w, act,
                                                               (__nv_bfloat16*)out_split, split_scale, split_scale_ld, out_from_n);

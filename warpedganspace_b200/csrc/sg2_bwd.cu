@@ -178,7 +178,7 @@ __global__ void rgb_up_bwd_kernel(const float* __restrict__ drgb, float* __restr
 }
 
 static int red_blocks(long long P, int N) {
-    const long long want = std::max<long long>(1, ((long long)num_sms() * 4) / std::max(1, N));
+    const long long want = std::max<long long>(1, ((long long)num_sms() * 16) / std::max(1, N));
     return (int)std::max<long long>(1, std::min<long long>(want, (P + 31) / 32));
 }
 
