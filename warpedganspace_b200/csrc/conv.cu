@@ -53,6 +53,9 @@ struct ConvKernelParams {
     int out_from_n;              // fp32 `out` is written only for images n >= out_from_n
     const float* rgb_w;          // [out_n][3][cout] modulated ToRGB weights; rgb_out += act . rgb_w
     float* rgb_out;              // [out_n][grid_h][grid_w][3], pre-initialised with bias + upsampled skip
+    // halo variant: the (bh + wy - 1) x (bw + wx - 1) input patch of a chunk is loaded once and every tap
+    // addresses it through its UMMA descriptor
+    int dy0, dx0, halo_h, halo_w, pitch, a_stage_bytes, a_stages, b_stages, desc_base_offset;
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -62,6 +65,118 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 2) return v > 0.f ? v : 0.2f * v;
     if (act == 3) return 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);      // FusedLeakyReLU
     return v;
+}
+
+// Epilogue shared by the tensor-core conv kernels: TMEM accumulator -> demod / noise / bias / activation ->
+// fp32 NHWC store, split32 operand of the next layer, fused ToRGB.  Executed by four warps whose (warp % 4)
+// selects the 32 TMEM lanes they may read; `first_thread` is threadIdx.x of the first epilogue thread.
+__device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep,
+                                              uint64_t* acc_bar, int warp, int lane, int n0, int oy0, int ox0,
+                                              int co0, int first_thread) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
+    const int n = n0 + nl, oy = oy0 + yl, ox = ox0 + xl;
+    const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
+    float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
+                 (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
+    const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
+    const float nz = (p.noise && valid)
+        ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
+        : 0.f;
+    // One image per tile (the common case): stage alpha / beta / next-layer style / ToRGB weights of this
+    // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
+    const bool cs = (p.bn == 1);
+    const int BN = p.BN;
+    if (cs) {
+        const bool n_ok = n0 < p.out_n;
+        for (int i = threadIdx.x - first_thread; i < BN; i += 128) {
+            const int cc = co0 + i;
+            const bool ok = n_ok && cc < p.cout;
+            ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
+            ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
+            ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+                ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    ptx::mbar_wait(acc_bar, 0);
+    ptx::tc_fence_after();
+    const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
+    float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+    for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        const int co = co0 + c;
+        if (!valid || co >= p.cout) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int cc = co + i;
+            if (cc < p.cout) {
+                float r = v[i];
+                if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
+                else {
+                    if (alpha) r *= __ldg(alpha + cc);
+                    r += nz;
+                    if (p.beta) r += __ldg(p.beta + cc);
+                }
+                if (p.accumulate) r += dst[cc];
+                v[i] = apply_act(r, p.act);
+            } else {
+                v[i] = 0.f;
+            }
+        }
+        if (p.rgb_w) {
+            if (cs) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    rgb0 += v[i] * ep[3 * BN + c + i];
+                    rgb1 += v[i] * ep[4 * BN + c + i];
+                    rgb2 += v[i] * ep[5 * BN + c + i];
+                }
+            } else {
+                const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (co + i < p.cout) {
+                        rgb0 += v[i] * __ldg(wm + i);
+                        rgb1 += v[i] * __ldg(wm + p.cout + i);
+                        rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
+                    }
+                }
+            }
+        }
+        if (p.out_split) {
+            __align__(16) __nv_bfloat16 hi[16], lo[16];
+            const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
+            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
+                                (size_t)(co >> 5) * 64 + (co & 16);
+            reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
+            reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
+            reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
+            reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
+        }
+        if (write_f32) {
+            if (vec_ok && co + 16 <= p.cout) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+                for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+            }
+        }
+    }
+    if (p.rgb_out && valid) {
+        float* ro = p.rgb_out + pix * 3;
+        atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
+    }
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 4)
@@ -144,111 +259,134 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mma_commit(acc_bar);                         // accumulator complete
         }
     } else {
-        // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
-        const int n = n0 + nl, oy = oy0 + yl, ox = ox0 + xl;
-        const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
-        float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
-                     (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
-        const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
-        const float nz = (p.noise && valid)
-            ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
-            : 0.f;
-        // One image per tile (the common case): stage alpha / beta / next-layer style / ToRGB weights of this
-        // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
-        const bool cs = (p.bn == 1);
-        const int BN = p.BN;
-        if (cs) {
-            const bool n_ok = n0 < p.out_n;
-            for (int i = threadIdx.x - 64; i < BN; i += 128) {
-                const int cc = co0 + i;
-                const bool ok = n_ok && cc < p.cout;
-                ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
-                ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
-                ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
-#pragma unroll
-                for (int o = 0; o < 3; ++o)
-                    ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
+        conv_epilogue(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, 64);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Halo variant for stride-1 tap lists on low-channel / high-resolution layers (L2-fabric bound in the kernel
+// above, where every tap re-fetches its shifted 128-pixel patch: 11-13x the input size crosses L2->SM,
+// profiles/r01_conv_tc_ncu_full.md).  Tile = 16 rows x 8 columns of output pixels.  Per 32-channel chunk ONE
+// TMA box brings the (16 + wy - 1) x (8 + wx - 1) input patch; the A operand of tap (ty, tx) is that same
+// buffer viewed through a descriptor whose start address is advanced by (ty * pitch + tx) rows and whose
+// stride-byte-offset is the patch row pitch: the eight pixels of one output row are eight consecutive
+// 128-byte rows (one swizzle-atom group), successive output rows are `pitch` rows apart.  The 128B swizzle is
+// a function of the absolute shared-memory address for both the TMA write and the UMMA read, so shifted views
+// stay consistent.  Weights stream through their own ring (one tap slice per stage).
+//   warp 0: patch producer   warp 1: MMA issuer + TMEM   warps 2-5: epilogue   warp 6: weight producer
+constexpr int HALO_THREADS = 224;
+
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)(base_offset & 7u) << 49) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(HALO_THREADS, 3)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ ConvKernelParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_stage_bytes = p.BN * 128;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_stage_bytes);
+    uint64_t* a_empty = a_full + p.a_stages;
+    uint64_t* b_full = a_empty + p.a_stages;
+    uint64_t* b_empty = b_full + p.b_stages;
+    uint64_t* acc_bar = b_empty + p.b_stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    float* ep = reinterpret_cast<float*>(tmem_slot + 4);
+
+    int t = blockIdx.x;
+    const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    const int n0 = t;
+    const int ox0 = tx * p.bw, oy0 = ty * p.bh, co0 = co_tile * p.BN;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full + s, 1); ptx::mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full + s, 1); ptx::mbar_init(b_empty + s, 1); }
+        ptx::mbar_init(acc_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)(p.halo_h * p.pitch * 128);
+            for (int ch = 0; ch < p.c_chunks; ++ch) {
+                ptx::mbar_wait(a_empty + stage, phase ^ 1);
+                ptx::mbar_expect_tx(a_full + stage, bytes);
+                ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_a, a_full + stage, 0, ch, ox0 + p.dx0,
+                                 oy0 + p.dy0, n0);
+                if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        ptx::mbar_wait(acc_bar, 0);
-        ptx::tc_fence_after();
-        const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
-        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-        for (int c = 0; c < BN; c += 16) {
-            float v[16];
-            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            const int co = co0 + c;
-            if (!valid || co >= p.cout) continue;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int cc = co + i;
-                if (cc < p.cout) {
-                    float r = v[i];
-                    if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
-                    else {
-                        if (alpha) r *= __ldg(alpha + cc);
-                        r += nz;
-                        if (p.beta) r += __ldg(p.beta + cc);
-                    }
-                    if (p.accumulate) r += dst[cc];
-                    v[i] = apply_act(r, p.act);
-                } else {
-                    v[i] = 0.f;
-                }
-            }
-            if (p.rgb_w) {
-                if (cs) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        rgb0 += v[i] * ep[3 * BN + c + i];
-                        rgb1 += v[i] * ep[4 * BN + c + i];
-                        rgb2 += v[i] * ep[5 * BN + c + i];
-                    }
-                } else {
-                    const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (co + i < p.cout) {
-                            rgb0 += v[i] * __ldg(wm + i);
-                            rgb1 += v[i] * __ldg(wm + p.cout + i);
-                            rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
-                        }
-                    }
-                }
-            }
-            if (p.out_split) {
-                __align__(16) __nv_bfloat16 hi[16], lo[16];
-                const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
-                __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
-                                    (size_t)(co >> 5) * 64 + (co & 16);
-                reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
-                reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
-                reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
-                reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
-            }
-            if (write_f32) {
-                if (vec_ok && co + 16 <= p.cout) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                } else {
-                    for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+    } else if (warp == 6) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = 0; ch < p.c_chunks; ++ch) {
+                for (int tap = 0; tap < p.num_taps; ++tap) {
+                    ptx::mbar_wait(b_empty + stage, phase ^ 1);
+                    ptx::mbar_expect_tx(b_full + stage, (uint32_t)b_stage_bytes);
+                    ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, b_full + stage, 0, ch, co0,
+                                     (int)p.tap_w[tap]);
+                    if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-        if (p.rgb_out && valid) {
-            float* ro = p.rgb_out + pix * 3;
-            atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
+            const uint32_t sbo = (uint32_t)p.pitch * 128u;
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0, accum = 0;
+            for (int ch = 0; ch < p.c_chunks; ++ch) {
+                ptx::mbar_wait(a_full + as, aph);
+                const uint32_t a_base = ptx::smem_u32(smem_a + (size_t)as * p.a_stage_bytes);
+                for (int tap = 0; tap < p.num_taps; ++tap) {
+                    ptx::mbar_wait(b_full + bs, bph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr =
+                        a_base + (uint32_t)((p.tap_dy[tap] - p.dy0) * p.pitch + (p.tap_dx[tap] - p.dx0)) * 128u;
+                    const uint32_t bo = p.desc_base_offset ? ((a_addr >> 7) & 7u) : 0u;
+                    const uint64_t da = umma_desc_k_sw128(a_addr, sbo, bo);
+                    const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + (size_t)bs * b_stage_bytes));
+                    ptx::mma_f16(tmem_base, da + 0, db + 0, idesc, accum);              // hi*hi
+                    accum = 1u;
+                    ptx::mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
+                    ptx::mma_f16(tmem_base, da + 0, db + 4, idesc, 1u);                 // hi*lo
+                    ptx::mma_f16(tmem_base, da + 2, db + 6, idesc, 1u);
+                    ptx::mma_f16(tmem_base, da + 4, db + 0, idesc, 1u);                 // lo*hi
+                    ptx::mma_f16(tmem_base, da + 6, db + 2, idesc, 1u);
+                    ptx::mma_commit(b_empty + bs);
+                    if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                }
+                ptx::mma_commit(a_empty + as);
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            }
+            ptx::mma_commit(acc_bar);
         }
+    } else {
+        conv_epilogue(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, 64);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -402,6 +540,79 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
 
     auto encode = get_encode();
     WGS_REQUIRE(encode != nullptr, "conv: cuTensorMapEncodeTiled entry point not available");
+
+    // ---- halo variant ---------------------------------------------------------------------------------
+    {
+        int dy0 = 127, dy1 = -127, dx0 = 127, dx1 = -127;
+        for (int i = 0; i < d->num_taps; ++i) {
+            dy0 = std::min(dy0, d->tap_dy[i]); dy1 = std::max(dy1, d->tap_dy[i]);
+            dx0 = std::min(dx0, d->tap_dx[i]); dx1 = std::max(dx1, d->tap_dx[i]);
+        }
+        const int wy = dy1 - dy0 + 1, wx = dx1 - dx0 + 1;
+        static int halo_mode = -1, halo_pitch16 = 0, halo_bo = 0;
+        if (halo_mode < 0) {
+            const char* e = getenv("WGS_CONV_HALO");           // 0 = off, 1 = on (default)
+            halo_mode = (e && e[0] == '0') ? 0 : 1;
+            const char* e2 = getenv("WGS_CONV_HALO_PITCH16");
+            halo_pitch16 = (e2 && e2[0] == '1') ? 1 : 0;
+            const char* e3 = getenv("WGS_CONV_HALO_BASE_OFFSET");
+            halo_bo = (e3 && e3[0] == '1') ? 1 : 0;
+        }
+        const bool eligible = halo_mode && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
+                              d->grid_h >= 16 && d->grid_w >= 8 && d->c_chunks <= 8 && d->force_bn == 0;
+        if (eligible) {
+            p.bw = 8; p.bh = 16; p.bn = 1;
+            p.tiles_x = ceil_div(d->grid_w, 8); p.tiles_y = ceil_div(d->grid_h, 16); p.tiles_n = d->out_n;
+            p.dy0 = dy0; p.dx0 = dx0;
+            p.halo_h = 16 + wy - 1; p.halo_w = 8 + wx - 1;
+            p.pitch = halo_pitch16 ? 16 : p.halo_w;
+            p.desc_base_offset = halo_bo;
+            int hBN = std::min(128, (d->cout + 15) / 16 * 16);
+            p.BN = hBN;
+            p.n_tiles_co = ceil_div(d->cout, hBN);
+            p.tmem_cols = std::max(32, next_pow2(hBN));
+            p.a_stage_bytes = (p.halo_h * p.pitch * 128 + 1023) / 1024 * 1024;
+            p.a_stages = std::min(2, d->c_chunks);
+            p.b_stages = std::max(2, std::min(6, d->num_taps * d->c_chunks));
+            alignas(64) CUtensorMap ta, tb;
+            {
+                const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
+                                            (cuuint64_t)d->in_n};
+                const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->in_w, s4 = s3 * d->in_h;
+                const cuuint64_t strides[4] = {s1, s2, s3, s4};
+                const cuuint32_t box[5] = {64, 1, (cuuint32_t)p.pitch, (cuuint32_t)p.halo_h, 1};
+                const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->in), dims, strides, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(input) failed with code " + std::to_string((int)r));
+            }
+            {
+                const cuuint64_t dims[4] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_cout, (cuuint64_t)d->w_taps};
+                const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->w_cout;
+                const cuuint64_t strides[3] = {s1, s2, s3};
+                const cuuint32_t box[4] = {64, 1, (cuuint32_t)hBN, 1};
+                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->w), dims, strides, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
+            }
+            const size_t hsmem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * hBN * 128 +
+                                 (2 * p.a_stages + 2 * p.b_stages + 1) * 8 + 16 + 6 * hBN * 4 + 1024;
+            static bool attr = false;
+            if (!attr) {
+                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                attr = true;
+            }
+            const int hgrid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
+            conv_halo_kernel<<<hgrid, HALO_THREADS, hsmem, st>>>(ta, tb, p);
+            count_launch();
+            WGS_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+
     alignas(64) CUtensorMap tmap_a, tmap_b;
     {
         const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
