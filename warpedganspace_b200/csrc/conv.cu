@@ -56,6 +56,7 @@ struct ConvKernelParams {
     // halo variant: the (bh + wy - 1) x (bw + wx - 1) input patch of a chunk is loaded once and every tap
     // addresses it through its UMMA descriptor
     int dy0, dx0, halo_h, halo_w, pitch, a_stage_bytes, a_stages, b_stages, desc_base_offset;
+    int w_resident, total_tiles;
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -72,7 +73,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // selects the 32 TMEM lanes they may read; `first_thread` is threadIdx.x of the first epilogue thread.
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep,
                                               uint64_t* acc_bar, int warp, int lane, int n0, int oy0, int ox0,
-                                              int co0, int first_thread) {
+                                              int co0, int first_thread, uint32_t acc_parity = 0,
+                                              bool persistent = false) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
@@ -90,6 +92,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     const int BN = p.BN;
     if (cs) {
         const bool n_ok = n0 < p.out_n;
+        if (persistent) asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers of `ep` are done
         for (int i = threadIdx.x - first_thread; i < BN; i += 128) {
             const int cc = co0 + i;
             const bool ok = n_ok && cc < p.cout;
@@ -102,7 +105,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    ptx::mbar_wait(acc_bar, 0);
+    ptx::mbar_wait(acc_bar, acc_parity);
     ptx::tc_fence_after();
     const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
@@ -288,36 +291,36 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32
            ((uint64_t)(base_offset & 7u) << 49) | ((uint64_t)2 << 61);
 }
 
-__global__ void __launch_bounds__(HALO_THREADS, 3)
+// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (gridDim.x is a multiple of the number of
+// output-channel tiles, so a CTA keeps its channel slice and, when they fit, its weights stay resident in shared
+// memory for the whole kernel).  Two TMEM accumulators let the epilogue of tile i overlap the loads and MMAs of
+// tile i+1.
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_stage_bytes = p.BN * 128;
+    const int k_slices = p.c_chunks * p.num_taps;                         // weight slices per tile
+    const int b_slots = p.w_resident ? k_slices : p.b_stages;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_stage_bytes);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)b_slots * b_stage_bytes);
     uint64_t* a_empty = a_full + p.a_stages;
-    uint64_t* b_full = a_empty + p.a_stages;
+    uint64_t* b_full = a_empty + p.a_stages;                              // [b_stages] (or [1] when resident)
     uint64_t* b_empty = b_full + p.b_stages;
-    uint64_t* acc_bar = b_empty + p.b_stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    uint64_t* acc_full = b_empty + p.b_stages;                            // [2]
+    uint64_t* acc_empty = acc_full + 2;                                   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* ep = reinterpret_cast<float*>(tmem_slot + 4);
-
-    int t = blockIdx.x;
-    const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;
-    const int tx = t % p.tiles_x; t /= p.tiles_x;
-    const int ty = t % p.tiles_y; t /= p.tiles_y;
-    const int n0 = t;
-    const int ox0 = tx * p.bw, oy0 = ty * p.bh, co0 = co_tile * p.BN;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
         for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full + s, 1); ptx::mbar_init(a_empty + s, 1); }
         for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full + s, 1); ptx::mbar_init(b_empty + s, 1); }
-        ptx::mbar_init(acc_bar, 1);
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(acc_full + s, 1); ptx::mbar_init(acc_empty + s, 128); }
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -325,68 +328,115 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int co0 = (int)(blockIdx.x % p.n_tiles_co) * p.BN;
+
+    auto decode = [&](int tile, int& n0, int& oy0, int& ox0) {
+        int t = tile / p.n_tiles_co;
+        ox0 = (t % p.tiles_x) * p.bw; t /= p.tiles_x;
+        oy0 = (t % p.tiles_y) * p.bh; t /= p.tiles_y;
+        n0 = t;
+    };
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(p.halo_h * p.pitch * 128);
-            for (int ch = 0; ch < p.c_chunks; ++ch) {
-                ptx::mbar_wait(a_empty + stage, phase ^ 1);
-                ptx::mbar_expect_tx(a_full + stage, bytes);
-                ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_a, a_full + stage, 0, ch, ox0 + p.dx0,
-                                 oy0 + p.dy0, n0);
-                if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int n0, oy0, ox0;
+                decode(tile, n0, oy0, ox0);
+                for (int ch = 0; ch < p.c_chunks; ++ch) {
+                    ptx::mbar_wait(a_empty + stage, phase ^ 1);
+                    ptx::mbar_expect_tx(a_full + stage, bytes);
+                    ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_a, a_full + stage, 0, ch,
+                                     ox0 + p.dx0, oy0 + p.dy0, n0);
+                    if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 6) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int ch = 0; ch < p.c_chunks; ++ch) {
-                for (int tap = 0; tap < p.num_taps; ++tap) {
-                    ptx::mbar_wait(b_empty + stage, phase ^ 1);
-                    ptx::mbar_expect_tx(b_full + stage, (uint32_t)b_stage_bytes);
-                    ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, b_full + stage, 0, ch, co0,
-                                     (int)p.tap_w[tap]);
-                    if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
-                }
+            if (p.w_resident) {
+                // all weight slices of this CTA's channel tile, once
+                ptx::mbar_expect_tx(b_full, (uint32_t)(k_slices * b_stage_bytes));
+                for (int ch = 0; ch < p.c_chunks; ++ch)
+                    for (int tap = 0; tap < p.num_taps; ++tap)
+                        ptx::tma_load_4d(smem_b + (size_t)(ch * p.num_taps + tap) * b_stage_bytes, &tmap_b, b_full, 0, ch,
+                                         co0, (int)p.tap_w[tap]);
+            } else {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+                    for (int ch = 0; ch < p.c_chunks; ++ch)
+                        for (int tap = 0; tap < p.num_taps; ++tap) {
+                            ptx::mbar_wait(b_empty + stage, phase ^ 1);
+                            ptx::mbar_expect_tx(b_full + stage, (uint32_t)b_stage_bytes);
+                            ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, b_full + stage, 0, ch, co0,
+                                             (int)p.tap_w[tap]);
+                            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+                        }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
             const uint32_t sbo = (uint32_t)p.pitch * 128u;
-            int as = 0, bs = 0;
-            uint32_t aph = 0, bph = 0, accum = 0;
-            for (int ch = 0; ch < p.c_chunks; ++ch) {
-                ptx::mbar_wait(a_full + as, aph);
-                const uint32_t a_base = ptx::smem_u32(smem_a + (size_t)as * p.a_stage_bytes);
-                for (int tap = 0; tap < p.num_taps; ++tap) {
-                    ptx::mbar_wait(b_full + bs, bph);
+            int as = 0, bs = 0, it = 0;
+            uint32_t aph = 0, bph = 0;
+            if (p.w_resident) ptx::mbar_wait(b_full, 0);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                ptx::mbar_wait(acc_empty + buf, (((uint32_t)it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+                uint32_t accum = 0;
+                for (int ch = 0; ch < p.c_chunks; ++ch) {
+                    ptx::mbar_wait(a_full + as, aph);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr =
-                        a_base + (uint32_t)((p.tap_dy[tap] - p.dy0) * p.pitch + (p.tap_dx[tap] - p.dx0)) * 128u;
-                    const uint32_t bo = p.desc_base_offset ? ((a_addr >> 7) & 7u) : 0u;
-                    const uint64_t da = umma_desc_k_sw128(a_addr, sbo, bo);
-                    const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + (size_t)bs * b_stage_bytes));
-                    ptx::mma_f16(tmem_base, da + 0, db + 0, idesc, accum);              // hi*hi
-                    accum = 1u;
-                    ptx::mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
-                    ptx::mma_f16(tmem_base, da + 0, db + 4, idesc, 1u);                 // hi*lo
-                    ptx::mma_f16(tmem_base, da + 2, db + 6, idesc, 1u);
-                    ptx::mma_f16(tmem_base, da + 4, db + 0, idesc, 1u);                 // lo*hi
-                    ptx::mma_f16(tmem_base, da + 6, db + 2, idesc, 1u);
-                    ptx::mma_commit(b_empty + bs);
-                    if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                    const uint32_t a_base = ptx::smem_u32(smem_a + (size_t)as * p.a_stage_bytes);
+                    for (int tap = 0; tap < p.num_taps; ++tap) {
+                        uint32_t b_addr;
+                        if (p.w_resident) {
+                            b_addr = ptx::smem_u32(smem_b + (size_t)(ch * p.num_taps + tap) * b_stage_bytes);
+                        } else {
+                            ptx::mbar_wait(b_full + bs, bph);
+                            ptx::tc_fence_after();
+                            b_addr = ptx::smem_u32(smem_b + (size_t)bs * b_stage_bytes);
+                        }
+                        const uint32_t a_addr =
+                            a_base + (uint32_t)((p.tap_dy[tap] - p.dy0) * p.pitch + (p.tap_dx[tap] - p.dx0)) * 128u;
+                        const uint32_t bo = p.desc_base_offset ? ((a_addr >> 7) & 7u) : 0u;
+                        const uint64_t da = umma_desc_k_sw128(a_addr, sbo, bo);
+                        const uint64_t db = ptx::umma_desc_sw128(b_addr);
+                        ptx::mma_f16(d_tmem, da + 0, db + 0, idesc, accum);              // hi*hi
+                        accum = 1u;
+                        ptx::mma_f16(d_tmem, da + 2, db + 2, idesc, 1u);
+                        ptx::mma_f16(d_tmem, da + 0, db + 4, idesc, 1u);                 // hi*lo
+                        ptx::mma_f16(d_tmem, da + 2, db + 6, idesc, 1u);
+                        ptx::mma_f16(d_tmem, da + 4, db + 0, idesc, 1u);                 // lo*hi
+                        ptx::mma_f16(d_tmem, da + 6, db + 2, idesc, 1u);
+                        if (!p.w_resident) {
+                            ptx::mma_commit(b_empty + bs);
+                            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                    ptx::mma_commit(a_empty + as);
+                    if (++as == p.a_stages) { as = 0; aph ^= 1; }
                 }
-                ptx::mma_commit(a_empty + as);
-                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                ptx::mma_commit(acc_full + buf);
             }
-            ptx::mma_commit(acc_bar);
         }
     } else {
-        conv_epilogue(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, 64);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int n0, oy0, ox0;
+            decode(tile, n0, oy0, ox0);
+            const int buf = it & 1;
+            conv_epilogue(p, tmem_base + (uint32_t)(buf * p.BN), ep, acc_full + buf, warp, lane, n0, oy0, ox0, co0, 64,
+                          ((uint32_t)it >> 1) & 1u, true);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(acc_empty + buf);                 // 128 arrivals free the accumulator
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -559,7 +609,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             halo_bo = (e3 && e3[0] == '1') ? 1 : 0;
         }
         const bool eligible = halo_mode && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
-                              d->grid_h >= 16 && d->grid_w >= 8 && d->c_chunks <= 8 && d->force_bn == 0;
+                              d->grid_h >= 16 && d->grid_w >= 8 && d->c_chunks <= 2 && d->force_bn == 0;
         if (eligible) {
             p.bw = 8; p.bh = 16; p.bn = 1;
             p.tiles_x = ceil_div(d->grid_w, 8); p.tiles_y = ceil_div(d->grid_h, 16); p.tiles_n = d->out_n;
@@ -568,12 +618,20 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             p.pitch = halo_pitch16 ? 16 : p.halo_w;
             p.desc_base_offset = halo_bo;
             int hBN = std::min(128, (d->cout + 15) / 16 * 16);
+            // prefer a channel tile whose weights (all taps x chunks) stay resident in shared memory
+            while (hBN > 32 && hBN % 32 == 0 && d->num_taps * d->c_chunks * hBN * 128 > 80 * 1024) hBN /= 2;
             p.BN = hBN;
             p.n_tiles_co = ceil_div(d->cout, hBN);
-            p.tmem_cols = std::max(32, next_pow2(hBN));
             p.a_stage_bytes = (p.halo_h * p.pitch * 128 + 1023) / 1024 * 1024;
-            p.a_stages = std::min(2, d->c_chunks);
-            p.b_stages = std::max(2, std::min(6, d->num_taps * d->c_chunks));
+            const int k_slices = d->num_taps * d->c_chunks;
+            const int w_bytes = k_slices * hBN * 128;
+            p.w_resident = (w_bytes <= 80 * 1024) ? 1 : 0;
+            p.b_stages = p.w_resident ? 1 : std::max(2, std::min(8, k_slices));
+            const int b_bytes = p.w_resident ? w_bytes : p.b_stages * hBN * 128;
+            p.tmem_cols = std::max(32, next_pow2(2 * hBN));
+            const int fixed = b_bytes + (2 * 8 + 2 * p.b_stages + 4) * 8 + 16 + 6 * hBN * 4 + 2048;
+            p.a_stages = std::max(1, std::min(6, (200 * 1024 - fixed) / p.a_stage_bytes));
+            p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
             alignas(64) CUtensorMap ta, tb;
             {
                 const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
@@ -598,14 +656,15 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
             }
-            const size_t hsmem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * hBN * 128 +
-                                 (2 * p.a_stages + 2 * p.b_stages + 1) * 8 + 16 + 6 * hBN * 4 + 1024;
+            const size_t hsmem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)b_bytes +
+                                 (2 * p.a_stages + 2 * p.b_stages + 4) * 8 + 16 + 6 * hBN * 4 + 1024;
             static bool attr = false;
             if (!attr) {
                 WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
                 attr = true;
             }
-            const int hgrid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
+            int hgrid = std::min(p.total_tiles, num_sms());
+            hgrid = std::max(p.n_tiles_co, hgrid / p.n_tiles_co * p.n_tiles_co);     // a CTA keeps its channel tile
             conv_halo_kernel<<<hgrid, HALO_THREADS, hsmem, st>>>(ta, tb, p);
             count_launch();
             WGS_LAUNCH_CHECK();
