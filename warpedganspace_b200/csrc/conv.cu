@@ -74,7 +74,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep,
                                               uint64_t* acc_bar, int warp, int lane, int n0, int oy0, int ox0,
                                               int co0, int first_thread, uint32_t acc_parity = 0,
-                                              bool persistent = false) {
+                                              bool persistent = false, int bar_id = 1) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
@@ -92,7 +92,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     const int BN = p.BN;
     if (cs) {
         const bool n_ok = n0 < p.out_n;
-        if (persistent) asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers of `ep` are done
+        if (persistent) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // previous tile's readers of `ep` are done
         for (int i = threadIdx.x - first_thread; i < BN; i += 128) {
             const int cc = co0 + i;
             const bool ok = n_ok && cc < p.cout;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
             for (int o = 0; o < 3; ++o)
                 ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     }
     ptx::mbar_wait(acc_bar, acc_parity);
     ptx::tc_fence_after();
@@ -284,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // a function of the absolute shared-memory address for both the TMA write and the UMMA read, so shifted views
 // stay consistent.  Weights stream through their own ring (one tap slice per stage).
 //   warp 0: patch producer   warp 1: MMA issuer + TMEM   warps 2-5: epilogue   warp 6: weight producer
-constexpr int HALO_THREADS = 224;
+constexpr int HALO_THREADS = 352;
 
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
@@ -293,8 +293,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32
 
 // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (gridDim.x is a multiple of the number of
 // output-channel tiles, so a CTA keeps its channel slice and, when they fit, its weights stay resident in shared
-// memory for the whole kernel).  Two TMEM accumulators let the epilogue of tile i overlap the loads and MMAs of
-// tile i+1.
+// memory for the whole kernel).  Two TMEM accumulators and two epilogue warpgroups: the epilogue of tile i overlaps
+// the loads and MMAs of tiles i+1, i+2.  The MMA warp runs warp-uniform (descriptor arithmetic stays in uniform
+// registers) and only the elected lane issues tcgen05.mma / commit — with N = 32..64 an MMA is 16-32 tensor cycles,
+// so the issue path, not the tensor pipe, is what has to be short (profiles/r01_conv_halo_ncu.md).
+//   warp 0: patch producer  warp 1: MMA  warps 2-5: epilogue group 0  warp 6: weight producer  warps 7-10: group 1
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ ConvKernelParams p) {
@@ -313,7 +316,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* acc_full = b_empty + p.b_stages;                            // [2]
     uint64_t* acc_empty = acc_full + 2;                                   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* ep = reinterpret_cast<float*>(tmem_slot + 4);
+    uint32_t* tap_off = tmem_slot + 4;                                    // [WGS_MAX_TAPS] descriptor offsets (>>4)
+    float* ep = reinterpret_cast<float*>(tap_off + WGS_MAX_TAPS);         // [2][6][BN]
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -323,6 +327,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(acc_full + s, 1); ptx::mbar_init(acc_empty + s, 128); }
         ptx::fence_mbar_init();
     }
+    if (threadIdx.x < p.num_taps)
+        tap_off[threadIdx.x] =
+            (uint32_t)(((p.tap_dy[threadIdx.x] - p.dy0) * p.pitch + (p.tap_dx[threadIdx.x] - p.dx0)) * 128) >> 4;
     if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tc_fence_before();
     __syncthreads();
@@ -378,64 +385,71 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
-            const uint32_t sbo = (uint32_t)p.pitch * 128u;
-            int as = 0, bs = 0, it = 0;
-            uint32_t aph = 0, bph = 0;
-            if (p.w_resident) ptx::mbar_wait(b_full, 0);
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                ptx::mbar_wait(acc_empty + buf, (((uint32_t)it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+        // whole warp, uniform control flow; one elected lane issues
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
+        const uint64_t a_proto = umma_desc_k_sw128(0, (uint32_t)p.pitch * 128u, 0);
+        const uint64_t b_proto = ptx::umma_desc_sw128(0);
+        const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+        const uint32_t a_lo0 = (ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4;
+        const uint32_t b_lo0 = (ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4;
+        const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)b_stage_bytes >> 4;
+        int as = 0, bs = 0, it = 0;
+        uint32_t aph = 0, bph = 0;
+        if (p.w_resident) ptx::mbar_wait(b_full, 0);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            ptx::mbar_wait(acc_empty + buf, (((uint32_t)it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+            uint32_t accum = 0;
+            for (int ch = 0; ch < p.c_chunks; ++ch) {
+                ptx::mbar_wait(a_full + as, aph);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
-                uint32_t accum = 0;
-                for (int ch = 0; ch < p.c_chunks; ++ch) {
-                    ptx::mbar_wait(a_full + as, aph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_base = ptx::smem_u32(smem_a + (size_t)as * p.a_stage_bytes);
-                    for (int tap = 0; tap < p.num_taps; ++tap) {
-                        uint32_t b_addr;
-                        if (p.w_resident) {
-                            b_addr = ptx::smem_u32(smem_b + (size_t)(ch * p.num_taps + tap) * b_stage_bytes);
-                        } else {
-                            ptx::mbar_wait(b_full + bs, bph);
-                            ptx::tc_fence_after();
-                            b_addr = ptx::smem_u32(smem_b + (size_t)bs * b_stage_bytes);
-                        }
-                        const uint32_t a_addr =
-                            a_base + (uint32_t)((p.tap_dy[tap] - p.dy0) * p.pitch + (p.tap_dx[tap] - p.dx0)) * 128u;
-                        const uint32_t bo = p.desc_base_offset ? ((a_addr >> 7) & 7u) : 0u;
-                        const uint64_t da = umma_desc_k_sw128(a_addr, sbo, bo);
-                        const uint64_t db = ptx::umma_desc_sw128(b_addr);
-                        ptx::mma_f16(d_tmem, da + 0, db + 0, idesc, accum);              // hi*hi
-                        accum = 1u;
-                        ptx::mma_f16(d_tmem, da + 2, db + 2, idesc, 1u);
-                        ptx::mma_f16(d_tmem, da + 0, db + 4, idesc, 1u);                 // hi*lo
-                        ptx::mma_f16(d_tmem, da + 2, db + 6, idesc, 1u);
-                        ptx::mma_f16(d_tmem, da + 4, db + 0, idesc, 1u);                 // lo*hi
-                        ptx::mma_f16(d_tmem, da + 6, db + 2, idesc, 1u);
-                        if (!p.w_resident) {
-                            ptx::mma_commit(b_empty + bs);
-                            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-                        }
+                const uint32_t a_lo = a_lo0 + (uint32_t)as * a_step;
+                for (int tap = 0; tap < p.num_taps; ++tap) {
+                    uint32_t b_lo;
+                    if (p.w_resident) {
+                        b_lo = b_lo0 + (uint32_t)(ch * p.num_taps + tap) * b_step;
+                    } else {
+                        ptx::mbar_wait(b_full + bs, bph);
+                        ptx::tc_fence_after();
+                        b_lo = b_lo0 + (uint32_t)bs * b_step;
                     }
-                    ptx::mma_commit(a_empty + as);
-                    if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                    const uint32_t da = a_lo + tap_off[tap];
+                    if (ptx::elect_one()) {
+                        // 128-byte row = [hi k0 | hi k1 | lo k0 | lo k1], 32 B each -> +2 per slot in descriptor units
+                        ptx::mma_f16_lh(d_tmem, da + 0, a_hi, b_lo + 0, b_hi, idesc, accum);   // hi*hi
+                        ptx::mma_f16_lh(d_tmem, da + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                        ptx::mma_f16_lh(d_tmem, da + 0, a_hi, b_lo + 4, b_hi, idesc, 1u);      // hi*lo
+                        ptx::mma_f16_lh(d_tmem, da + 2, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                        ptx::mma_f16_lh(d_tmem, da + 4, a_hi, b_lo + 0, b_hi, idesc, 1u);      // lo*hi
+                        ptx::mma_f16_lh(d_tmem, da + 6, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                        if (!p.w_resident) ptx::mma_commit(b_empty + bs);
+                    }
+                    __syncwarp();
+                    accum = 1u;
+                    if (!p.w_resident) { if (++bs == p.b_stages) { bs = 0; bph ^= 1; } }
                 }
-                ptx::mma_commit(acc_full + buf);
+                if (ptx::elect_one()) ptx::mma_commit(a_empty + as);
+                __syncwarp();
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
             }
+            if (ptx::elect_one()) ptx::mma_commit(acc_full + buf);
+            __syncwarp();
         }
     } else {
+        // epilogue group g (warps 2-5 -> 0, warps 7-10 -> 1) owns accumulator g and every second tile
+        const int grp = warp >= 7 ? 1 : 0;
+        const int first_thread = grp ? 224 : 64;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            if ((it & 1) != grp) continue;
             int n0, oy0, ox0;
             decode(tile, n0, oy0, ox0);
-            const int buf = it & 1;
-            conv_epilogue(p, tmem_base + (uint32_t)(buf * p.BN), ep, acc_full + buf, warp, lane, n0, oy0, ox0, co0, 64,
-                          ((uint32_t)it >> 1) & 1u, true);
+            conv_epilogue(p, tmem_base + (uint32_t)(grp * p.BN), ep + grp * 6 * p.BN, acc_full + grp, warp, lane, n0, oy0,
+                          ox0, co0, first_thread, ((uint32_t)it >> 1) & 1u, true, 1 + grp);
             ptx::tc_fence_before();
-            ptx::mbar_arrive(acc_empty + buf);                 // 128 arrivals free the accumulator
+            ptx::mbar_arrive(acc_empty + grp);                 // 128 arrivals free the accumulator
         }
     }
     ptx::tc_fence_before();
@@ -629,7 +643,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             p.b_stages = p.w_resident ? 1 : std::max(2, std::min(8, k_slices));
             const int b_bytes = p.w_resident ? w_bytes : p.b_stages * hBN * 128;
             p.tmem_cols = std::max(32, next_pow2(2 * hBN));
-            const int fixed = b_bytes + (2 * 8 + 2 * p.b_stages + 4) * 8 + 16 + 6 * hBN * 4 + 2048;
+            const int fixed = b_bytes + (2 * 8 + 2 * p.b_stages + 4) * 8 + 16 + WGS_MAX_TAPS * 4 + 12 * hBN * 4 + 2048;
             p.a_stages = std::max(1, std::min(6, (200 * 1024 - fixed) / p.a_stage_bytes));
             p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
             alignas(64) CUtensorMap ta, tb;
@@ -657,7 +671,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                 WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
             }
             const size_t hsmem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)b_bytes +
-                                 (2 * p.a_stages + 2 * p.b_stages + 4) * 8 + 16 + 6 * hBN * 4 + 1024;
+                                 (2 * p.a_stages + 2 * p.b_stages + 4) * 8 + 16 + WGS_MAX_TAPS * 4 + 12 * hBN * 4 + 1024;
             static bool attr = false;
             if (!attr) {
                 WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
