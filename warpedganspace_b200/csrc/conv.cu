@@ -57,6 +57,7 @@ struct ConvKernelParams {
     // addresses it through its UMMA descriptor
     int dy0, dx0, halo_h, halo_w, pitch, a_stage_bytes, a_stages, b_stages, desc_base_offset;
     int w_resident, total_tiles;
+    int nacc;                    // independent TMEM accumulators per tile (summed in the epilogue)
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -114,6 +115,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     for (int c = 0; c < BN; c += 16) {
         float v[16];
         ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        for (int a = 1; a < p.nacc; ++a) {                   // partial accumulators (short dependent MMA chains)
+            float u[16];
+            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += u[i];
+        }
         const int co = co0 + c;
         if (!valid || co >= p.cout) continue;
 #pragma unroll
@@ -400,7 +407,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int buf = it & 1;
             ptx::mbar_wait(acc_empty + buf, (((uint32_t)it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nacc * p.BN);
+            // the six MMAs of a (tap, chunk) go to nacc independent accumulators: an MMA with N = 32..64 lasts 16-32
+            // tensor cycles but a dependent accumulate waits ~100 cycles for its predecessor, so one chain of
+            // 6*taps*chunks MMAs would leave the tensor pipe idle most of the time
+            uint32_t dcol[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) dcol[j] = d_tmem + (uint32_t)((j % p.nacc) * p.BN);
             uint32_t accum = 0;
             for (int ch = 0; ch < p.c_chunks; ++ch) {
                 ptx::mbar_wait(a_full + as, aph);
@@ -418,12 +431,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const uint32_t da = a_lo + tap_off[tap];
                     if (ptx::elect_one()) {
                         // 128-byte row = [hi k0 | hi k1 | lo k0 | lo k1], 32 B each -> +2 per slot in descriptor units
-                        ptx::mma_f16_lh(d_tmem, da + 0, a_hi, b_lo + 0, b_hi, idesc, accum);   // hi*hi
-                        ptx::mma_f16_lh(d_tmem, da + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
-                        ptx::mma_f16_lh(d_tmem, da + 0, a_hi, b_lo + 4, b_hi, idesc, 1u);      // hi*lo
-                        ptx::mma_f16_lh(d_tmem, da + 2, a_hi, b_lo + 6, b_hi, idesc, 1u);
-                        ptx::mma_f16_lh(d_tmem, da + 4, a_hi, b_lo + 0, b_hi, idesc, 1u);      // lo*hi
-                        ptx::mma_f16_lh(d_tmem, da + 6, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                        const int na = p.nacc;
+                        ptx::mma_f16_lh(dcol[0], da + 0, a_hi, b_lo + 0, b_hi, idesc, accum);                      // hi*hi
+                        ptx::mma_f16_lh(dcol[1], da + 2, a_hi, b_lo + 2, b_hi, idesc, (accum | (na < 2)) ? 1u : 0u);
+                        ptx::mma_f16_lh(dcol[2], da + 0, a_hi, b_lo + 4, b_hi, idesc, (accum | (na < 3)) ? 1u : 0u);   // hi*lo
+                        ptx::mma_f16_lh(dcol[3], da + 2, a_hi, b_lo + 6, b_hi, idesc, (accum | (na < 4)) ? 1u : 0u);
+                        ptx::mma_f16_lh(dcol[4], da + 4, a_hi, b_lo + 0, b_hi, idesc, (accum | (na < 5)) ? 1u : 0u);   // lo*hi
+                        ptx::mma_f16_lh(dcol[5], da + 6, a_hi, b_lo + 2, b_hi, idesc, (accum | (na < 6)) ? 1u : 0u);
                         if (!p.w_resident) ptx::mma_commit(b_empty + bs);
                     }
                     __syncwarp();
@@ -446,7 +460,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if ((it & 1) != grp) continue;
             int n0, oy0, ox0;
             decode(tile, n0, oy0, ox0);
-            conv_epilogue(p, tmem_base + (uint32_t)(grp * p.BN), ep + grp * 6 * p.BN, acc_full + grp, warp, lane, n0, oy0,
+            conv_epilogue(p, tmem_base + (uint32_t)(grp * p.nacc * p.BN), ep + grp * 6 * p.BN, acc_full + grp, warp, lane, n0, oy0,
                           ox0, co0, first_thread, ((uint32_t)it >> 1) & 1u, true, 1 + grp);
             ptx::tc_fence_before();
             ptx::mbar_arrive(acc_empty + grp);                 // 128 arrivals free the accumulator
@@ -579,6 +593,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.BN = BN;
     p.n_tiles_co = ceil_div(d->cout, BN);
     p.tmem_cols = std::max(32, next_pow2(BN));
+    p.nacc = 1;
     const int stage_bytes = A_STAGE_BYTES + BN * 128;
     // Short contractions (few taps x chunks) are latency-bound per tile: keep the ring shallow so that several
     // CTAs fit on one SM (smem and TMEM columns permitting) and overlap each other's prologue / epilogue.
@@ -642,7 +657,9 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             p.w_resident = (w_bytes <= 80 * 1024) ? 1 : 0;
             p.b_stages = p.w_resident ? 1 : std::max(2, std::min(8, k_slices));
             const int b_bytes = p.w_resident ? w_bytes : p.b_stages * hBN * 128;
-            p.tmem_cols = std::max(32, next_pow2(2 * hBN));
+            p.nacc = std::max(1, std::min(6, 512 / (2 * hBN)));
+            if (p.nacc == 4 || p.nacc == 5) p.nacc = 3;            // keep hi*hi / hi*lo / lo*hi chains separate
+            p.tmem_cols = std::max(32, next_pow2(2 * p.nacc * hBN));
             const int fixed = b_bytes + (2 * 8 + 2 * p.b_stages + 4) * 8 + 16 + WGS_MAX_TAPS * 4 + 12 * hBN * 4 + 2048;
             p.a_stages = std::max(1, std::min(6, (200 * 1024 - fixed) / p.a_stage_bytes));
             p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
