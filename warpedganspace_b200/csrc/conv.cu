@@ -305,7 +305,7 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32
 // registers) and only the elected lane issues tcgen05.mma / commit — with N = 32..64 an MMA is 16-32 tensor cycles,
 // so the issue path, not the tensor pipe, is what has to be short (profiles/r01_conv_halo_ncu.md).
 //   warp 0: patch producer  warp 1: MMA  warps 2-5: epilogue group 0  warp 6: weight producer  warps 7-10: group 1
-__global__ void __launch_bounds__(HALO_THREADS, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -661,7 +661,10 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             if (p.nacc == 4 || p.nacc == 5) p.nacc = 3;            // keep hi*hi / hi*lo / lo*hi chains separate
             p.tmem_cols = std::max(32, next_pow2(2 * p.nacc * hBN));
             const int fixed = b_bytes + (2 * 8 + 2 * p.b_stages + 4) * 8 + 16 + WGS_MAX_TAPS * 4 + 12 * hBN * 4 + 2048;
-            p.a_stages = std::max(1, std::min(6, (200 * 1024 - fixed) / p.a_stage_bytes));
+            // two persistent CTAs per SM (two MMA issuers, four epilogue warpgroups) when the weights leave room
+            const int per_cta = (fixed + 2 * p.a_stage_bytes <= 110 * 1024) ? 110 * 1024 : 200 * 1024;
+            const int ctas_per_sm_h = per_cta <= 110 * 1024 ? 2 : 1;
+            p.a_stages = std::max(1, std::min(6, (per_cta - fixed) / p.a_stage_bytes));
             p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
             alignas(64) CUtensorMap ta, tb;
             {
@@ -694,7 +697,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                 WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
                 attr = true;
             }
-            int hgrid = std::min(p.total_tiles, num_sms());
+            int hgrid = std::min(p.total_tiles, num_sms() * ctas_per_sm_h);
             hgrid = std::max(p.n_tiles_co, hgrid / p.n_tiles_co * p.n_tiles_co);     // a CTA keeps its channel tile
             conv_halo_kernel<<<hgrid, HALO_THREADS, hsmem, st>>>(ta, tb, p);
             count_launch();
