@@ -53,11 +53,6 @@ struct ConvKernelParams {
     int out_from_n;              // fp32 `out` is written only for images n >= out_from_n
     const float* rgb_w;          // [out_n][3][cout] modulated ToRGB weights; rgb_out += act . rgb_w
     float* rgb_out;              // [out_n][grid_h][grid_w][3], pre-initialised with bias + upsampled skip
-    // halo variant: the (bh + wy - 1) x (bw + wx - 1) input patch of a chunk is loaded once and every tap
-    // addresses it through its UMMA descriptor
-    int dy0, dx0, halo_h, halo_w, pitch, a_stage_bytes, a_stages, b_stages, desc_base_offset;
-    int w_resident, total_tiles;
-    int nacc;                    // independent TMEM accumulators per tile (summed in the epilogue)
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -67,126 +62,6 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 2) return v > 0.f ? v : 0.2f * v;
     if (act == 3) return 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);      // FusedLeakyReLU
     return v;
-}
-
-// Epilogue shared by the tensor-core conv kernels: TMEM accumulator -> demod / noise / bias / activation ->
-// fp32 NHWC store, split32 operand of the next layer, fused ToRGB.  Executed by four warps whose (warp % 4)
-// selects the 32 TMEM lanes they may read; `first_thread` is threadIdx.x of the first epilogue thread.
-__device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep,
-                                              uint64_t* acc_bar, int warp, int lane, int n0, int oy0, int ox0,
-                                              int co0, int first_thread, uint32_t acc_parity = 0,
-                                              bool persistent = false, int bar_id = 1) {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
-    const int n = n0 + nl, oy = oy0 + yl, ox = ox0 + xl;
-    const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
-    float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
-                 (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
-    const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
-    const float nz = (p.noise && valid)
-        ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
-        : 0.f;
-    // One image per tile (the common case): stage alpha / beta / next-layer style / ToRGB weights of this
-    // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
-    const bool cs = (p.bn == 1);
-    const int BN = p.BN;
-    if (cs) {
-        const bool n_ok = n0 < p.out_n;
-        if (persistent) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // previous tile's readers of `ep` are done
-        for (int i = threadIdx.x - first_thread; i < BN; i += 128) {
-            const int cc = co0 + i;
-            const bool ok = n_ok && cc < p.cout;
-            ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
-            ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
-            ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
-#pragma unroll
-            for (int o = 0; o < 3; ++o)
-                ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-    }
-    ptx::mbar_wait(acc_bar, acc_parity);
-    ptx::tc_fence_after();
-    const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
-    float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-    for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        for (int a = 1; a < p.nacc; ++a) {                   // partial accumulators (short dependent MMA chains)
-            float u[16];
-            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), u);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += u[i];
-        }
-        const int co = co0 + c;
-        if (!valid || co >= p.cout) continue;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int cc = co + i;
-            if (cc < p.cout) {
-                float r = v[i];
-                if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
-                else {
-                    if (alpha) r *= __ldg(alpha + cc);
-                    r += nz;
-                    if (p.beta) r += __ldg(p.beta + cc);
-                }
-                if (p.accumulate) r += dst[cc];
-                v[i] = apply_act(r, p.act);
-            } else {
-                v[i] = 0.f;
-            }
-        }
-        if (p.rgb_w) {
-            if (cs) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    rgb0 += v[i] * ep[3 * BN + c + i];
-                    rgb1 += v[i] * ep[4 * BN + c + i];
-                    rgb2 += v[i] * ep[5 * BN + c + i];
-                }
-            } else {
-                const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (co + i < p.cout) {
-                        rgb0 += v[i] * __ldg(wm + i);
-                        rgb1 += v[i] * __ldg(wm + p.cout + i);
-                        rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
-                    }
-                }
-            }
-        }
-        if (p.out_split) {
-            __align__(16) __nv_bfloat16 hi[16], lo[16];
-            const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
-            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
-                                (size_t)(co >> 5) * 64 + (co & 16);
-            reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
-            reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
-            reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
-            reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
-        }
-        if (write_f32) {
-            if (vec_ok && co + 16 <= p.cout) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-                for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
-            }
-        }
-    }
-    if (p.rgb_out && valid) {
-        float* ro = p.rgb_out + pix * 3;
-        atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
-    }
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 4)
@@ -269,201 +144,110 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mma_commit(acc_bar);                         // accumulator complete
         }
     } else {
-        conv_epilogue(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, 64);
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------
-// Halo variant for stride-1 tap lists on low-channel / high-resolution layers (L2-fabric bound in the kernel
-// above, where every tap re-fetches its shifted 128-pixel patch: 11-13x the input size crosses L2->SM,
-// profiles/r01_conv_tc_ncu_full.md).  Tile = 16 rows x 8 columns of output pixels.  Per 32-channel chunk ONE
-// TMA box brings the (16 + wy - 1) x (8 + wx - 1) input patch; the A operand of tap (ty, tx) is that same
-// buffer viewed through a descriptor whose start address is advanced by (ty * pitch + tx) rows and whose
-// stride-byte-offset is the patch row pitch: the eight pixels of one output row are eight consecutive
-// 128-byte rows (one swizzle-atom group), successive output rows are `pitch` rows apart.  The 128B swizzle is
-// a function of the absolute shared-memory address for both the TMA write and the UMMA read, so shifted views
-// stay consistent.  Weights stream through their own ring (one tap slice per stage).
-//   warp 0: patch producer   warp 1: MMA issuer + TMEM   warps 2-5: epilogue   warp 6: weight producer
-constexpr int HALO_THREADS = 352;
-
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)(base_offset & 7u) << 49) | ((uint64_t)2 << 61);
-}
-
-// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (gridDim.x is a multiple of the number of
-// output-channel tiles, so a CTA keeps its channel slice and, when they fit, its weights stay resident in shared
-// memory for the whole kernel).  Two TMEM accumulators and two epilogue warpgroups: the epilogue of tile i overlaps
-// the loads and MMAs of tiles i+1, i+2.  The MMA warp runs warp-uniform (descriptor arithmetic stays in uniform
-// registers) and only the elected lane issues tcgen05.mma / commit — with N = 32..64 an MMA is 16-32 tensor cycles,
-// so the issue path, not the tensor pipe, is what has to be short (profiles/r01_conv_halo_ncu.md).
-//   warp 0: patch producer  warp 1: MMA  warps 2-5: epilogue group 0  warp 6: weight producer  warps 7-10: group 1
-__global__ void __launch_bounds__(HALO_THREADS, 2)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ ConvKernelParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b_stage_bytes = p.BN * 128;
-    const int k_slices = p.c_chunks * p.num_taps;                         // weight slices per tile
-    const int b_slots = p.w_resident ? k_slices : p.b_stages;
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)b_slots * b_stage_bytes);
-    uint64_t* a_empty = a_full + p.a_stages;
-    uint64_t* b_full = a_empty + p.a_stages;                              // [b_stages] (or [1] when resident)
-    uint64_t* b_empty = b_full + p.b_stages;
-    uint64_t* acc_full = b_empty + p.b_stages;                            // [2]
-    uint64_t* acc_empty = acc_full + 2;                                   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    uint32_t* tap_off = tmem_slot + 4;                                    // [WGS_MAX_TAPS] descriptor offsets (>>4)
-    float* ep = reinterpret_cast<float*>(tap_off + WGS_MAX_TAPS);         // [2][6][BN]
-
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&tmap_a);
-        ptx::prefetch_tmap(&tmap_b);
-        for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(a_full + s, 1); ptx::mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full + s, 1); ptx::mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(acc_full + s, 1); ptx::mbar_init(acc_empty + s, 128); }
-        ptx::fence_mbar_init();
-    }
-    if (threadIdx.x < p.num_taps)
-        tap_off[threadIdx.x] =
-            (uint32_t)(((p.tap_dy[threadIdx.x] - p.dy0) * p.pitch + (p.tap_dx[threadIdx.x] - p.dx0)) * 128) >> 4;
-    if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int co0 = (int)(blockIdx.x % p.n_tiles_co) * p.BN;
-
-    auto decode = [&](int tile, int& n0, int& oy0, int& ox0) {
-        int t = tile / p.n_tiles_co;
-        ox0 = (t % p.tiles_x) * p.bw; t /= p.tiles_x;
-        oy0 = (t % p.tiles_y) * p.bh; t /= p.tiles_y;
-        n0 = t;
-    };
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t bytes = (uint32_t)(p.halo_h * p.pitch * 128);
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                int n0, oy0, ox0;
-                decode(tile, n0, oy0, ox0);
-                for (int ch = 0; ch < p.c_chunks; ++ch) {
-                    ptx::mbar_wait(a_empty + stage, phase ^ 1);
-                    ptx::mbar_expect_tx(a_full + stage, bytes);
-                    ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_a, a_full + stage, 0, ch,
-                                     ox0 + p.dx0, oy0 + p.dy0, n0);
-                    if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 6) {
-        if (lane == 0) {
-            if (p.w_resident) {
-                // all weight slices of this CTA's channel tile, once
-                ptx::mbar_expect_tx(b_full, (uint32_t)(k_slices * b_stage_bytes));
-                for (int ch = 0; ch < p.c_chunks; ++ch)
-                    for (int tap = 0; tap < p.num_taps; ++tap)
-                        ptx::tma_load_4d(smem_b + (size_t)(ch * p.num_taps + tap) * b_stage_bytes, &tmap_b, b_full, 0, ch,
-                                         co0, (int)p.tap_w[tap]);
-            } else {
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
-                    for (int ch = 0; ch < p.c_chunks; ++ch)
-                        for (int tap = 0; tap < p.num_taps; ++tap) {
-                            ptx::mbar_wait(b_empty + stage, phase ^ 1);
-                            ptx::mbar_expect_tx(b_full + stage, (uint32_t)b_stage_bytes);
-                            ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, b_full + stage, 0, ch, co0,
-                                             (int)p.tap_w[tap]);
-                            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
-                        }
-            }
-        }
-    } else if (warp == 1) {
-        // whole warp, uniform control flow; one elected lane issues
-        const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
-        const uint64_t a_proto = umma_desc_k_sw128(0, (uint32_t)p.pitch * 128u, 0);
-        const uint64_t b_proto = ptx::umma_desc_sw128(0);
-        const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
-        const uint32_t a_lo0 = (ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4;
-        const uint32_t b_lo0 = (ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4;
-        const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)b_stage_bytes >> 4;
-        int as = 0, bs = 0, it = 0;
-        uint32_t aph = 0, bph = 0;
-        if (p.w_resident) ptx::mbar_wait(b_full, 0);
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            ptx::mbar_wait(acc_empty + buf, (((uint32_t)it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nacc * p.BN);
-            // the six MMAs of a (tap, chunk) go to nacc independent accumulators: an MMA with N = 32..64 lasts 16-32
-            // tensor cycles but a dependent accumulate waits ~100 cycles for its predecessor, so one chain of
-            // 6*taps*chunks MMAs would leave the tensor pipe idle most of the time
-            uint32_t dcol[6];
+        // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
+        const int n = n0 + nl, oy = oy0 + yl, ox = ox0 + xl;
+        const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
+        float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
+                     (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
+        const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
+        const float nz = (p.noise && valid)
+            ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
+            : 0.f;
+        // One image per tile (the common case): stage alpha / beta / next-layer style / ToRGB weights of this
+        // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
+        const bool cs = (p.bn == 1);
+        const int BN = p.BN;
+        if (cs) {
+            const bool n_ok = n0 < p.out_n;
+            for (int i = threadIdx.x - 64; i < BN; i += 128) {
+                const int cc = co0 + i;
+                const bool ok = n_ok && cc < p.cout;
+                ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
+                ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
+                ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) dcol[j] = d_tmem + (uint32_t)((j % p.nacc) * p.BN);
-            uint32_t accum = 0;
-            for (int ch = 0; ch < p.c_chunks; ++ch) {
-                ptx::mbar_wait(a_full + as, aph);
-                ptx::tc_fence_after();
-                const uint32_t a_lo = a_lo0 + (uint32_t)as * a_step;
-                for (int tap = 0; tap < p.num_taps; ++tap) {
-                    uint32_t b_lo;
-                    if (p.w_resident) {
-                        b_lo = b_lo0 + (uint32_t)(ch * p.num_taps + tap) * b_step;
-                    } else {
-                        ptx::mbar_wait(b_full + bs, bph);
-                        ptx::tc_fence_after();
-                        b_lo = b_lo0 + (uint32_t)bs * b_step;
-                    }
-                    const uint32_t da = a_lo + tap_off[tap];
-                    if (ptx::elect_one()) {
-                        // 128-byte row = [hi k0 | hi k1 | lo k0 | lo k1], 32 B each -> +2 per slot in descriptor units
-                        const int na = p.nacc;
-                        ptx::mma_f16_lh(dcol[0], da + 0, a_hi, b_lo + 0, b_hi, idesc, accum);                      // hi*hi
-                        ptx::mma_f16_lh(dcol[1], da + 2, a_hi, b_lo + 2, b_hi, idesc, (accum | (na < 2)) ? 1u : 0u);
-                        ptx::mma_f16_lh(dcol[2], da + 0, a_hi, b_lo + 4, b_hi, idesc, (accum | (na < 3)) ? 1u : 0u);   // hi*lo
-                        ptx::mma_f16_lh(dcol[3], da + 2, a_hi, b_lo + 6, b_hi, idesc, (accum | (na < 4)) ? 1u : 0u);
-                        ptx::mma_f16_lh(dcol[4], da + 4, a_hi, b_lo + 0, b_hi, idesc, (accum | (na < 5)) ? 1u : 0u);   // lo*hi
-                        ptx::mma_f16_lh(dcol[5], da + 6, a_hi, b_lo + 2, b_hi, idesc, (accum | (na < 6)) ? 1u : 0u);
-                        if (!p.w_resident) ptx::mma_commit(b_empty + bs);
-                    }
-                    __syncwarp();
-                    accum = 1u;
-                    if (!p.w_resident) { if (++bs == p.b_stages) { bs = 0; bph ^= 1; } }
-                }
-                if (ptx::elect_one()) ptx::mma_commit(a_empty + as);
-                __syncwarp();
-                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                for (int o = 0; o < 3; ++o)
+                    ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
             }
-            if (ptx::elect_one()) ptx::mma_commit(acc_full + buf);
-            __syncwarp();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-    } else {
-        // epilogue group g (warps 2-5 -> 0, warps 7-10 -> 1) owns accumulator g and every second tile
-        const int grp = warp >= 7 ? 1 : 0;
-        const int first_thread = grp ? 224 : 64;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != grp) continue;
-            int n0, oy0, ox0;
-            decode(tile, n0, oy0, ox0);
-            conv_epilogue(p, tmem_base + (uint32_t)(grp * p.nacc * p.BN), ep + grp * 6 * p.BN, acc_full + grp, warp, lane, n0, oy0,
-                          ox0, co0, first_thread, ((uint32_t)it >> 1) & 1u, true, 1 + grp);
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(acc_empty + grp);                 // 128 arrivals free the accumulator
+        ptx::mbar_wait(acc_bar, 0);
+        ptx::tc_fence_after();
+        const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
+        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+        for (int c = 0; c < BN; c += 16) {
+            float v[16];
+            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            const int co = co0 + c;
+            if (!valid || co >= p.cout) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int cc = co + i;
+                if (cc < p.cout) {
+                    float r = v[i];
+                    if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
+                    else {
+                        if (alpha) r *= __ldg(alpha + cc);
+                        r += nz;
+                        if (p.beta) r += __ldg(p.beta + cc);
+                    }
+                    if (p.accumulate) r += dst[cc];
+                    v[i] = apply_act(r, p.act);
+                } else {
+                    v[i] = 0.f;
+                }
+            }
+            if (p.rgb_w) {
+                if (cs) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        rgb0 += v[i] * ep[3 * BN + c + i];
+                        rgb1 += v[i] * ep[4 * BN + c + i];
+                        rgb2 += v[i] * ep[5 * BN + c + i];
+                    }
+                } else {
+                    const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (co + i < p.cout) {
+                            rgb0 += v[i] * __ldg(wm + i);
+                            rgb1 += v[i] * __ldg(wm + p.cout + i);
+                            rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
+                        }
+                    }
+                }
+            }
+            if (p.out_split) {
+                __align__(16) __nv_bfloat16 hi[16], lo[16];
+                const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
+                __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
+                                    (size_t)(co >> 5) * 64 + (co & 16);
+                reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
+                reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
+                reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
+                reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
+            }
+            if (write_f32) {
+                if (vec_ok && co + 16 <= p.cout) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+                    for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+                }
+            }
+        }
+        if (p.rgb_out && valid) {
+            float* ro = p.rgb_out + pix * 3;
+            atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
         }
     }
     ptx::tc_fence_before();
@@ -593,7 +377,6 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.BN = BN;
     p.n_tiles_co = ceil_div(d->cout, BN);
     p.tmem_cols = std::max(32, next_pow2(BN));
-    p.nacc = 1;
     const int stage_bytes = A_STAGE_BYTES + BN * 128;
     // Short contractions (few taps x chunks) are latency-bound per tile: keep the ring shallow so that several
     // CTAs fit on one SM (smem and TMEM columns permitting) and overlap each other's prologue / epilogue.
@@ -619,93 +402,6 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
 
     auto encode = get_encode();
     WGS_REQUIRE(encode != nullptr, "conv: cuTensorMapEncodeTiled entry point not available");
-
-    // ---- halo variant ---------------------------------------------------------------------------------
-    {
-        int dy0 = 127, dy1 = -127, dx0 = 127, dx1 = -127;
-        for (int i = 0; i < d->num_taps; ++i) {
-            dy0 = std::min(dy0, d->tap_dy[i]); dy1 = std::max(dy1, d->tap_dy[i]);
-            dx0 = std::min(dx0, d->tap_dx[i]); dx1 = std::max(dx1, d->tap_dx[i]);
-        }
-        const int wy = dy1 - dy0 + 1, wx = dx1 - dx0 + 1;
-        static int halo_mode = -1, halo_pitch16 = 0, halo_bo = 0;
-        if (halo_mode < 0) {
-            const char* e = getenv("WGS_CONV_HALO");           // 0 = off, 1 = on (default)
-            halo_mode = (e && e[0] == '0') ? 0 : 1;
-            const char* e2 = getenv("WGS_CONV_HALO_PITCH16");
-            halo_pitch16 = (e2 && e2[0] == '1') ? 1 : 0;
-            const char* e3 = getenv("WGS_CONV_HALO_BASE_OFFSET");
-            halo_bo = (e3 && e3[0] == '1') ? 1 : 0;
-        }
-        const bool eligible = halo_mode && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
-                              d->grid_h >= 16 && d->grid_w >= 8 && d->c_chunks <= 2 && d->force_bn == 0;
-        if (eligible) {
-            p.bw = 8; p.bh = 16; p.bn = 1;
-            p.tiles_x = ceil_div(d->grid_w, 8); p.tiles_y = ceil_div(d->grid_h, 16); p.tiles_n = d->out_n;
-            p.dy0 = dy0; p.dx0 = dx0;
-            p.halo_h = 16 + wy - 1; p.halo_w = 8 + wx - 1;
-            p.pitch = halo_pitch16 ? 16 : p.halo_w;
-            p.desc_base_offset = halo_bo;
-            int hBN = std::min(128, (d->cout + 15) / 16 * 16);
-            // prefer a channel tile whose weights (all taps x chunks) stay resident in shared memory
-            while (hBN > 32 && hBN % 32 == 0 && d->num_taps * d->c_chunks * hBN * 128 > 80 * 1024) hBN /= 2;
-            p.BN = hBN;
-            p.n_tiles_co = ceil_div(d->cout, hBN);
-            p.a_stage_bytes = (p.halo_h * p.pitch * 128 + 1023) / 1024 * 1024;
-            const int k_slices = d->num_taps * d->c_chunks;
-            const int w_bytes = k_slices * hBN * 128;
-            p.w_resident = (w_bytes <= 80 * 1024) ? 1 : 0;
-            p.b_stages = p.w_resident ? 1 : std::max(2, std::min(8, k_slices));
-            const int b_bytes = p.w_resident ? w_bytes : p.b_stages * hBN * 128;
-            p.nacc = std::max(1, std::min(6, 512 / (2 * hBN)));
-            if (p.nacc == 4 || p.nacc == 5) p.nacc = 3;            // keep hi*hi / hi*lo / lo*hi chains separate
-            p.tmem_cols = std::max(32, next_pow2(2 * p.nacc * hBN));
-            const int fixed = b_bytes + (2 * 8 + 2 * p.b_stages + 4) * 8 + 16 + WGS_MAX_TAPS * 4 + 12 * hBN * 4 + 2048;
-            // two persistent CTAs per SM (two MMA issuers, four epilogue warpgroups) when the weights leave room
-            const int per_cta = (fixed + 2 * p.a_stage_bytes <= 110 * 1024) ? 110 * 1024 : 200 * 1024;
-            const int ctas_per_sm_h = per_cta <= 110 * 1024 ? 2 : 1;
-            p.a_stages = std::max(1, std::min(6, (per_cta - fixed) / p.a_stage_bytes));
-            p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
-            alignas(64) CUtensorMap ta, tb;
-            {
-                const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
-                                            (cuuint64_t)d->in_n};
-                const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->in_w, s4 = s3 * d->in_h;
-                const cuuint64_t strides[4] = {s1, s2, s3, s4};
-                const cuuint32_t box[5] = {64, 1, (cuuint32_t)p.pitch, (cuuint32_t)p.halo_h, 1};
-                const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-                CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->in), dims, strides, box,
-                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(input) failed with code " + std::to_string((int)r));
-            }
-            {
-                const cuuint64_t dims[4] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_cout, (cuuint64_t)d->w_taps};
-                const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->w_cout;
-                const cuuint64_t strides[3] = {s1, s2, s3};
-                const cuuint32_t box[4] = {64, 1, (cuuint32_t)hBN, 1};
-                const cuuint32_t estr[4] = {1, 1, 1, 1};
-                CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->w), dims, strides, box,
-                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
-            }
-            const size_t hsmem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)b_bytes +
-                                 (2 * p.a_stages + 2 * p.b_stages + 4) * 8 + 16 + WGS_MAX_TAPS * 4 + 12 * hBN * 4 + 1024;
-            static bool attr = false;
-            if (!attr) {
-                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-                attr = true;
-            }
-            int hgrid = std::min(p.total_tiles, num_sms() * ctas_per_sm_h);
-            hgrid = std::max(p.n_tiles_co, hgrid / p.n_tiles_co * p.n_tiles_co);     // a CTA keeps its channel tile
-            conv_halo_kernel<<<hgrid, HALO_THREADS, hsmem, st>>>(ta, tb, p);
-            count_launch();
-            WGS_LAUNCH_CHECK();
-            return 0;
-        }
-    }
-
     alignas(64) CUtensorMap tmap_a, tmap_b;
     {
         const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
