@@ -64,6 +64,9 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// FUSED = false: plain epilogue (demod / noise / bias / activation / accumulate -> fp32), lean register budget.
+// FUSED = true: additionally emits the next layer's split32 operand, ToRGB partial sums, selective fp32 stores.
+template <bool FUSED>
 __global__ void __launch_bounds__(CONV_THREADS, 4)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvKernelParams p) {
@@ -122,27 +125,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                ptx::mbar_wait(full_bar + stage, phase);
-                ptx::tc_fence_after();
-                const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES));
-                const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smem_b + (size_t)stage * b_stage_bytes));
+        // whole warp with uniform control flow (descriptor arithmetic stays in uniform registers); one elected lane
+        // issues the MMAs and commits
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
+        const uint32_t dhi = (uint32_t)(ptx::umma_desc_sw128(0) >> 32);
+        const uint32_t a_lo0 = (ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4;
+        const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = (uint32_t)b_stage_bytes >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+            ptx::mbar_wait(full_bar + stage, phase);
+            ptx::tc_fence_after();
+            const uint32_t da = a_lo0 + (uint32_t)stage * a_step, db = b_lo0 + (uint32_t)stage * b_step;
+            if (ptx::elect_one()) {
                 // 128-byte row = [hi k0 | hi k1 | lo k0 | lo k1], 32 B each -> descriptor address +2 per slot
-                ptx::mma_f16(tmem_base, da + 0, db + 0, idesc, kb > 0 ? 1u : 0u);   // hi*hi
-                ptx::mma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
-                ptx::mma_f16(tmem_base, da + 0, db + 4, idesc, 1u);                 // hi*lo
-                ptx::mma_f16(tmem_base, da + 2, db + 6, idesc, 1u);
-                ptx::mma_f16(tmem_base, da + 4, db + 0, idesc, 1u);                 // lo*hi
-                ptx::mma_f16(tmem_base, da + 6, db + 2, idesc, 1u);
+                ptx::mma_f16_lh(tmem_base, da + 0, dhi, db + 0, dhi, idesc, kb > 0 ? 1u : 0u);   // hi*hi
+                ptx::mma_f16_lh(tmem_base, da + 2, dhi, db + 2, dhi, idesc, 1u);
+                ptx::mma_f16_lh(tmem_base, da + 0, dhi, db + 4, dhi, idesc, 1u);                 // hi*lo
+                ptx::mma_f16_lh(tmem_base, da + 2, dhi, db + 6, dhi, idesc, 1u);
+                ptx::mma_f16_lh(tmem_base, da + 4, dhi, db + 0, dhi, idesc, 1u);                 // lo*hi
+                ptx::mma_f16_lh(tmem_base, da + 6, dhi, db + 2, dhi, idesc, 1u);
                 ptx::mma_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            ptx::mma_commit(acc_bar);                         // accumulator complete
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        if (ptx::elect_one()) ptx::mma_commit(acc_bar);       // accumulator complete
+        __syncwarp();
     } else {
         // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
         const int q = warp & 3;
@@ -167,16 +176,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const bool ok = n_ok && cc < p.cout;
                 ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
                 ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
-                ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
+                if constexpr (FUSED) {
+                    ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
 #pragma unroll
-                for (int o = 0; o < 3; ++o)
-                    ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
+                    for (int o = 0; o < 3; ++o)
+                        ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
+                }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         ptx::mbar_wait(acc_bar, 0);
         ptx::tc_fence_after();
-        const bool write_f32 = p.out != nullptr && n >= p.out_from_n;
+        const bool write_f32 = FUSED ? (p.out != nullptr && n >= p.out_from_n) : true;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
         const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
@@ -202,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     v[i] = 0.f;
                 }
             }
-            if (p.rgb_w) {
+            if (FUSED && p.rgb_w) {
                 if (cs) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -222,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                 }
             }
-            if (p.out_split) {
+            if (FUSED && p.out_split) {
                 __align__(16) __nv_bfloat16 hi[16], lo[16];
                 const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
 #pragma unroll
@@ -245,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
         }
-        if (p.rgb_out && valid) {
+        if (FUSED && p.rgb_out && valid) {
             float* ro = p.rgb_out + pix * 3;
             atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
         }
@@ -428,13 +439,16 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         WGS_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
     }
     const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 6 * BN * 4 + 1024;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        smem_set = 227 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        attr_set = true;
     }
     const int grid = m_tiles * p.n_tiles_co;
-    conv_tc_kernel<<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+    const bool fused = d->out_split != nullptr || d->rgb_out != nullptr || d->out_from_n > 0 || d->out == nullptr;
+    if (fused) conv_tc_kernel<true><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+    else conv_tc_kernel<false><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
