@@ -41,33 +41,50 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """Samples SM clocks and throttle reasons (NVML, every 20 ms) while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.max_mhz = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(',')]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((mhz, reasons))
+                time.sleep(0.02)
+        except Exception:
+            # fall back to nvidia-smi (slow: a few samples only)
+            q = 'clocks.sm,clocks.max.sm'
+            while not self.stop_flag:
+                try:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                    a, b = [float(x) for x in out.strip().split(',')[:2]]
+                    self.max_mhz = b
+                    self.samples.append((a, 0))
+                except Exception:
+                    pass
+                time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
-        mhz = sorted(float(s[0]) for s in self.samples)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': mhz[len(mhz) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unsampled']}
+        mhz = sorted(s[0] for s in self.samples)
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+        return {'sm_mhz': mhz[len(mhz) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': [n for b, n in names.items() if bits & b],
                 'samples': len(self.samples)}
 
 
@@ -168,7 +185,7 @@ def run_reference(args, world, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='product', choices=['product', 'reference'])
     ap.add_argument('--batch-per-gpu', type=int, default=4)
@@ -278,5 +295,13 @@ def main():
     print(json.dumps(line), flush=True)
 
 
+def _shutdown():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
 if __name__ == '__main__':
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()

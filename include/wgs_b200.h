@@ -153,6 +153,13 @@ int wgs_sg2_torgb_bwd(const float* drgb, const float* a, const float* s, long lo
                       long long P, int C, void* stream);
 int wgs_sg2_rgb_up_bwd(const float* drgb, float* dprev, int N, int H, int W, const float* h_taps4,
                        void* stream);
+/* Fused layer boundary of the data-gradient chain (mod_bwd of the layer above + torgb_bwd + act_bwd of this layer):
+ * every tensor is read once.  dx_up / drgb are optional (NULL) but not both.                                    */
+int wgs_sg2_layer_bwd(const float* dx_up, const float* s_up, long long s_up_ld, float* ds_up, long long ds_up_ld,
+                      const float* drgb, const float* s_rgb, long long s_rgb_ld, const float* Wrgb, float wscale,
+                      float* ds_rgb, long long ds_rgb_ld, const float* a, const float* demod, const float* bias,
+                      const float* noise, float noise_w, float* dd, float* dpre, void* g_split, int N,
+                      long long P, int C, void* stream);
 
 /* Fused Adam over a flat fp32 buffer, torch.optim.Adam defaults semantics (lib/trainer.py:153-156,253-254);
  * the gradient is multiplied by grad_scale first (1/world_size after the NCCL sum).                  */

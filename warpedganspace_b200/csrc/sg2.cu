@@ -70,42 +70,63 @@ __global__ void pixelnorm_rows_kernel(const float* __restrict__ x, float* __rest
 // Separable 4-tap FIR (upfirdn2d with up = down = 1, op/upfirdn2d_kernel.cu:52-137) fused with the
 // StyledConv tail: out = act(alpha[n,c] * fir(y)[Y,X,c] + noise_w * noise[Y,X] + beta[c]).
 // y: [N, Hin, Win, C] NHWC, out: [N, Hout, Wout, C]; fir(y)[Y,X] = sum_ij kf[i] kf[j] y[Y+i-pad0, X+j-pad0].
-__global__ void __launch_bounds__(256, 3)
+constexpr int FIR_ROWS = 8;                                        // output rows per thread
+
+__global__ void __launch_bounds__(256, 2)
 fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int Hin, int Win, int Hout, int Wout,
                 int C, int pad0, float k0, float k1, float k2, float k3, const float* __restrict__ alpha,
                 const float* __restrict__ beta, const float* __restrict__ noise, float noise_w, int act,
                 __nv_bfloat16* __restrict__ out_split, const float* __restrict__ split_scale, long long split_scale_ld,
                 int out_from_n) {
-    // each thread produces a 4-row strip of one channel quad: 7 x 4 float4 loads for 4 outputs (7 loads per output
-    // instead of 16); horizontal pass first, then the vertical combination in registers.
+    // each thread produces an 8-row strip of one channel quad: (8 + 3) x 4 float4 loads for 8 outputs (5.5 loads
+    // per output instead of 16); horizontal pass first, then the vertical combination in registers.  Interior
+    // strips take a path without per-load bounds checks (the kernel is instruction-bound, not DRAM-bound:
+    // profiles/r01_misc_ncu.md).
     const int c4n = C >> 2;
-    const int yb_n = (Hout + 3) >> 2;
+    const int yb_n = (Hout + FIR_ROWS - 1) / FIR_ROWS;
     const long long total = (long long)N * yb_n * Wout * c4n;
     const float kf[4] = {k3, k2, k1, k0};                       // correlation with the flipped kernel
+    const long long row_stride = (long long)Win * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4n) * 4;
         long long r = i / c4n;
         const int X = (int)(r % Wout); r /= Wout;
-        const int Y0 = (int)(r % yb_n) * 4;
+        const int Y0 = (int)(r % yb_n) * FIR_ROWS;
         const int n = (int)(r / yb_n);
-        float4 h[7];
+        const int yy0 = Y0 - pad0, xx0 = X - pad0;
+        const float* base = y + ((long long)n * Hin + yy0) * row_stride + (long long)xx0 * C + c;
+        float4 h[FIR_ROWS + 3];
+        if (yy0 >= 0 && yy0 + FIR_ROWS + 2 < Hin && xx0 >= 0 && xx0 + 3 < Win) {
 #pragma unroll
-        for (int a = 0; a < 7; ++a) {
-            const int yy = Y0 + a - pad0;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yy >= 0 && yy < Hin) {
-                const float* row = y + (((size_t)n * Hin + yy) * Win) * C + c;
+            for (int a = 0; a < FIR_ROWS + 3; ++a) {
+                const float* rowp = base + a * row_stride;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(rowp));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(rowp + C));
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(rowp + 2 * C));
+                const float4 v3 = __ldg(reinterpret_cast<const float4*>(rowp + 3 * C));
+                h[a].x = kf[0] * v0.x + kf[1] * v1.x + kf[2] * v2.x + kf[3] * v3.x;
+                h[a].y = kf[0] * v0.y + kf[1] * v1.y + kf[2] * v2.y + kf[3] * v3.y;
+                h[a].z = kf[0] * v0.z + kf[1] * v1.z + kf[2] * v2.z + kf[3] * v3.z;
+                h[a].w = kf[0] * v0.w + kf[1] * v1.w + kf[2] * v2.w + kf[3] * v3.w;
+            }
+        } else {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int xx = X + b - pad0;
-                    if (xx >= 0 && xx < Win) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(row + (size_t)xx * C));
-                        t.x += kf[b] * v.x; t.y += kf[b] * v.y; t.z += kf[b] * v.z; t.w += kf[b] * v.w;
+            for (int a = 0; a < FIR_ROWS + 3; ++a) {
+                const int yy = yy0 + a;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (yy >= 0 && yy < Hin) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int xx = xx0 + b;
+                        if (xx >= 0 && xx < Win) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(base + a * row_stride + (long long)b * C));
+                            t.x += kf[b] * v.x; t.y += kf[b] * v.y; t.z += kf[b] * v.z; t.w += kf[b] * v.w;
+                        }
                     }
                 }
+                h[a] = t;
             }
-            h[a] = t;
         }
         float al[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
@@ -115,8 +136,9 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
             if (split_scale) sc[k] = __ldg(split_scale + (size_t)n * split_scale_ld + c + k);
         }
         const bool f32 = out && n >= out_from_n;
+        const int chunk_stride = ((C + 31) >> 5) * 64;
 #pragma unroll
-        for (int oy = 0; oy < 4; ++oy) {
+        for (int oy = 0; oy < FIR_ROWS; ++oy) {
             const int Y = Y0 + oy;
             if (Y >= Hout) break;
             float v4[4];
@@ -139,7 +161,7 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
                 __align__(8) __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) split_bf16(v4[k] * sc[k], hi[k], lo[k]);
-                __nv_bfloat16* sp = out_split + pix * (size_t)(((C + 31) >> 5) * 64) + (size_t)(c >> 5) * 64 + (c & 31);
+                __nv_bfloat16* sp = out_split + pix * (size_t)chunk_stride + (size_t)(c >> 5) * 64 + (c & 31);
                 *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
                 *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
             }
@@ -301,7 +323,7 @@ extern "C" int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win,
                             int out_from_n, void* stream) {
     WGS_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "fir4_act: channels must be a multiple of 4");
     WGS_REQUIRE(taps4 != nullptr, "fir4_act: taps4 is a HOST pointer to 4 floats");
-    const long long total = (long long)N * ((Hout + 3) / 4) * Wout * (C / 4);
+    const long long total = (long long)N * ((Hout + FIR_ROWS - 1) / FIR_ROWS) * Wout * (C / 4);
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 48);
     fir4_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1],
                                                               taps4[2], taps4[3], alpha, beta, noise, noise_w, act,

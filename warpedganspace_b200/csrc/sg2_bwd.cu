@@ -146,6 +146,96 @@ sg2_torgb_bwd_kernel(const float* __restrict__ drgb, const float* __restrict__ a
     reduce_quads_to_global(acc, sm, C, C4, PL, ds + (size_t)n * ds_ld);
 }
 
+// One pass over a layer boundary of the data-gradient chain, fusing sg2_mod_bwd (of the layer above), sg2_torgb_bwd
+// and sg2_act_bwd (of this layer):
+//   da    = s_up[n,c] * dx_up            (gradient arriving through the next conv's modulated input; optional)
+//         + s_rgb[n,c] * sum_o drgb[o] * wscale * Wrgb[o,c]                         (ToRGB branch; optional)
+//   ds_up[n,c]  += sum_p dx_up * a ;   ds_rgb[n,c] += sum_p a * sum_o drgb[o] * wscale * Wrgb[o,c]
+//   dpre  = da * sqrt2 * (a > 0 ? 1 : 0.2) ;   dd[n,c] += sum_p dpre * (pre - nw*noise - b) / d
+//   out:  split32(d * dpre)  (operand of this layer's data-gradient conv)  and / or  dpre in fp32
+// Every tensor is read once: 3 reads + 1 write instead of the 9 passes of the three separate kernels.
+__global__ void __launch_bounds__(RED_THREADS)
+sg2_layer_bwd_kernel(const float* __restrict__ dx_up, const float* __restrict__ s_up, long long s_up_ld,
+                     float* __restrict__ ds_up, long long ds_up_ld, const float* __restrict__ drgb,
+                     const float* __restrict__ s_rgb, long long s_rgb_ld, const float* __restrict__ Wrgb, float wscale,
+                     float* __restrict__ ds_rgb, long long ds_rgb_ld, const float* __restrict__ a,
+                     const float* __restrict__ demod, const float* __restrict__ bias, const float* __restrict__ noise,
+                     float noise_w, float* __restrict__ dd, float* __restrict__ dpre, __nv_bfloat16* __restrict__ g_split,
+                     long long P, int C) {
+    extern __shared__ float sm[];
+    const int n = blockIdx.y;
+    const int C4 = C >> 2, PL = RED_THREADS / C4;
+    const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
+    const long long per = (P + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * per, p1 = min(P, p0 + per);
+    float dv[4], bv[4], su[4] = {0.f, 0.f, 0.f, 0.f}, sr[4] = {0.f, 0.f, 0.f, 0.f}, w[3][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = q * 4 + k;
+        dv[k] = __ldg(demod + (size_t)n * C + c);
+        bv[k] = __ldg(bias + c);
+        if (dx_up) su[k] = __ldg(s_up + (size_t)n * s_up_ld + c);
+        if (drgb) {
+            sr[k] = __ldg(s_rgb + (size_t)n * s_rgb_ld + c);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) w[o][k] = wscale * __ldg(Wrgb + (size_t)o * C + c);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) w[o][k] = 0.f;
+        }
+    }
+    float acc_u[4] = {0.f, 0.f, 0.f, 0.f}, acc_r[4] = {0.f, 0.f, 0.f, 0.f}, acc_d[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long p = p0 + pl; p < p1; p += PL) {
+        const size_t off = ((size_t)n * P + p) * C + q * 4;
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(a + off));
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+        float da[4] = {0.f, 0.f, 0.f, 0.f};
+        if (dx_up) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(dx_up + off));
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { acc_u[k] += gv[k] * av[k]; da[k] = gv[k] * su[k]; }
+        }
+        if (drgb) {
+            const float* g = drgb + ((size_t)n * P + p) * 3;
+            const float g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float t = g0 * w[0][k] + g1 * w[1][k] + g2 * w[2][k];
+                acc_r[k] += t * av[k];
+                da[k] += t * sr[k];
+            }
+        }
+        const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool pos = av[k] > 0.f;
+            const float pre = pos ? av[k] * (1.f / SQRT2) : av[k] * (1.f / (0.2f * SQRT2));
+            o[k] = da[k] * (pos ? SQRT2 : 0.2f * SQRT2);
+            acc_d[k] += o[k] * (pre - nz - bv[k]) / dv[k];
+        }
+        if (dpre) *reinterpret_cast<float4*>(dpre + off) = make_float4(o[0], o[1], o[2], o[3]);
+        if (g_split) {
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(o[k] * dv[k], hi[k], lo[k]);
+            __nv_bfloat16* sp = g_split + ((size_t)n * P + p) * (size_t)(C * 2) + (size_t)(q >> 3) * 64 + ((q & 7) << 2);
+            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+    reduce_quads_to_global(acc_d, sm, C, C4, PL, dd + (size_t)n * C);
+    if (dx_up) {
+        __syncthreads();
+        reduce_quads_to_global(acc_u, sm, C, C4, PL, ds_up + (size_t)n * ds_up_ld);
+    }
+    if (drgb) {
+        __syncthreads();
+        reduce_quads_to_global(acc_r, sm, C, C4, PL, ds_rgb + (size_t)n * ds_rgb_ld);
+    }
+}
+
 // Transpose of the FIR skip upsample (Upsample, model.py:29-45): drgb [N,H,W,3] -> dprev [N,H/2,W/2,3]
 //   dprev[i] = k0*d[2i-1] + k1*d[2i] + k2*d[2i+1] + k3*d[2i+2]   per axis
 __global__ void rgb_up_bwd_kernel(const float* __restrict__ drgb, float* __restrict__ dprev, int N, int H, int W,
@@ -233,6 +323,23 @@ extern "C" int wgs_sg2_rgb_up_bwd(const float* drgb, float* dprev, int N, int H,
     const long long total = (long long)N * (H / 2) * (W / 2);
     rgb_up_bwd_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16), 256, 0,
                         (cudaStream_t)stream>>>(drgb, dprev, N, H, W, k0, k1, k2, k3);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_sg2_layer_bwd(const float* dx_up, const float* s_up, long long s_up_ld, float* ds_up, long long ds_up_ld,
+                                 const float* drgb, const float* s_rgb, long long s_rgb_ld, const float* Wrgb, float wscale,
+                                 float* ds_rgb, long long ds_rgb_ld, const float* a, const float* demod, const float* bias,
+                                 const float* noise, float noise_w, float* dd, float* dpre, void* g_split, int N,
+                                 long long P, int C, void* stream) {
+    WGS_REQUIRE(red_ok(C), "sg2_layer_bwd: channel count must be a power of two in [4, 1024]");
+    WGS_REQUIRE(!g_split || C % 32 == 0, "sg2_layer_bwd: split32 output needs C % 32 == 0");
+    WGS_REQUIRE(dx_up || drgb, "sg2_layer_bwd: no incoming gradient");
+    const size_t smem = (size_t)(RED_THREADS / (C / 4)) * C * sizeof(float);
+    sg2_layer_bwd_kernel<<<dim3(red_blocks(P, N), N), RED_THREADS, smem, (cudaStream_t)stream>>>(
+        dx_up, s_up, s_up_ld, ds_up, ds_up_ld, drgb, s_rgb, s_rgb_ld, Wrgb, wscale, ds_rgb, ds_rgb_ld, a, demod, bias, noise,
+        noise_w, dd, dpre, (__nv_bfloat16*)g_split, P, C);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

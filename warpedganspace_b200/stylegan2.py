@@ -308,70 +308,75 @@ def synthesis(G, w, tape=None, grad_from=0):
 # ----------------------------------------------------------------------------------------------
 # backward (data gradient only)
 def synthesis_backward(G, tape, dimg):
-    """dimg [B, size, size, 3] NHWC -> d(loss)/dw [B, style_dim] using the activations recorded in `tape`."""
+    """dimg [B, size, size, 3] NHWC -> d(loss)/dw [B, style_dim] using the activations recorded in `tape`.
+
+    Per layer (top to bottom): one fused boundary kernel (incoming conv gradient * style + ToRGB branch -> dpre,
+    with the three style / demod reductions), [transposed FIR for up-sampling layers], one tensor-core
+    data-gradient conv."""
     P = G.plan()
     s_all, demod, acts = tape['s_all'], tape['demod'], tape['acts']
     B = s_all.shape[0]
     dev = s_all.device
     ds_all = torch.zeros_like(s_all)
     drgb = dimg.contiguous()
-    da = None
     st = _lib.stream
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
 
     def sl(t, e):
         return t[:, e['s_off']: e['s_off'] + e['ci']]
 
+    dx_up, up_e = None, None                     # gradient w.r.t. the modulated input of the layer above, and that layer
     for li in range(len(P['styled']) - 1, -1, -1):
         e = P['styled'][li]
-        a, a_prev = acts[li + 1], acts[li]
+        a = acts[li + 1]
         n, h, wd, co = a.shape
         npix = h * wd
-        if not e['up']:
-            # this activation also feeds ToRGB number li // 2
-            r = P['rgb'][li // 2]
-            s_r, ds_r = sl(s_all, r), sl(ds_all, r)
-            acc = da is not None
-            if da is None:
-                da = torch.empty_like(a)
-            _lib.call('wgs_sg2_torgb_bwd', _lib.ptr(drgb), _lib.ptr(a), ctypes.c_void_p(s_r.data_ptr()), s_r.stride(0),
-                      _lib.ptr(r['w']), r['scale'], _lib.ptr(da), int(acc), ctypes.c_void_p(ds_r.data_ptr()),
-                      ds_r.stride(0), n, npix, co, st())
-            if li > 0:
-                dprev = torch.empty(n, h // 2, wd // 2, 3, device=dev, dtype=torch.float32)
-                _lib.call('wgs_sg2_rgb_up_bwd', _lib.ptr(drgb), _lib.ptr(dprev), n, h, wd, _TAPS, st())
-                drgb = dprev
+        has_rgb = not e['up']
+        r = P['rgb'][li // 2] if has_rgb else None
         dd = torch.zeros(n, co, device=dev, dtype=torch.float32)
         if e['up']:
-            # dpre (fp32, in place) -> transposed blur * demod written straight as the split32 conv operand
-            _lib.call('wgs_sg2_act_bwd', _lib.ptr(da), _lib.ptr(a), _lib.ptr(demod[li]), _lib.ptr(e['bias']),
-                      _lib.ptr(P['noise'][li]), e['noise_w'], _lib.ptr(da), _lib.ptr(dd), None, n, npix, co, st())
+            dpre = torch.empty_like(a)
+            gs = None
+        else:
+            dpre = None
+            gs = torch.empty(n, h, wd, co // 32, 64, device=dev, dtype=torch.bfloat16)
+        s_u = sl(s_all, up_e) if dx_up is not None else None
+        ds_u = sl(ds_all, up_e) if dx_up is not None else None
+        s_r = sl(s_all, r) if has_rgb else None
+        ds_r = sl(ds_all, r) if has_rgb else None
+        _lib.call('wgs_sg2_layer_bwd',
+                  _lib.ptr(dx_up), vp(s_u) if s_u is not None else None, s_u.stride(0) if s_u is not None else 0,
+                  vp(ds_u) if ds_u is not None else None, ds_u.stride(0) if ds_u is not None else 0,
+                  _lib.ptr(drgb) if has_rgb else None, vp(s_r) if has_rgb else None, s_r.stride(0) if has_rgb else 0,
+                  _lib.ptr(r['w']) if has_rgb else None, r['scale'] if has_rgb else 0.0,
+                  vp(ds_r) if has_rgb else None, ds_r.stride(0) if has_rgb else 0,
+                  _lib.ptr(a), _lib.ptr(demod[li]), _lib.ptr(e['bias']), _lib.ptr(P['noise'][li]), e['noise_w'],
+                  _lib.ptr(dd), _lib.ptr(dpre), _lib.ptr(gs), n, npix, co, st())
+        if has_rgb and li > 0:
+            dprev = torch.empty(n, h // 2, wd // 2, 3, device=dev, dtype=torch.float32)
+            _lib.call('wgs_sg2_rgb_up_bwd', _lib.ptr(drgb), _lib.ptr(dprev), n, h, wd, _TAPS, st())
+            drgb = dprev
+        if e['up']:
+            # transposed blur * demod written straight as the split32 operand of the strided data-gradient conv
             hi, wi = h // 2, wd // 2
             gs = torch.empty(n, h + 1, wd + 1, co // 32, 64, device=dev, dtype=torch.bfloat16)
-            _lib.call('wgs_fir4_act', _lib.ptr(da), None, n, h, wd, h + 1, wd + 1, co, 2, _TAPS,
+            _lib.call('wgs_fir4_act', _lib.ptr(dpre), None, n, h, wd, h + 1, wd + 1, co, 2, _TAPS,
                       _lib.ptr(demod[li]), None, None, 0.0, 0, _lib.ptr(gs), None, 0, 0, st())
             dx = C.conv2d(gs, e['w_bwd'], 3, 3, stride=2, padding=0, cout=e['ci'])       # [n, hi, wi, ci]
             assert dx.shape[1] == hi and dx.shape[2] == wi
         else:
-            gs = torch.empty(n, h, wd, co // 32, 64, device=dev, dtype=torch.bfloat16)
-            _lib.call('wgs_sg2_act_bwd', _lib.ptr(da), _lib.ptr(a), _lib.ptr(demod[li]), _lib.ptr(e['bias']),
-                      _lib.ptr(P['noise'][li]), e['noise_w'], None, _lib.ptr(dd), _lib.ptr(gs), n, npix, co, st())
             dx = C.conv2d(gs, e['w_bwd'], 3, 3, padding=1, cout=e['ci'])
-        s_e, ds_e = sl(s_all, e), sl(ds_all, e)
-        pin = dx.shape[1] * dx.shape[2]
-        if li == 0:
-            _lib.call('wgs_sg2_mod_bwd', _lib.ptr(dx), _lib.ptr(P['const']), 1, ctypes.c_void_p(s_e.data_ptr()),
-                      s_e.stride(0), None, 0, ctypes.c_void_p(ds_e.data_ptr()), ds_e.stride(0), n, pin, e['ci'], st())
-            da = None
-        else:
-            da = torch.empty_like(a_prev)
-            _lib.call('wgs_sg2_mod_bwd', _lib.ptr(dx), _lib.ptr(a_prev), 0, ctypes.c_void_p(s_e.data_ptr()),
-                      s_e.stride(0), _lib.ptr(da), 0, ctypes.c_void_p(ds_e.data_ptr()), ds_e.stride(0), n, pin,
-                      e['ci'], st())
         # demodulation: d = rsqrt(scale^2 sum_i s_i^2 Wsq[o,i] + eps)  ->  ds_i += s_i * sum_o (-dd_o d_o^3 scale^2) Wsq[o,i]
+        s_e, ds_e = sl(s_all, e), sl(ds_all, e)
         t = (dd * demod[li].pow(3)).mul_(-(e['scale'] ** 2))
         u = torch.empty(n, e['ci'], device=dev, dtype=torch.float32)
         _linear(t, e['wsq_t'], None, u)
         ds_e.add_(u * s_e)
+        if li == 0:
+            pin = dx.shape[1] * dx.shape[2]
+            _lib.call('wgs_sg2_mod_bwd', _lib.ptr(dx), _lib.ptr(P['const']), 1, vp(s_e), s_e.stride(0), None, 0,
+                      vp(ds_e), ds_e.stride(0), n, pin, e['ci'], st())
+        dx_up, up_e = dx, e
     dw = torch.empty(B, G.style_dim, device=dev, dtype=torch.float32)
     _linear(ds_all, P['mod_w_t'], None, dw, wscale=1.0 / math.sqrt(G.style_dim))
     return dw
