@@ -164,7 +164,9 @@ int wgs_sg2_layer_bwd(const float* dx_up, const float* s_up, long long s_up_ld, 
 /* Fused Adam over a flat fp32 buffer, torch.optim.Adam defaults semantics (lib/trainer.py:153-156,253-254);
  * the gradient is multiplied by grad_scale first (1/world_size after the NCCL sum).                  */
 int wgs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
-                  float eps, int step, float grad_scale, void* stream);
+                  float eps, int step, float grad_scale, const int* step_dev, void* stream);
+/* step_dev (device int) replaces `step` when non-NULL so that the launch can be replayed from a CUDA graph. */
+int wgs_step_increment(int* step_dev, void* stream);
 
 /* im2col into split32 for few-input-channel convs (ResNet stem 7x7/2 on 6 channels, lib/reconstructor.py:56-60):
  * x fp32 NHWC [N,H,W,C] -> out split32 [N,OH,OW,ceil(kh*kw*C/32),64], K index = (ky*kw+kx)*C + c.             */

@@ -132,3 +132,34 @@ def test_full_size_properties():
     assert rel(out['img'], alone) < 1e-6
     delta = (S.SUPPORT_SETS.detach().cpu() - s_sd['SUPPORT_SETS']).abs().sum(dim=1)
     assert set(delta.nonzero().flatten().tolist()) == {5, 77}
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured step (forward + backward + Adam, device-side step counter) replays to the same parameters and
+    losses as eager execution."""
+    from warpedganspace_b200.trainer import PairedTrainer
+    ch = {4: 64, 8: 64, 16: 32, 32: 32}
+    K, D, B, size = 16, 4, 4, 32
+    g = gen(50)
+    batches = [(torch.randn(B, 512, generator=g).cuda(), torch.randint(0, K, (B,), generator=g).cuda(),
+                o_step.sample_shift_magnitudes(B, 0.1, 0.2, generator=g).cuda()) for _ in range(4)]
+    results = []
+    for use_graph in (False, True):
+        _, (W, S, R) = build(size, ch, K, D, 60)
+        T = PairedTrainer(W, S, R)
+        if use_graph:
+            # capture() runs warm-up steps that update the parameters: restore the initial state afterwards
+            s0 = T.flat_s.flat.clone(); r0 = T.flat_r.flat.clone()
+            bn0 = {k: v.clone() for k, v in R.state_dict().items() if 'running' in k or 'num_batches' in k}
+            assert T.capture(*batches[0]), getattr(T, 'capture_error', None)
+            T.flat_s.flat.copy_(s0); T.flat_r.flat.copy_(r0)
+            for f in (T.flat_s, T.flat_r):
+                f.exp_avg.zero_(); f.exp_avg_sq.zero_(); f.step_dev.zero_(); f.step_count = 0
+            R.load_state_dict({**R.state_dict(), **bn0})
+        losses = [float(T.step(*b)['loss']) for b in batches]
+        torch.cuda.synchronize()
+        results.append((losses, T.flat_s.flat.clone(), T.flat_r.flat.clone()))
+    (l0, s0, r0), (l1, s1, r1) = results
+    assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-4 * max(abs(x) for x in l0)
+    assert rel(s1, s0) < 1e-6
+    assert rel(r1 - r0.mean() * 0, r0) < 1e-4

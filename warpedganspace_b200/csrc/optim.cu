@@ -8,7 +8,13 @@ namespace wgs {
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
+            const int* __restrict__ step_ptr) {
+    if (step_ptr) {                      // step counter lives on the device (CUDA-graph replay): derive the corrections here
+        const double st = (double)(*step_ptr);
+        bc1 = (float)(1.0 - pow((double)b1, st));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, st));
+    }
     const long long n4 = n >> 2;
     const float step = lr / bc1;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -41,20 +47,28 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
-}  // namespace wgs
+__global__ void step_inc_kernel(int* step) { *step += 1; }
 
+}  // namespace wgs
 using namespace wgs;
 
+extern "C" int wgs_step_increment(int* step_dev, void* stream) {
+    step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int wgs_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
-                             float eps, int step, float grad_scale, void* stream) {
-    WGS_REQUIRE(n >= 0 && step >= 1, "adam_step: bad arguments");
+                             float eps, int step, float grad_scale, const int* step_dev, void* stream) {
+    WGS_REQUIRE(n >= 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
     WGS_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0,
                 "adam_step: buffers must be 16-byte aligned");
     if (n == 0) return 0;
-    const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+    const double bc1 = 1.0 - pow((double)b1, std::max(1, step)), bc2 = 1.0 - pow((double)b2, std::max(1, step));
     const int blocks = (int)std::min<long long>((n / 4 + 255) / 256 + 1, (long long)num_sms() * 8);
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2),
-                                                         grad_scale);
+                                                         grad_scale, step_dev);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

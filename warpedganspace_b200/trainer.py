@@ -47,6 +47,7 @@ class FlatParams:
                 p.grad = self.grad[off: off + p.numel()].view_as(p)
                 off += sz
         self.step_count = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)      # device-side step counter (graph replay)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -56,10 +57,12 @@ class FlatParams:
                 raise RuntimeError('parameter gradient left the flat buffer')
 
     def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        # the step counter lives on the device so that the same launches can be replayed from a CUDA graph
         self.step_count += 1
+        _lib.call('wgs_step_increment', _lib.ptr(self.step_dev), _lib.stream())
         _lib.call('wgs_adam_step', _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
                   _lib.ptr(self.exp_avg_sq), self.n, float(lr), float(betas[0]), float(betas[1]), float(eps),
-                  self.step_count, float(grad_scale), _lib.stream())
+                  0, float(grad_scale), _lib.ptr(self.step_dev), _lib.stream())
 
 
 def sample_shift_magnitudes(batch, min_mag, max_mag, device, generator=None):
@@ -123,7 +126,53 @@ class PairedTrainer:
         self.flat_r.adam_step(self.lr_r, grad_scale=scale)                            # :254
 
     def step(self, z, indices, magnitudes):
+        if self._graph is not None:
+            return self._replay(z, indices, magnitudes)
         out = self.forward_backward(z, indices, magnitudes)
         self.all_reduce_gradients()
         self.optimizer_step()
         return out
+
+    # ---- CUDA-graph mode: the whole step (≈330 of our launches + ≈500 small ATen ones) becomes one graph launch ----
+    _graph = None
+
+    def capture(self, z, indices, magnitudes, warmup=3):
+        """Capture forward + backward + all-reduce + both Adam updates for this batch shape.  Afterwards step()
+        copies its arguments into the static inputs and replays.  Returns True on success; on failure the trainer
+        stays in eager mode (still entirely on the CUDA kernels)."""
+        self._static_in = (z.clone(), indices.clone(), magnitudes.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self.forward_backward(*self._static_in)
+                    self.all_reduce_gradients()
+                    self.optimizer_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out = self.forward_backward(*self._static_in)
+                self.all_reduce_gradients()
+                self.optimizer_step()
+            self.launches_per_step = _lib.launch_count() - before
+            self._static_out = out
+            self._graph = graph
+            return True
+        except Exception as e:                                   # pragma: no cover - depends on driver / NCCL support
+            self._graph = None
+            self.capture_error = repr(e)
+            torch.cuda.synchronize()
+            return False
+
+    def _replay(self, z, indices, magnitudes):
+        zi, ii, mi = self._static_in
+        zi.copy_(z, non_blocking=True)
+        ii.copy_(indices, non_blocking=True)
+        mi.copy_(magnitudes, non_blocking=True)
+        self._graph.replay()
+        self.flat_s.step_count += 1
+        self.flat_r.step_count += 1
+        return self._static_out
