@@ -213,26 +213,8 @@ def main():
     total = args.warmup + args.steps
     batches = make_batches(total, B, device, seed=1000 + rank)
 
-    # ---- instrumented eager steps: per-launch CUDA-event timing of the tensor-core kernels (roofline) -----------------
-    # (events cannot be recorded inside a CUDA graph, so the per-launch numbers come from these eager steps of the
-    #  same workload; the whole-step numbers below come from the timed region proper)
-    for i in range(args.warmup):
-        trainer.step(*batches[i])
-    torch.cuda.synchronize()
-    C.PROFILE = []
-    _lib.reset_launch_count()
-    n_prof = min(args.steps, 5)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(args.warmup, args.warmup + n_prof):
-        trainer.step(*batches[i])
-    p1.record()
-    torch.cuda.synchronize()
-    launches = _lib.launch_count() / n_prof
-    prof, C.PROFILE = C.PROFILE, None
-    prof_ms_total = p0.elapsed_time(p1)
-
     # ---- device-resident run: `value` -----------------------------------------------------------------
+    # (capture first: a CUDA graph must be captured before any eager backward pass, see PairedTrainer.capture)
     graphed = False
     if not args.no_graph:
         graphed = trainer.capture(*batches[0])
@@ -257,6 +239,45 @@ def main():
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
 
+    # ---- end-to-end run through the public API with host buffers: `e2e` ---------------------------------------
+    host = make_batches(total, B, device, seed=2000 + rank, pinned=True)
+    def e2e_step(hb):
+        z, idx, mag = (t.to(device, non_blocking=True) for t in hb)
+        out = trainer.step(z, idx, mag)
+        return float(out['loss'].item())                       # device -> host read of the step's result
+    for i in range(args.warmup):
+        e2e_step(host[i])
+    torch.cuda.synchronize()
+    wdist.barrier()
+    e0.record()
+    for i in range(args.warmup, total):
+        e2e_step(host[i])
+    e1.record()
+    torch.cuda.synchronize()
+    wdist.barrier()
+    e2e_ms = wdist.max_over_ranks(e0.elapsed_time(e1), device) / args.steps
+    e2e = {'value': world * B / (e2e_ms / 1e3), 'unit': 'pairs/s', 'ms_per_step': e2e_ms,
+           'h2d_bytes_per_step': B * (DIM * 4 + 8 + 4), 'd2h_bytes_per_step': 4}
+
+    # ---- instrumented eager steps: per-launch CUDA-event timing of the tensor-core kernels (roofline) -----------------
+    # (events cannot be recorded inside a CUDA graph, so the per-launch numbers come from eager steps of the same
+    #  workload run right after the timed regions)
+    for i in range(2):
+        trainer.step(*batches[i], eager=True)
+    torch.cuda.synchronize()
+    C.PROFILE = []
+    _lib.reset_launch_count()
+    n_prof = min(args.steps, 5)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(args.warmup, args.warmup + n_prof):
+        trainer.step(*batches[i], eager=True)
+    p1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() / n_prof
+    prof, C.PROFILE = C.PROFILE, None
+    prof_ms_total = p0.elapsed_time(p1)
+
     # ---- roofline of the dominant kernel (tensor-core conv), per launch, from the same timed region -------
     pk = peaks()
     conv = [(fl, a.elapsed_time(b)) for kind, fl, a, b in prof if kind == 'conv']
@@ -277,26 +298,6 @@ def main():
                          'launches': len(wg), 'share_of_step': sum(t for _, t in wg) / prof_ms_total if prof_ms_total else None},
         'whole_step_algorithmic_tflops': ALGO_FLOPS_PER_PAIR * B / (ms_step * 1e-3) / 1e12,
     }
-
-    # ---- end-to-end run through the public API with host buffers: `e2e` ---------------------------------------
-    host = make_batches(total, B, device, seed=2000 + rank, pinned=True)
-    def e2e_step(hb):
-        z, idx, mag = (t.to(device, non_blocking=True) for t in hb)
-        out = trainer.step(z, idx, mag)
-        return float(out['loss'].item())                       # device -> host read of the step's result
-    for i in range(args.warmup):
-        e2e_step(host[i])
-    torch.cuda.synchronize()
-    wdist.barrier()
-    e0.record()
-    for i in range(args.warmup, total):
-        e2e_step(host[i])
-    e1.record()
-    torch.cuda.synchronize()
-    wdist.barrier()
-    e2e_ms = wdist.max_over_ranks(e0.elapsed_time(e1), device) / args.steps
-    e2e = {'value': world * B / (e2e_ms / 1e3), 'unit': 'pairs/s', 'ms_per_step': e2e_ms,
-           'h2d_bytes_per_step': B * (DIM * 4 + 8 + 4), 'd2h_bytes_per_step': 4}
 
     if rank != 0:
         return

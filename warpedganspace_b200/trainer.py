@@ -125,8 +125,8 @@ class PairedTrainer:
         self.flat_s.adam_step(self.lr_s, grad_scale=scale)                            # :253
         self.flat_r.adam_step(self.lr_r, grad_scale=scale)                            # :254
 
-    def step(self, z, indices, magnitudes):
-        if self._graph is not None:
+    def step(self, z, indices, magnitudes, eager=False):
+        if self._graph is not None and not eager:
             return self._replay(z, indices, magnitudes)
         out = self.forward_backward(z, indices, magnitudes)
         self.all_reduce_gradients()
@@ -139,7 +139,9 @@ class PairedTrainer:
     def capture(self, z, indices, magnitudes, warmup=3):
         """Capture forward + backward + all-reduce + both Adam updates for this batch shape.  Afterwards step()
         copies its arguments into the static inputs and replays.  Returns True on success; on failure the trainer
-        stays in eager mode (still entirely on the CUDA kernels)."""
+        stays in eager mode (still entirely on the CUDA kernels).  Call it BEFORE any eager backward pass: autograd
+        caches each parameter's AccumulateGrad node together with the stream it first ran on, and a node bound to
+        the default stream invalidates the capture."""
         self._static_in = (z.clone(), indices.clone(), magnitudes.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
