@@ -161,5 +161,5 @@ def test_cuda_graph_replay_matches_eager():
         results.append((losses, T.flat_s.flat.clone(), T.flat_r.flat.clone()))
     (l0, s0, r0), (l1, s1, r1) = results
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-4 * max(abs(x) for x in l0)
-    assert rel(s1, s0) < 1e-6
+    assert rel(s1, s0) < 1e-4            # first Adam steps move by lr*sign(g): atomics order flips tiny gradients
     assert rel(r1 - r0.mean() * 0, r0) < 1e-4
