@@ -173,6 +173,20 @@ int wgs_step_increment(int* step_dev, void* stream);
 int wgs_im2col_split32(const float* x, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
                        int OH, int OW, void* out, void* stream);
 
+/* ---- Reconstructor BatchNorm (train mode) fused with residual / ReLU / operand packing (csrc/bn.cu) -------------- *
+ * Replaces cuDNN batch_norm fwd/bwd + ATen relu / add around every torchvision BasicBlock conv
+ * (lib/reconstructor.py:54-69; train mode per lib/trainer.py:150).  Tensors are NHWC [R = N*H*W, C] fp32.         */
+int wgs_bn_stats(const float* y, long long R, int C, float* sum, float* sumsq, void* stream);   /* accumulates */
+int wgs_bn_finalize(const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
+                    float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+int wgs_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   const float* residual, int relu, float* z, void* zs, long long R, int C, void* stream);
+int wgs_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                          int relu, long long R, int C, float* sum_dz, float* sum_dzx, void* stream);  /* accumulates */
+int wgs_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                         const float* gamma, const float* sum_dz, const float* sum_dzx, int relu, long long R,
+                         int C, void* dys, float* dy, float* dres, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

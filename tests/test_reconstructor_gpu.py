@@ -17,14 +17,17 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-300))
 
 
-@pytest.mark.parametrize('name', ['resnet', 'lenet'])
+@pytest.mark.parametrize('name', ['resnet', 'resnet_unfused', 'lenet'])
 def test_reconstructor_fixture(golden, name):
+    fused = name != 'resnet_unfused'
+    name = 'resnet' if name.startswith('resnet') else name
     from warpedganspace_b200.reconstructor import Reconstructor
     torch.backends.cudnn.allow_tf32 = False
     fx = golden('reconstructor_%s.pt' % name)
     sd = o_rec.init_state(fx['type'], fx['dim'], fx['channels'], generator=gen(fx['seed']))
     R = Reconstructor(fx['type'], fx['dim'], fx['channels'])
     R.load_state_dict(sd, strict=True)
+    R.fused = fused
     R.cuda().train()
     x1 = fx['x1'].cuda().requires_grad_(True)
     x2 = fx['x2'].cuda().requires_grad_(True)

@@ -1,0 +1,236 @@
+// Train-mode BatchNorm (+ residual + ReLU) for the Reconstructor, fused with the operand packing of the next
+// convolution.  Replaces, per conv block, cuDNN batch-norm forward/backward, ATen relu / threshold_backward / add and a
+// separate split32 pack (lib/reconstructor.py:54-69 -> torchvision BasicBlock; train mode set at lib/trainer.py:150):
+//   forward : bn_stats (one read of y)  ->  bn_act_fwd (y [, residual] -> z fp32 and split32(z))
+//   backward: bn_act_bwd_reduce (dz, z, y -> sum dzr, sum dzr*xhat)  ->  bn_act_bwd_apply (-> split32(dy) [, dzr])
+// All tensors are NHWC [R, C] (R = N*H*W rows); C is a multiple of 4 with (C/4) dividing 256.
+#include "common.cuh"
+#include "wgs_b200.h"
+
+namespace wgs {
+
+constexpr int BN_THREADS = 256;
+
+__device__ __forceinline__ void bn_reduce2_to_global(const float a[4], const float b[4], float* sm, int C, int C4, int PL,
+                                                     float* dst_a, float* dst_b) {
+    const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
+    float* sa = sm;
+    float* sb = sm + (size_t)PL * C;
+    *reinterpret_cast<float4*>(sa + (size_t)pl * C + q * 4) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(sb + (size_t)pl * C + q * 4) = make_float4(b[0], b[1], b[2], b[3]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+        float ta = 0.f, tb = 0.f;
+        for (int l = 0; l < PL; ++l) { ta += sa[(size_t)l * C + c]; tb += sb[(size_t)l * C + c]; }
+        atomicAdd(dst_a + c, ta);
+        atomicAdd(dst_b + c, tb);
+    }
+}
+
+// sum[c] += sum_r y[r,c];  sumsq[c] += sum_r (y[r,c] - shift[c])^2-free form: plain sum of squares (fp32; |mean| ~ std here)
+__global__ void __launch_bounds__(BN_THREADS)
+bn_stats_kernel(const float* __restrict__ y, long long R, int C, float* __restrict__ sum, float* __restrict__ sumsq) {
+    extern __shared__ float sm[];
+    const int C4 = C >> 2, PL = BN_THREADS / C4;
+    const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
+    const long long per = (R + gridDim.x - 1) / gridDim.x;
+    const long long r0 = blockIdx.x * per, r1 = min(R, r0 + per);
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long r = r0 + pl; r < r1; r += PL) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + q * 4));
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
+    }
+    bn_reduce2_to_global(a, b, sm, C, C4, PL, sum, sumsq);
+}
+
+// mean / rstd from the sums, running-stat update (momentum, unbiased variance), one thread per channel
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long R, int C,
+                                   float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = (double)sum[c] / (double)R;
+    double var = (double)sumsq[c] / (double)R - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// z = [relu]( gamma * (y - mean) * rstd + beta [+ residual] );  writes z (fp32, optional) and split32(z) (optional)
+__global__ void __launch_bounds__(BN_THREADS)
+bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
+                  int relu, float* __restrict__ z, __nv_bfloat16* __restrict__ zs, long long R, int C) {
+    const int C4 = C >> 2;
+    const long long total = R * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % C4);
+        const long long r = i / C4;
+        const int c = q * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float o[4] = {(v.x - m4.x) * s4.x * g4.x + b4.x, (v.y - m4.y) * s4.y * g4.y + b4.y,
+                      (v.z - m4.z) * s4.z * g4.z + b4.z, (v.w - m4.w) * s4.w * g4.w + b4.w};
+        if (residual) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(residual + r * C + c));
+            o[0] += e.x; o[1] += e.y; o[2] += e.z; o[3] += e.w;
+        }
+        if (relu) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = o[k] > 0.f ? o[k] : 0.f;
+        }
+        if (z) *reinterpret_cast<float4*>(z + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (zs) {
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(o[k], hi[k], lo[k]);
+            __nv_bfloat16* sp = zs + r * (long long)(((C + 31) >> 5) * 64) + (c >> 5) * 64 + (c & 31);
+            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+}
+
+// dzr = dz * (relu ? z > 0 : 1);  sum_dz[c] += sum_r dzr;  sum_dzx[c] += sum_r dzr * (y - mean) * rstd
+__global__ void __launch_bounds__(BN_THREADS)
+bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, int relu, long long R, int C,
+                         float* __restrict__ sum_dz, float* __restrict__ sum_dzx) {
+    extern __shared__ float sm[];
+    const int C4 = C >> 2, PL = BN_THREADS / C4;
+    const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
+    const long long per = (R + gridDim.x - 1) / gridDim.x;
+    const long long r0 = blockIdx.x * per, r1 = min(R, r0 + per);
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + q * 4));
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(rstd + q * 4));
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long r = r0 + pl; r < r1; r += PL) {
+        const long long off = r * C + q * 4;
+        float4 g = __ldg(reinterpret_cast<const float4*>(dz + off));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y + off));
+        if (relu) {
+            const float4 zz = __ldg(reinterpret_cast<const float4*>(z + off));
+            g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f;
+            g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
+        }
+        a[0] += g.x; a[1] += g.y; a[2] += g.z; a[3] += g.w;
+        b[0] += g.x * (v.x - m4.x) * s4.x; b[1] += g.y * (v.y - m4.y) * s4.y;
+        b[2] += g.z * (v.z - m4.z) * s4.z; b[3] += g.w * (v.w - m4.w) * s4.w;
+    }
+    bn_reduce2_to_global(a, b, sm, C, C4, PL, sum_dz, sum_dzx);
+}
+
+// dy = gamma * rstd * (dzr - sum_dz/R - xhat * sum_dzx/R)  -> split32 (operand of the dgrad / wgrad convs) and/or fp32;
+// dres = dzr (gradient of the residual branch, optional)
+__global__ void __launch_bounds__(BN_THREADS)
+bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
+                        const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                        const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx, int relu, long long R, int C,
+                        __nv_bfloat16* __restrict__ dys, float* __restrict__ dy, float* __restrict__ dres) {
+    const int C4 = C >> 2;
+    const long long total = R * C4;
+    const float inv_r = 1.f / (float)R;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % C4);
+        const long long r = i / C4;
+        const int c = q * 4;
+        const long long off = r * C + c;
+        float4 g = __ldg(reinterpret_cast<const float4*>(dz + off));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y + off));
+        if (relu) {
+            const float4 zz = __ldg(reinterpret_cast<const float4*>(z + off));
+            g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f;
+            g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
+        }
+        if (dres) *reinterpret_cast<float4*>(dres + off) = g;
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(sum_dz + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(sum_dzx + c));
+        float o[4];
+        o[0] = g4.x * s4.x * (g.x - a4.x * inv_r - (v.x - m4.x) * s4.x * b4.x * inv_r);
+        o[1] = g4.y * s4.y * (g.y - a4.y * inv_r - (v.y - m4.y) * s4.y * b4.y * inv_r);
+        o[2] = g4.z * s4.z * (g.z - a4.z * inv_r - (v.z - m4.z) * s4.z * b4.z * inv_r);
+        o[3] = g4.w * s4.w * (g.w - a4.w * inv_r - (v.w - m4.w) * s4.w * b4.w * inv_r);
+        if (dy) *reinterpret_cast<float4*>(dy + off) = make_float4(o[0], o[1], o[2], o[3]);
+        if (dys) {
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(o[k], hi[k], lo[k]);
+            __nv_bfloat16* sp = dys + r * (long long)(((C + 31) >> 5) * 64) + (c >> 5) * 64 + (c & 31);
+            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+}
+
+static bool bn_ok(int C) { return C >= 4 && C % 4 == 0 && (C / 4) <= BN_THREADS && BN_THREADS % (C / 4) == 0; }
+static int bn_red_blocks(long long R) { return (int)std::max<long long>(1, std::min<long long>((long long)num_sms() * 8, (R + 63) / 64)); }
+static int bn_ew_blocks(long long total) { return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)num_sms() * 32)); }
+
+}  // namespace wgs
+
+using namespace wgs;
+
+extern "C" int wgs_bn_stats(const float* y, long long R, int C, float* sum, float* sumsq, void* stream) {
+    WGS_REQUIRE(bn_ok(C) && R > 0, "bn_stats: C must be a multiple of 4 with C/4 dividing 256");
+    const size_t smem = 2 * (size_t)(BN_THREADS / (C / 4)) * C * sizeof(float);
+    bn_stats_kernel<<<bn_red_blocks(R), BN_THREADS, smem, (cudaStream_t)stream>>>(y, R, C, sum, sumsq);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_bn_finalize(const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
+                               float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
+    WGS_REQUIRE(C > 0 && R > 0, "bn_finalize: bad sizes");
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, R, C, eps, momentum, mean, rstd,
+                                                                         running_mean, running_var);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                              const float* residual, int relu, float* z, void* zs, long long R, int C, void* stream) {
+    WGS_REQUIRE(C % 4 == 0 && R > 0, "bn_act_fwd: C must be a multiple of 4");
+    bn_act_fwd_kernel<<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        y, mean, rstd, gamma, beta, residual, relu, z, (__nv_bfloat16*)zs, R, C);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                                     int relu, long long R, int C, float* sum_dz, float* sum_dzx, void* stream) {
+    WGS_REQUIRE(bn_ok(C) && R > 0, "bn_act_bwd_reduce: C must be a multiple of 4 with C/4 dividing 256");
+    const size_t smem = 2 * (size_t)(BN_THREADS / (C / 4)) * C * sizeof(float);
+    bn_act_bwd_reduce_kernel<<<bn_red_blocks(R), BN_THREADS, smem, (cudaStream_t)stream>>>(dz, z, y, mean, rstd, relu, R, C,
+                                                                                         sum_dz, sum_dzx);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                                    const float* gamma, const float* sum_dz, const float* sum_dzx, int relu, long long R,
+                                    int C, void* dys, float* dy, float* dres, void* stream) {
+    WGS_REQUIRE(C % 4 == 0 && R > 0, "bn_act_bwd_apply: C must be a multiple of 4");
+    bn_act_bwd_apply_kernel<<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        dz, z, y, mean, rstd, gamma, sum_dz, sum_dzx, relu, R, C, (__nv_bfloat16*)dys, dy, dres);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}

@@ -110,14 +110,14 @@ class _StemConvFn(torch.autograd.Function):
         return dx, dw, None, None
 
 
-def conv_dgrad(dys, w, in_hw, stride, padding):
+def conv_dgrad(dys, w, in_hw, stride, padding, out=None, accumulate=False):
     """Data gradient of F.conv2d: dx[iy,ix,ci] = sum_{ky,kx,co} dy[(iy+p-ky)/s, (ix+p-kx)/s, co] * w[co,ci,ky,kx]
     (terms with non-integer quotients vanish).  stride 1: one flipped-tap conv; stride s: s*s output phases."""
     co, ci, kh, kw = w.shape
     h, wd = in_hw
     n, oh, ow = dys.shape[0], dys.shape[1], dys.shape[2]
     wt = _packed(w, True)                                                   # [kh*kw, Ci, Co]
-    dx = torch.empty(n, h, wd, ci, device=dys.device, dtype=torch.float32)
+    dx = out if out is not None else torch.empty(n, h, wd, ci, device=dys.device, dtype=torch.float32)
     for py in range(stride):
         for px in range(stride):
             gh = (h - py + stride - 1) // stride
@@ -127,11 +127,13 @@ def conv_dgrad(dys, w, in_hw, stride, padding):
             kys = [ky for ky in range(kh) if (py + padding - ky) % stride == 0]
             kxs = [kx for kx in range(kw) if (px + padding - kx) % stride == 0]
             if not kys or not kxs:
-                dx[:, py::stride, px::stride, :] = 0
+                if not accumulate:
+                    dx[:, py::stride, px::stride, :] = 0
                 continue
             taps = [((py + padding - ky) // stride, (px + padding - kx) // stride, ky * kw + kx)
                     for ky in kys for kx in kxs]
-            C.conv_taps(dys, wt, taps, dx, grid=(gh, gw), out_origin=(py, px), out_step=(stride, stride), cout=ci, cin=co)
+            C.conv_taps(dys, wt, taps, dx, grid=(gh, gw), out_origin=(py, px), out_step=(stride, stride), cout=ci, cin=co,
+                        accumulate=accumulate)
     return dx
 
 
@@ -194,6 +196,7 @@ class Reconstructor(nn.Module):
         self.reconstructor_type = reconstructor_type
         self.dim = dim
         self.channels = channels
+        self.fused = True            # ResNet trunk as one hand-scheduled autograd node (train mode); False = per-op autograd
         if reconstructor_type == 'LeNet':
             self.lenet_width = 2
             fe = nn.ModuleList([nn.Identity() for _ in range(11)])
@@ -218,6 +221,9 @@ class Reconstructor(nn.Module):
             x = F.relu(fe[9](conv2d(x, fe[8].weight, fe[8].bias)))
             return x.mean(dim=[-1, -2]).view(x.shape[0], -1)
         r = self.features_extractor
+        if self.fused and self.training:
+            from .resnet_fused import ResNetFeatures
+            return ResNetFeatures.apply(x, r, *ResNetFeatures.param_list(r))
         x = F.relu(r.bn1(conv2d(x, r.conv1.weight, None, 2, 3)))
         x = F.max_pool2d(x, 3, 2, 1)
         for li in range(1, 5):
