@@ -53,6 +53,9 @@ struct ConvKernelParams {
     int out_from_n;              // fp32 `out` is written only for images n >= out_from_n
     const float* rgb_w;          // [out_n][3][cout] modulated ToRGB weights; rgb_out += act . rgb_w
     float* rgb_out;              // [out_n][grid_h][grid_w][3], pre-initialised with bias + upsampled skip
+    // halo variant: the (bh + wy - 1) x (bw + wx - 1) input patch of a chunk is loaded once and every tap
+    // addresses it through its UMMA descriptor
+    int dy0, dx0, halo_h, halo_w, a_stage_bytes;
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -62,6 +65,119 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 2) return v > 0.f ? v : 0.2f * v;
     if (act == 3) return 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);      // FusedLeakyReLU
     return v;
+}
+
+// Epilogue shared by the tensor-core conv kernels (executed by warps 2..5, threads 64..191).
+template <bool FUSED>
+__device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep, uint64_t* acc_bar,
+                                              int warp, int lane, int n0, int oy0, int ox0, int co0) {
+    // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
+    const int n = n0 + nl, oy = oy0 + yl, ox = ox0 + xl;
+    const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
+    float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
+                 (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
+    const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
+    const float nz = (p.noise && valid)
+        ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
+        : 0.f;
+    // One image per tile (the common case): stage alpha / beta / next-layer style / ToRGB weights of this
+    // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
+    const bool cs = (p.bn == 1);
+    const int BN = p.BN;
+    if (cs) {
+        const bool n_ok = n0 < p.out_n;
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+            const int cc = co0 + i;
+            const bool ok = n_ok && cc < p.cout;
+            ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
+            ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
+            if constexpr (FUSED) {
+                ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
+#pragma unroll
+                for (int o = 0; o < 3; ++o)
+                    ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    ptx::mbar_wait(acc_bar, 0);
+    ptx::tc_fence_after();
+    const bool write_f32 = FUSED ? (p.out != nullptr && n >= p.out_from_n) : true;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
+    float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+    for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        const int co = co0 + c;
+        if (!valid || co >= p.cout) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int cc = co + i;
+            if (cc < p.cout) {
+                float r = v[i];
+                if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
+                else {
+                    if (alpha) r *= __ldg(alpha + cc);
+                    r += nz;
+                    if (p.beta) r += __ldg(p.beta + cc);
+                }
+                if (p.accumulate) r += dst[cc];
+                v[i] = apply_act(r, p.act);
+            } else {
+                v[i] = 0.f;
+            }
+        }
+        if (FUSED && p.rgb_w) {
+            if (cs) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    rgb0 += v[i] * ep[3 * BN + c + i];
+                    rgb1 += v[i] * ep[4 * BN + c + i];
+                    rgb2 += v[i] * ep[5 * BN + c + i];
+                }
+            } else {
+                const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (co + i < p.cout) {
+                        rgb0 += v[i] * __ldg(wm + i);
+                        rgb1 += v[i] * __ldg(wm + p.cout + i);
+                        rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
+                    }
+                }
+            }
+        }
+        if (FUSED && p.out_split) {
+            __align__(16) __nv_bfloat16 hi[16], lo[16];
+            const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
+            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
+                                (size_t)(co >> 5) * 64 + (co & 16);
+            reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
+            reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
+            reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
+            reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
+        }
+        if (write_f32) {
+            if (vec_ok && co + 16 <= p.cout) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+                for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+            }
+        }
+    }
+    if (FUSED && p.rgb_out && valid) {
+        float* ro = p.rgb_out + pix * 3;
+        atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
+    }
 }
 
 // FUSED = false: plain epilogue (demod / noise / bias / activation / accumulate -> fp32), lean register budget.
@@ -153,113 +269,119 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (ptx::elect_one()) ptx::mma_commit(acc_bar);       // accumulator complete
         __syncwarp();
     } else {
-        // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int xl = row % p.bw, yl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
-        const int n = n0 + nl, oy = oy0 + yl, ox = ox0 + xl;
-        const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
-        float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
-                     (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
-        const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
-        const float nz = (p.noise && valid)
-            ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
-            : 0.f;
-        // One image per tile (the common case): stage alpha / beta / next-layer style / ToRGB weights of this
-        // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
-        const bool cs = (p.bn == 1);
-        const int BN = p.BN;
-        if (cs) {
-            const bool n_ok = n0 < p.out_n;
-            for (int i = threadIdx.x - 64; i < BN; i += 128) {
-                const int cc = co0 + i;
-                const bool ok = n_ok && cc < p.cout;
-                ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
-                ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
-                if constexpr (FUSED) {
-                    ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
-#pragma unroll
-                    for (int o = 0; o < 3; ++o)
-                        ep[(3 + o) * BN + i] = (ok && p.rgb_w) ? __ldg(p.rgb_w + ((size_t)n0 * 3 + o) * p.cout + cc) : 0.f;
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        ptx::mbar_wait(acc_bar, 0);
-        ptx::tc_fence_after();
-        const bool write_f32 = FUSED ? (p.out != nullptr && n >= p.out_from_n) : true;
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
-        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-        for (int c = 0; c < BN; c += 16) {
-            float v[16];
-            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            const int co = co0 + c;
-            if (!valid || co >= p.cout) continue;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int cc = co + i;
-                if (cc < p.cout) {
-                    float r = v[i];
-                    if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
-                    else {
-                        if (alpha) r *= __ldg(alpha + cc);
-                        r += nz;
-                        if (p.beta) r += __ldg(p.beta + cc);
-                    }
-                    if (p.accumulate) r += dst[cc];
-                    v[i] = apply_act(r, p.act);
-                } else {
-                    v[i] = 0.f;
-                }
-            }
-            if (FUSED && p.rgb_w) {
-                if (cs) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        rgb0 += v[i] * ep[3 * BN + c + i];
-                        rgb1 += v[i] * ep[4 * BN + c + i];
-                        rgb2 += v[i] * ep[5 * BN + c + i];
-                    }
-                } else {
-                    const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (co + i < p.cout) {
-                            rgb0 += v[i] * __ldg(wm + i);
-                            rgb1 += v[i] * __ldg(wm + p.cout + i);
-                            rgb2 += v[i] * __ldg(wm + 2 * p.cout + i);
-                        }
-                    }
-                }
-            }
-            if (FUSED && p.out_split) {
-                __align__(16) __nv_bfloat16 hi[16], lo[16];
-                const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
-                __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
-                                    (size_t)(co >> 5) * 64 + (co & 16);
-                reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
-                reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
-                reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
-                reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
-            }
-            if (write_f32) {
-                if (vec_ok && co + 16 <= p.cout) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                } else {
-                    for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
-                }
+        conv_epilogue<FUSED>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Halo variant for stride-1 tap lists on <= 64-channel layers (L2-fabric bound in conv_tc_kernel, where every tap
+// re-fetches its shifted 128-pixel patch).  Tile = 16 rows x 8 columns of output pixels.  Per 32-channel chunk ONE
+// stage holds the (16 + wy - 1) x (8 + wx - 1) input patch (one TMA box) plus the weight slices of all taps; the A
+// operand of tap (ty, tx) is the patch viewed through a descriptor whose start address is advanced by
+// (ty * halo_w + tx) 128-byte rows and whose stride-byte-offset is the patch row pitch: the eight pixels of one output
+// row are eight consecutive rows (one swizzle group), successive output rows are halo_w rows apart.  TMA and UMMA both
+// apply the 128B swizzle as a function of the absolute shared-memory address, so shifted views stay consistent
+// (descriptor base_offset = 0; measured, csrc/experimental/README.md).  One tile per CTA, 3 CTAs per SM.
+template <bool FUSED>
+__global__ void __launch_bounds__(CONV_THREADS, 3)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ ConvKernelParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_slice = p.BN * 128;
+    const int stage_bytes = p.a_stage_bytes + p.num_taps * b_slice;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* acc_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    uint32_t* tap_off = tmem_slot + 4;                                    // [WGS_MAX_TAPS] descriptor offsets (>>4)
+    float* ep = reinterpret_cast<float*>(tap_off + WGS_MAX_TAPS);
+
+    int t = blockIdx.x;
+    const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    const int n0 = t;
+    const int ox0 = tx * p.bw, oy0 = ty * p.bh, co0 = co_tile * p.BN;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
+        ptx::mbar_init(acc_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (threadIdx.x >= 64 && threadIdx.x - 64 < p.num_taps) {
+        const int i = threadIdx.x - 64;
+        tap_off[i] = (uint32_t)(((p.tap_dy[i] - p.dy0) * p.halo_w + (p.tap_dx[i] - p.dx0)) * 128) >> 4;
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)(p.halo_h * p.halo_w * 128 + p.num_taps * b_slice);
+            for (int ch = 0; ch < p.c_chunks; ++ch) {
+                ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+                ptx::mbar_expect_tx(full_bar + stage, bytes);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                ptx::tma_load_5d(sa, &tmap_a, full_bar + stage, 0, ch, ox0 + p.dx0, oy0 + p.dy0, n0);
+                for (int tap = 0; tap < p.num_taps; ++tap)
+                    ptx::tma_load_4d(sa + p.a_stage_bytes + (size_t)tap * b_slice, &tmap_b, full_bar + stage, 0, ch, co0,
+                                     (int)p.tap_w[tap]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-        if (FUSED && p.rgb_out && valid) {
-            float* ro = p.rgb_out + pix * 3;
-            atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
+    } else if (warp == 1) {
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
+        const uint32_t b_hi = (uint32_t)(ptx::umma_desc_sw128(0) >> 32);
+        // A: K-major SW128, SBO = patch row pitch, version 1, base_offset 0
+        const uint32_t a_hi = (uint32_t)((((uint64_t)((uint32_t)p.halo_w * 128u >> 4) << 32) | ((uint64_t)1 << 46) |
+                                          ((uint64_t)2 << 61)) >> 32);
+        const uint32_t lo0 = (ptx::smem_u32(smem) & 0x3FFFFu) >> 4;
+        const uint32_t st_step = (uint32_t)stage_bytes >> 4, a_sz = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)b_slice >> 4;
+        int stage = 0;
+        uint32_t phase = 0, accum = 0;
+        for (int ch = 0; ch < p.c_chunks; ++ch) {
+            ptx::mbar_wait(full_bar + stage, phase);
+            ptx::tc_fence_after();
+            const uint32_t a_lo = lo0 + (uint32_t)stage * st_step;
+            const uint32_t b_lo0 = a_lo + a_sz;
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+                const uint32_t da = a_lo + tap_off[tap];
+                const uint32_t db = b_lo0 + (uint32_t)tap * b_step;
+                if (ptx::elect_one()) {
+                    ptx::mma_f16_lh(tmem_base, da + 0, a_hi, db + 0, b_hi, idesc, accum);   // hi*hi
+                    ptx::mma_f16_lh(tmem_base, da + 2, a_hi, db + 2, b_hi, idesc, 1u);
+                    ptx::mma_f16_lh(tmem_base, da + 0, a_hi, db + 4, b_hi, idesc, 1u);      // hi*lo
+                    ptx::mma_f16_lh(tmem_base, da + 2, a_hi, db + 6, b_hi, idesc, 1u);
+                    ptx::mma_f16_lh(tmem_base, da + 4, a_hi, db + 0, b_hi, idesc, 1u);      // lo*hi
+                    ptx::mma_f16_lh(tmem_base, da + 6, a_hi, db + 2, b_hi, idesc, 1u);
+                }
+                __syncwarp();
+                accum = 1u;
+            }
+            if (ptx::elect_one()) ptx::mma_commit(empty_bar + stage);
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        if (ptx::elect_one()) ptx::mma_commit(acc_bar);
+        __syncwarp();
+    } else {
+        conv_epilogue<FUSED>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -413,6 +535,76 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
 
     auto encode = get_encode();
     WGS_REQUIRE(encode != nullptr, "conv: cuTensorMapEncodeTiled entry point not available");
+    // ---- halo variant ---------------------------------------------------------------------------------
+    {
+        int dy0 = 127, dy1 = -127, dx0 = 127, dx1 = -127;
+        for (int i = 0; i < d->num_taps; ++i) {
+            dy0 = std::min(dy0, d->tap_dy[i]); dy1 = std::max(dy1, d->tap_dy[i]);
+            dx0 = std::min(dx0, d->tap_dx[i]); dx1 = std::max(dx1, d->tap_dx[i]);
+        }
+        const int wy = dy1 - dy0 + 1, wx = dx1 - dx0 + 1;
+        static int halo_mode = -1;
+        if (halo_mode < 0) {
+            const char* e = getenv("WGS_CONV_HALO");           // 0 = off, 1 = on (default)
+            halo_mode = (e && e[0] == '0') ? 0 : 1;
+        }
+        int hBN = std::min(64, (d->cout + 15) / 16 * 16);
+        const int halo_h = 16 + wy - 1, halo_w = 8 + wx - 1;
+        const int a_bytes = (halo_h * halo_w * 128 + 1023) / 1024 * 1024;
+        while (hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > 72 * 1024) hBN /= 2;
+        const int h_stage = a_bytes + d->num_taps * hBN * 128;
+        const bool eligible = halo_mode && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
+                              d->grid_h >= 16 && d->grid_w >= 8 && d->c_chunks <= 2 && d->force_bn == 0 &&
+                              h_stage <= 72 * 1024;
+        if (eligible) {
+            p.bw = 8; p.bh = 16; p.bn = 1;
+            p.tiles_x = ceil_div(d->grid_w, 8); p.tiles_y = ceil_div(d->grid_h, 16); p.tiles_n = d->out_n;
+            p.dy0 = dy0; p.dx0 = dx0; p.halo_h = halo_h; p.halo_w = halo_w; p.a_stage_bytes = a_bytes;
+            p.BN = hBN;
+            p.n_tiles_co = ceil_div(d->cout, hBN);
+            p.tmem_cols = std::max(32, next_pow2(hBN));
+            p.stages = 1;
+            alignas(64) CUtensorMap ta, tb;
+            {
+                const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
+                                            (cuuint64_t)d->in_n};
+                const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->in_w, s4 = s3 * d->in_h;
+                const cuuint64_t strides[4] = {s1, s2, s3, s4};
+                const cuuint32_t box[5] = {64, 1, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 1};
+                const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->in), dims, strides, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(input) failed with code " + std::to_string((int)r));
+            }
+            {
+                const cuuint64_t dims[4] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_cout, (cuuint64_t)d->w_taps};
+                const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->w_cout;
+                const cuuint64_t strides[3] = {s1, s2, s3};
+                const cuuint32_t box[4] = {64, 1, (cuuint32_t)hBN, 1};
+                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->w), dims, strides, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
+            }
+            const size_t hsmem = (size_t)p.stages * h_stage + (2 * p.stages + 1) * 8 + 16 + WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
+            static bool hattr = false;
+            if (!hattr) {
+                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                hattr = true;
+            }
+            const int hgrid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
+            const bool hfused = d->out_split != nullptr || d->rgb_out != nullptr || d->out_from_n > 0 || d->out == nullptr;
+            if (hfused) conv_halo_kernel<true><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
+            else conv_halo_kernel<false><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
+            count_launch();
+            WGS_LAUNCH_CHECK();
+            return 0;
+        }
+    }
+
     alignas(64) CUtensorMap tmap_a, tmap_b;
     {
         const cuuint64_t dims[5] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h,
