@@ -133,11 +133,12 @@ int wgs_sg2_torgb(const float* a, const float* s, long long s_ld, const float* W
 
 /* Weight gradient of F.conv2d(x, w, stride, padding) on tensor cores (csrc/wgrad.cu):
  * xs split32 [n,h,w,ci_chunks,64], dys split32 [n,oh,ow,co_chunks,64] ->
- * dw fp32 [kh*kw][co_chunks*32][ci_chunks*32], ACCUMULATED (zero it first).  Replaces the cuDNN wgrad
- * reached from loss.backward(), lib/trainer.py:250.                                                */
+ * dw fp32, ACCUMULATED (zero it first): layout 0 = [kh*kw][co_chunks*32][ci_chunks*32]; layout 1 = torch
+ * [out_co][out_ci][kh][kw] (e.g. straight into the parameter's .grad).  Replaces the cuDNN wgrad reached from
+ * loss.backward(), lib/trainer.py:250.                                                              */
 int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int ci_chunks, const void* dys, int oh,
                            int ow, int co_chunks, int kh, int kw, int stride, int pad, float* dw,
-                           void* stream);
+                           int layout, int out_co, int out_ci, void* stream);
 
 /* ---- StyleGAN2 data-gradient glue (csrc/sg2_bwd.cu) — replaces autograd through
  * models/StyleGAN2/model.py:187-282 for the frozen generator (no weight gradients are formed).
@@ -186,6 +187,11 @@ int wgs_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const
 int wgs_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
                          const float* gamma, const float* sum_dz, const float* sum_dzx, int relu, long long R,
                          int C, void* dys, float* dy, float* dres, void* stream);
+
+/* 3x3 / stride 2 / pad 1 max-pool of the ResNet stem (torchvision resnet18.maxpool; lib/reconstructor.py:54), NHWC.
+ * fwd: out fp32 [N,OH,OW,C], idx uint8 argmax tap, optional split32 pack; bwd: gather, dz [N,H,W,C] fully written.   */
+int wgs_maxpool3s2_fwd(const float* z, int N, int H, int W, int C, float* out, void* idx, void* outs, void* stream);
+int wgs_maxpool3s2_bwd(const float* dout, const void* idx, int N, int H, int W, int C, float* dz, void* stream);
 
 #ifdef __cplusplus
 }

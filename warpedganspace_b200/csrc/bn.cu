@@ -234,3 +234,111 @@ extern "C" int wgs_bn_act_bwd_apply(const float* dz, const float* z, const float
     WGS_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// 3x3 / stride 2 / pad 1 max-pool of the ResNet stem (torchvision resnet18.maxpool), NHWC, fused with the split32
+// packing of the first BasicBlock's operand; the backward is a gather (each input pixel looks at the <= 4 windows that
+// contain it), so no memset / scatter-atomics are needed.  idx holds the argmax tap (0..8) per element.
+namespace wgs {
+
+__global__ void __launch_bounds__(256)
+maxpool3s2_fwd_kernel(const float* __restrict__ z, int N, int H, int W, int C, float* __restrict__ out,
+                      unsigned char* __restrict__ idx, __nv_bfloat16* __restrict__ outs) {
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2, C4 = C >> 2;
+    const long long total = (long long)N * OH * OW * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        long long r = i / C4;
+        const int ox = (int)(r % OW); r /= OW;
+        const int oy = (int)(r % OH);
+        const int n = (int)(r / OH);
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        unsigned char arg[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int y = 2 * oy - 1 + t / 3, x = 2 * ox - 1 + t % 3;
+            if (y < 0 || y >= H || x < 0 || x >= W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(z + (((size_t)n * H + y) * W + x) * C + c));
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (vv[k] > best[k]) { best[k] = vv[k]; arg[k] = (unsigned char)t; }
+        }
+        const size_t pix = ((size_t)n * OH + oy) * OW + ox;
+        *reinterpret_cast<float4*>(out + pix * C + c) = make_float4(best[0], best[1], best[2], best[3]);
+        *reinterpret_cast<uchar4*>(idx + pix * C + c) = make_uchar4(arg[0], arg[1], arg[2], arg[3]);
+        if (outs) {
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(best[k], hi[k], lo[k]);
+            __nv_bfloat16* sp = outs + pix * (size_t)(((C + 31) >> 5) * 64) + (size_t)(c >> 5) * 64 + (c & 31);
+            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool3s2_bwd_kernel(const float* __restrict__ dout, const unsigned char* __restrict__ idx, int N, int H, int W, int C,
+                      float* __restrict__ dz) {
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2, C4 = C >> 2;
+    const long long total = (long long)N * H * W * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        long long r = i / C4;
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H);
+        const int n = (int)(r / H);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // windows containing (y, x): oy in {floor(y/2), floor((y+1)/2)} (deduplicated), same for x
+        const int oy_a = y >> 1, oy_b = (y + 1) >> 1, ox_a = x >> 1, ox_b = (x + 1) >> 1;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int oy = a ? oy_b : oy_a;
+            if ((a && oy_b == oy_a) || oy >= OH) continue;
+            const int ty = y - (2 * oy - 1);
+            if (ty < 0 || ty > 2) continue;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int ox = b ? ox_b : ox_a;
+                if ((b && ox_b == ox_a) || ox >= OW) continue;
+                const int tx = x - (2 * ox - 1);
+                if (tx < 0 || tx > 2) continue;
+                const unsigned char t = (unsigned char)(ty * 3 + tx);
+                const size_t pix = ((size_t)n * OH + oy) * OW + ox;
+                const uchar4 id = *reinterpret_cast<const uchar4*>(idx + pix * C + c);
+                const float4 g = __ldg(reinterpret_cast<const float4*>(dout + pix * C + c));
+                if (id.x == t) acc[0] += g.x;
+                if (id.y == t) acc[1] += g.y;
+                if (id.z == t) acc[2] += g.z;
+                if (id.w == t) acc[3] += g.w;
+            }
+        }
+        *reinterpret_cast<float4*>(dz + (((size_t)n * H + y) * W + x) * C + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+}  // namespace wgs
+
+extern "C" int wgs_maxpool3s2_fwd(const float* z, int N, int H, int W, int C, float* out, void* idx, void* outs,
+                                  void* stream) {
+    WGS_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0, "maxpool3s2_fwd: C must be a multiple of 4");
+    const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+    wgs::maxpool3s2_fwd_kernel<<<wgs::bn_ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+        z, N, H, W, C, out, (unsigned char*)idx, (__nv_bfloat16*)outs);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_maxpool3s2_bwd(const float* dout, const void* idx, int N, int H, int W, int C, float* dz, void* stream) {
+    WGS_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0, "maxpool3s2_bwd: C must be a multiple of 4");
+    const long long total = (long long)N * H * W * (C / 4);
+    wgs::maxpool3s2_bwd_kernel<<<wgs::bn_ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+        dout, (const unsigned char*)idx, N, H, W, C, dz);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}

@@ -26,6 +26,7 @@ struct WgradParams {
     int n, h, w, ci_chunks, oh, ow, co_chunks, kh, kw, stride, pad;
     int bw, bh, bn, tiles_x, tiles_y, tiles_n;
     int NB, n_blocks, m_blocks, ksplit, stages, tmem_cols;
+    int layout, out_co, out_ci;      // layout 0: dw[T][co_pad][ci_pad]; 1: torch dw[out_co][out_ci][T]
     float* dw;
 };
 
@@ -99,34 +100,40 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
-                // both operands MN-major: a_major [15] = 1, b_major [16] = 1
-                const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)(64 * p.NB)) | (1u << 15) | (1u << 16);
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int k = 0; k < k_steps; ++k) {
-                    ptx::mbar_wait(full_bar + stage, phase);
-                    ptx::tc_fence_after();
-                    const uint32_t a0 = ptx::smem_u32(smem_a + (size_t)stage * a_bytes);
-                    const uint32_t b0 = ptx::smem_u32(smem_b + (size_t)stage * b_bytes);
+            // whole warp, uniform control flow; one elected lane issues.  Both operands MN-major: a_major [15] = 1,
+            // b_major [16] = 1
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)(64 * p.NB)) | (1u << 15) | (1u << 16);
+            const uint32_t dhi = (uint32_t)(umma_desc_mn_sw128(0, WG_BLOCK_BYTES, 1024) >> 32);
+            const uint32_t dlo_extra = (uint32_t)(umma_desc_mn_sw128(0, WG_BLOCK_BYTES, 1024) & 0xFFFFFFFFu);   // LBO bits
+            const uint32_t a_lo0 = ((ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4) | dlo_extra;
+            const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4) | dlo_extra;
+            const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < k_steps; ++k) {
+                ptx::mbar_wait(full_bar + stage, phase);
+                ptx::tc_fence_after();
+                const uint32_t a0 = a_lo0 + (uint32_t)stage * a_step, b0 = b_lo0 + (uint32_t)stage * b_step;
+                if (ptx::elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < WG_BK / 16; ++kk) {
-                        const uint64_t da = umma_desc_mn_sw128(a0 + kk * 2048, WG_BLOCK_BYTES, 1024);
-                        const uint64_t db = umma_desc_mn_sw128(b0 + kk * 2048, WG_BLOCK_BYTES, 1024);
-                        ptx::mma_f16(tmem_base, da, db, idesc, (k > 0 || kk > 0) ? 1u : 0u);
-                    }
+                    for (int kk = 0; kk < WG_BK / 16; ++kk)
+                        ptx::mma_f16_lh(tmem_base, a0 + kk * (2048 >> 4), dhi, b0 + kk * (2048 >> 4), dhi, idesc,
+                                        (k > 0 || kk > 0) ? 1u : 0u);
                     ptx::mma_commit(empty_bar + stage);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                ptx::mma_commit(acc_bar);
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
+            if (ptx::elect_one()) ptx::mma_commit(acc_bar);
+            __syncwarp();
         } else {
             const int q = warp & 3;
             const int m = q * 32 + lane;                         // accumulator row
             const int co = (mb * 2 + m / 64) * 32 + (m % 32);    // hi and lo rows of a chunk fold into one co
             const int ci_pad = p.ci_chunks * 32;
             float* dst_row = p.dw + ((size_t)tap * p.co_chunks * 32 + co) * ci_pad;
-            const bool row_ok = (mb * 2 + m / 64) < p.co_chunks;
+            const bool row_ok = (mb * 2 + m / 64) < p.co_chunks && (p.layout == 0 || co < p.out_co);
+            const int T = p.kh * p.kw;
             ptx::mbar_wait(acc_bar, 0);
             ptx::tc_fence_after();
             for (int c = 0; c < p.NB; ++c) {
@@ -136,9 +143,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                     ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64 + j * 16), v + j * 16);
                 const int chunk = nb * p.NB + c;
                 if (!row_ok || chunk >= p.ci_chunks) continue;
-                float* dst = dst_row + chunk * 32;
+                if (p.layout == 0) {
+                    float* dst = dst_row + chunk * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j] + v[j + 32]);
+                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j] + v[j + 32]);
+                } else {
+                    float* dst = p.dw + ((size_t)co * p.out_ci + chunk * 32) * T + tap;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (chunk * 32 + j < p.out_ci) atomicAdd(dst + (size_t)j * T, v[j] + v[j + 32]);
+                }
             }
         }
     }
@@ -176,7 +190,8 @@ __global__ void wgrad_simt_kernel(const __nv_bfloat16* __restrict__ xs, const __
                     acc += ah * bh + ah * bl + al * bh + al * bl;
                 }
             }
-        p.dw[i] += acc;
+        if (p.layout == 0) p.dw[i] += acc;
+        else if (co < p.out_co && ci < p.out_ci) p.dw[((size_t)co * p.out_ci + ci) * (p.kh * p.kw) + tap] += acc;
     }
 }
 
@@ -200,13 +215,15 @@ using namespace wgs;
 
 extern "C" int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int ci_chunks, const void* dys, int oh,
                                       int ow, int co_chunks, int kh, int kw, int stride, int pad, float* dw,
-                                      void* stream) {
+                                      int layout, int out_co, int out_ci, void* stream) {
+    WGS_REQUIRE(layout == 0 || (layout == 1 && out_co > 0 && out_ci > 0), "wgrad: bad output layout");
     WGS_REQUIRE(n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0 && ci_chunks > 0 && co_chunks > 0, "wgrad: bad sizes");
     WGS_REQUIRE(kh >= 1 && kw >= 1 && kh * kw <= 64 && stride >= 1 && stride <= 8 && pad >= 0, "wgrad: bad kernel geometry");
     WgradParams p;
     memset(&p, 0, sizeof(p));
     p.n = n; p.h = h; p.w = w; p.ci_chunks = ci_chunks; p.oh = oh; p.ow = ow; p.co_chunks = co_chunks;
     p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.dw = dw;
+    p.layout = layout; p.out_co = out_co; p.out_ci = out_ci;
     p.bw = std::min(8, pow2ceil(ow));
     p.bh = std::min(WG_BK / p.bw, pow2ceil(oh));
     p.bn = WG_BK / (p.bw * p.bh);

@@ -53,6 +53,12 @@ def _bn_backward(dz, z, y, stats, gamma, relu, want_res):
     return dys, dres, sums[1], sums[0]
 
 
+def _grad_target(w):
+    """The parameter's existing .grad (the trainer's flat, pre-zeroed buffer) when the wgrad kernel can accumulate into it."""
+    g = w.grad
+    return g if (g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.shape == w.shape) else None
+
+
 def _conv(xs, w, stride, padding):
     co, ci, kh, kw = w.shape
     return C.conv2d(xs, C.pack_weights(w.detach()), kh, kw, stride=stride, padding=padding, cin=ci)
@@ -89,9 +95,12 @@ class ResNetFeatures(torch.autograd.Function):
         wmat = w1.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci, 1, 1)
         y0 = C.conv2d(xcol, C.pack_weights(wmat), 1, 1, cin=kh * kw * ci)
         z0, _, st0 = _bn_forward(y0, net.bn1, None, True, want_split=False)
-        pooled, pool_idx = F.max_pool2d(z0.permute(0, 3, 1, 2), 3, 2, 1, return_indices=True)
-        cur = pooled.permute(0, 2, 3, 1).contiguous()                      # NHWC fp32
-        cur_s = C.pack_split32(cur)
+        ph, pw = (oh + 1) // 2, (ow + 1) // 2
+        cur = torch.empty(n, ph, pw, co, device=x.device, dtype=torch.float32)             # NHWC fp32
+        pool_idx = torch.empty(n, ph, pw, co, device=x.device, dtype=torch.uint8)
+        cur_s = torch.empty(n, ph, pw, C.chunks_of(co), 64, device=x.device, dtype=torch.bfloat16)
+        _lib.call('wgs_maxpool3s2_fwd', _lib.ptr(z0), n, oh, ow, co, _lib.ptr(cur), _lib.ptr(pool_idx), _lib.ptr(cur_s),
+                  _lib.stream())
         tape['stem'] = (xcol, y0, z0, st0, pool_idx, (n, ci, h, w))
         tape['blocks'] = []
         for li in range(1, 5):
@@ -126,26 +135,26 @@ class ResNetFeatures(torch.autograd.Function):
             dy2s, dres, dg2, db2 = _bn_backward(dcur, out, y2, st2, b.bn2.weight, True, want_res=True)
             grads[b.bn2.weight], grads[b.bn2.bias] = dg2, db2
             w2 = b.conv2.weight
-            grads[w2] = WG.conv_wgrad(z1s, dy2s, tuple(w2.shape), 1, 1)
+            grads[w2] = WG.conv_wgrad(z1s, dy2s, tuple(w2.shape), 1, 1, out=_grad_target(w2))
             dz1 = conv_dgrad(dy2s, w2, (y1.shape[1], y1.shape[2]), 1, 1)
             dy1s, _, dg1, db1 = _bn_backward(dz1, z1, y1, st1, b.bn1.weight, True, want_res=False)
             grads[b.bn1.weight], grads[b.bn1.bias] = dg1, db1
             w1 = b.conv1.weight
-            grads[w1] = WG.conv_wgrad(xs, dy1s, tuple(w1.shape), s, 1)
+            grads[w1] = WG.conv_wgrad(xs, dy1s, tuple(w1.shape), s, 1, out=_grad_target(w1))
             if yd is not None:
                 dyds, _, dgd, dbd = _bn_backward(dres, None, yd, std, b.downsample[1].weight, False, want_res=False)
                 grads[b.downsample[1].weight], grads[b.downsample[1].bias] = dgd, dbd
                 wd = b.downsample[0].weight
-                grads[wd] = WG.conv_wgrad(xs, dyds, tuple(wd.shape), s, 0)
+                grads[wd] = WG.conv_wgrad(xs, dyds, tuple(wd.shape), s, 0, out=_grad_target(wd))
                 dx = conv_dgrad(dy1s, w1, (xh, xw), s, 1)
                 dx = conv_dgrad(dyds, wd, (xh, xw), s, 0, out=dx, accumulate=True)
             else:
                 dx = conv_dgrad(dy1s, w1, (xh, xw), s, 1, out=dres, accumulate=True)     # dx = dres + conv^T(dy1)
             dcur = dx
         xcol, y0, z0, st0, pool_idx, (n, ci, h, w) = tape['stem']
-        dz0 = torch.ops.aten.max_pool2d_with_indices_backward(
-            dcur.permute(0, 3, 1, 2), z0.permute(0, 3, 1, 2), [3, 3], [2, 2], [1, 1], [1, 1], False, pool_idx)
-        dz0 = dz0.permute(0, 2, 3, 1).contiguous()
+        dz0 = torch.empty_like(z0)
+        _lib.call('wgs_maxpool3s2_bwd', _lib.ptr(dcur.contiguous()), _lib.ptr(pool_idx), z0.shape[0], z0.shape[1], z0.shape[2],
+                  z0.shape[3], _lib.ptr(dz0), _lib.stream())
         dy0s, _, dg0, db0 = _bn_backward(dz0, z0, y0, st0, net.bn1.weight, True, want_res=False)
         grads[net.bn1.weight], grads[net.bn1.bias] = dg0, db0
         w1 = net.conv1.weight
