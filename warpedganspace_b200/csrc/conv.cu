@@ -108,31 +108,77 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     const bool write_f32 = FUSED ? (p.out != nullptr && n >= p.out_from_n) : true;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
+    const uint32_t ep_s = ptx::smem_u32(ep);                 // explicit ld.shared: the generic pointer costs LD.E + a stall per use
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
     for (int c = 0; c < BN; c += 16) {
         float v[16];
         ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
         const int co = co0 + c;
         if (!valid || co >= p.cout) continue;
+        const bool fast = cs && (co + 16 <= p.cout);         // whole 16-channel group valid, constants staged in smem
+        if (fast) {
+            const uint32_t ea = ep_s + (uint32_t)c * 4u, eb = ea + (uint32_t)BN * 4u;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int cc = co + i;
-            if (cc < p.cout) {
-                float r = v[i];
-                if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
-                else {
-                    if (alpha) r *= __ldg(alpha + cc);
-                    r += nz;
-                    if (p.beta) r += __ldg(p.beta + cc);
+            for (int i = 0; i < 16; i += 4) {
+                const float4 al = ptx::lds128(ea + i * 4), be = ptx::lds128(eb + i * 4);
+                v[i + 0] = fmaf(v[i + 0], al.x, nz) + be.x;
+                v[i + 1] = fmaf(v[i + 1], al.y, nz) + be.y;
+                v[i + 2] = fmaf(v[i + 2], al.z, nz) + be.z;
+                v[i + 3] = fmaf(v[i + 3], al.w, nz) + be.w;
+            }
+            if (p.accumulate) {
+                if (vec_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 o = *reinterpret_cast<const float4*>(dst + co + i);
+                        v[i] += o.x; v[i + 1] += o.y; v[i + 2] += o.z; v[i + 3] += o.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += dst[co + i];
                 }
-                if (p.accumulate) r += dst[cc];
-                v[i] = apply_act(r, p.act);
-            } else {
-                v[i] = 0.f;
+            }
+            if (p.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (p.act == 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
+            } else if (p.act == 3) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 1.41421356237309515f * (v[i] > 0.f ? v[i] : 0.2f * v[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int cc = co + i;
+                if (cc < p.cout) {
+                    float r = v[i];
+                    if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
+                    else {
+                        if (alpha) r *= __ldg(alpha + cc);
+                        r += nz;
+                        if (p.beta) r += __ldg(p.beta + cc);
+                    }
+                    if (p.accumulate) r += dst[cc];
+                    v[i] = apply_act(r, p.act);
+                } else {
+                    v[i] = 0.f;
+                }
             }
         }
         if (FUSED && p.rgb_w) {
-            if (cs) {
+            if (fast) {
+                const uint32_t er = ep_s + (uint32_t)(3 * BN + c) * 4u;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 w0 = ptx::lds128(er + i * 4), w1 = ptx::lds128(er + (BN + i) * 4),
+                                 w2 = ptx::lds128(er + (2 * BN + i) * 4);
+                    rgb0 += v[i] * w0.x + v[i + 1] * w0.y + v[i + 2] * w0.z + v[i + 3] * w0.w;
+                    rgb1 += v[i] * w1.x + v[i + 1] * w1.y + v[i + 2] * w1.z + v[i + 3] * w1.w;
+                    rgb2 += v[i] * w2.x + v[i + 1] * w2.y + v[i + 2] * w2.z + v[i + 3] * w2.w;
+                }
+            } else if (cs) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     rgb0 += v[i] * ep[3 * BN + c + i];
@@ -153,10 +199,22 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
         }
         if (FUSED && p.out_split) {
             __align__(16) __nv_bfloat16 hi[16], lo[16];
-            const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+            if (fast) {
+                const uint32_t es = ep_s + (uint32_t)(2 * BN + c) * 4u;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 sc4 = ptx::lds128(es + i * 4);
+                    split_bf16(v[i + 0] * sc4.x, hi[i + 0], lo[i + 0]);
+                    split_bf16(v[i + 1] * sc4.y, hi[i + 1], lo[i + 1]);
+                    split_bf16(v[i + 2] * sc4.z, hi[i + 2], lo[i + 2]);
+                    split_bf16(v[i + 3] * sc4.w, hi[i + 3], lo[i + 3]);
+                }
+            } else {
+                const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
+            }
             __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
                                 (size_t)(co >> 5) * 64 + (co & 16);
             reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
@@ -196,7 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-    float* ep = reinterpret_cast<float*>(tmem_slot + 4);     // [6][BN] per-channel epilogue constants
+    float* ep = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [6][BN] per-channel epilogue constants
 
     // tile coordinates: co tile fastest so CTAs sharing an input patch are co-scheduled (L2 reuse)
     int t = blockIdx.x;
@@ -303,7 +361,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* acc_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
     uint32_t* tap_off = tmem_slot + 4;                                    // [WGS_MAX_TAPS] descriptor offsets (>>4)
-    float* ep = reinterpret_cast<float*>(tap_off + WGS_MAX_TAPS);
+    float* ep = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tap_off + WGS_MAX_TAPS) + 15) & ~uintptr_t(15));
 
     int t = blockIdx.x;
     const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;
@@ -589,7 +647,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
             }
-            const size_t hsmem = (size_t)p.stages * h_stage + (2 * p.stages + 1) * 8 + 16 + WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
+            const size_t hsmem = (size_t)p.stages * h_stage + (2 * p.stages + 1) * 8 + 32 + WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
             static bool hattr = false;
             if (!hattr) {
                 WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
@@ -631,7 +689,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         WGS_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 6 * BN * 4 + 1024;
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 32 + 6 * BN * 4 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
