@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 4)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_stage_bytes = p.BN * 128;
     uint8_t* smem_a = smem;
@@ -254,7 +254,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-    float* ep = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [6][BN] per-channel epilogue constants
+    float* ep = reinterpret_cast<float*>(tmem_slot + 4);
+    ep += ((16u - (ptx::smem_u32(ep) & 15u)) & 15u) >> 2;   // [6][BN] per-channel epilogue constants
 
     // tile coordinates: co tile fastest so CTAs sharing an input patch are co-scheduled (L2 reuse)
     int t = blockIdx.x;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 3)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_slice = p.BN * 128;
     const int stage_bytes = p.a_stage_bytes + p.num_taps * b_slice;
@@ -361,7 +362,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* acc_bar = empty_bar + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
     uint32_t* tap_off = tmem_slot + 4;                                    // [WGS_MAX_TAPS] descriptor offsets (>>4)
-    float* ep = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tap_off + WGS_MAX_TAPS) + 15) & ~uintptr_t(15));
+    float* ep = reinterpret_cast<float*>(tap_off + WGS_MAX_TAPS);
+    ep += ((16u - (ptx::smem_u32(ep) & 15u)) & 15u) >> 2;
 
     int t = blockIdx.x;
     const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;

@@ -73,12 +73,15 @@ im2col_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C, i
                       int OH, int OW, __nv_bfloat16* __restrict__ out, int chunks) {
     extern __shared__ int tab[];                                 // tab[k] = (ky << 20) | (kx << 10) | c, or -1
     const int K = kh * kw * C, Kp = chunks * 32;
+    int* rel = tab + Kp;                                         // rel[k] = ((ky * W + kx) * C + c), interior fast path
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
         if (k < K) {
             const int c = k % C, tap = k / C;
             tab[k] = ((tap / kw) << 20) | ((tap % kw) << 10) | c;
+            rel[k] = ((tap / kw) * W + (tap % kw)) * C + c;
         } else {
             tab[k] = -1;
+            rel[k] = 0;
         }
     }
     __syncthreads();
@@ -94,15 +97,31 @@ im2col_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C, i
         const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
         const float* img = x + (size_t)n * H * W * C;
         __align__(16) __nv_bfloat16 hi[8], lo[8];
+        if (iy0 >= 0 && iy0 + kh <= H && ix0 >= 0 && ix0 + kw <= W) {
+            // interior pixel: no bounds checks, one table word per element (two 16-byte shared loads per thread)
+            const float* base = img + ((size_t)iy0 * W + ix0) * C;
+            const int4 r0 = *reinterpret_cast<const int4*>(rel + g * 8), r1 = *reinterpret_cast<const int4*>(rel + g * 8 + 4);
+            const int ro[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int e = tab[g * 8 + j];
-            float v = 0.f;
-            if (e >= 0) {
-                const int iy = iy0 + (e >> 20), ix = ix0 + ((e >> 10) & 1023);
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((size_t)iy * W + ix) * C + (e & 1023));
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(base + ro[j]);
+            if (g * 8 + 8 > K) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (g * 8 + j >= K) v[j] = 0.f;
             }
-            split_bf16(v, hi[j], lo[j]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_bf16(v[j], hi[j], lo[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = tab[g * 8 + j];
+                float v = 0.f;
+                if (e >= 0) {
+                    const int iy = iy0 + (e >> 20), ix = ix0 + ((e >> 10) & 1023);
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((size_t)iy * W + ix) * C + (e & 1023));
+                }
+                split_bf16(v, hi[j], lo[j]);
+            }
         }
         __nv_bfloat16* dst = out + pix * (size_t)chunks * 64 + (size_t)(g >> 2) * 64 + (g & 3) * 8;
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
@@ -117,9 +136,10 @@ extern "C" int wgs_im2col_split32(const float* x, int N, int H, int W, int C, in
     WGS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && OH > 0 && OW > 0, "im2col: bad sizes");
     const int chunks = (kh * kw * C + 31) / 32;
     WGS_REQUIRE(kh < 1024 && kw < 1024 && C < 1024, "im2col: kernel / channel counts must be < 1024");
+    WGS_REQUIRE((long long)H * W * C < (1ll << 31), "im2col: one image must be smaller than 2^31 elements");
     const long long total = (long long)N * OH * OW * chunks * 4;
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)wgs::num_sms() * 32);
-    wgs::im2col_split32_kernel<<<blocks, 256, (size_t)chunks * 32 * sizeof(int), (cudaStream_t)stream>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW,
+    wgs::im2col_split32_kernel<<<blocks, 256, (size_t)chunks * 64 * sizeof(int), (cudaStream_t)stream>>>(x, N, H, W, C, kh, kw, stride, pad, OH, OW,
                                                                        (__nv_bfloat16*)out, chunks);
     wgs::count_launch();
     WGS_LAUNCH_CHECK();

@@ -96,6 +96,12 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
         const int n = (int)(r / yb_n);
         const int yy0 = Y0 - pad0, xx0 = X - pad0;
         const float* base = y + ((long long)n * Hin + yy0) * row_stride + (long long)xx0 * C + c;
+        // noise of the 8 output rows up front: loading it inside the row loop serialises 8 global-load latencies
+        // behind the stores (47 % of this kernel's stall samples, profiles/r01_bandwidth_kernels_ncu.md)
+        float nzv[FIR_ROWS];
+#pragma unroll
+        for (int oy = 0; oy < FIR_ROWS; ++oy)
+            nzv[oy] = (noise && Y0 + oy < Hout) ? noise_w * __ldg(noise + (size_t)(Y0 + oy) * Wout + X) : 0.f;
         float4 h[FIR_ROWS + 3];
         if (yy0 >= 0 && yy0 + FIR_ROWS + 2 < Hin && xx0 >= 0 && xx0 + 3 < Win) {
 #pragma unroll
@@ -146,7 +152,7 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
             v4[1] = kf[0] * h[oy].y + kf[1] * h[oy + 1].y + kf[2] * h[oy + 2].y + kf[3] * h[oy + 3].y;
             v4[2] = kf[0] * h[oy].z + kf[1] * h[oy + 1].z + kf[2] * h[oy + 2].z + kf[3] * h[oy + 3].z;
             v4[3] = kf[0] * h[oy].w + kf[1] * h[oy + 1].w + kf[2] * h[oy + 2].w + kf[3] * h[oy + 3].w;
-            const float nz = noise ? noise_w * __ldg(noise + (size_t)Y * Wout + X) : 0.f;
+            const float nz = nzv[oy];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float t = v4[k] * al[k] + nz + be[k];

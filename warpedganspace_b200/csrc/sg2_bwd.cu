@@ -185,44 +185,63 @@ sg2_layer_bwd_kernel(const float* __restrict__ dx_up, const float* __restrict__ 
         }
     }
     float acc_u[4] = {0.f, 0.f, 0.f, 0.f}, acc_r[4] = {0.f, 0.f, 0.f, 0.f}, acc_d[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long p = p0 + pl; p < p1; p += PL) {
-        const size_t off = ((size_t)n * P + p) * C + q * 4;
-        const float4 a4 = __ldg(reinterpret_cast<const float4*>(a + off));
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-        float da[4] = {0.f, 0.f, 0.f, 0.f};
-        if (dx_up) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(dx_up + off));
-            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    // LBW_U pixels per trip with every load issued before the first use: one pixel per trip leaves a single batch of
+    // loads in flight per thread and 66 % of the stall samples on the two first uses (profiles/r01_bandwidth_kernels_ncu.md)
+    constexpr int LBW_U = 4;
+    for (long long pb = p0 + pl; pb < p1; pb += (long long)PL * LBW_U) {
+        float4 a4[LBW_U], g4[LBW_U];
+        float r0[LBW_U], r1[LBW_U], r2[LBW_U], nzv[LBW_U];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { acc_u[k] += gv[k] * av[k]; da[k] = gv[k] * su[k]; }
+        for (int u = 0; u < LBW_U; ++u) {
+            const long long pu = pb + (long long)u * PL;
+            const long long p = pu < p1 ? pu : pb;                       // clamp: the tail re-reads a valid pixel
+            const size_t off = ((size_t)n * P + p) * C + q * 4;
+            a4[u] = __ldg(reinterpret_cast<const float4*>(a + off));
+            if (dx_up) g4[u] = __ldg(reinterpret_cast<const float4*>(dx_up + off));
+            if (drgb) {
+                const float* g = drgb + ((size_t)n * P + p) * 3;
+                r0[u] = __ldg(g); r1[u] = __ldg(g + 1); r2[u] = __ldg(g + 2);
+            }
+            nzv[u] = noise ? noise_w * __ldg(noise + p) : 0.f;
         }
-        if (drgb) {
-            const float* g = drgb + ((size_t)n * P + p) * 3;
-            const float g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+#pragma unroll
+        for (int u = 0; u < LBW_U; ++u) {
+            const long long p = pb + (long long)u * PL;
+            if (p >= p1) break;
+            const size_t off = ((size_t)n * P + p) * C + q * 4;
+            const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+            float da[4] = {0.f, 0.f, 0.f, 0.f};
+            if (dx_up) {
+                const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { acc_u[k] += gv[k] * av[k]; da[k] = gv[k] * su[k]; }
+            }
+            if (drgb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float t = r0[u] * w[0][k] + r1[u] * w[1][k] + r2[u] * w[2][k];
+                    acc_r[k] += t * av[k];
+                    da[k] += t * sr[k];
+                }
+            }
+            const float nz = nzv[u];
+            float o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float t = g0 * w[0][k] + g1 * w[1][k] + g2 * w[2][k];
-                acc_r[k] += t * av[k];
-                da[k] += t * sr[k];
+                const bool pos = av[k] > 0.f;
+                const float pre = pos ? av[k] * (1.f / SQRT2) : av[k] * (1.f / (0.2f * SQRT2));
+                o[k] = da[k] * (pos ? SQRT2 : 0.2f * SQRT2);
+                acc_d[k] += o[k] * (pre - nz - bv[k]) / dv[k];
             }
-        }
-        const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
-        float o[4];
+            if (dpre) *reinterpret_cast<float4*>(dpre + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (g_split) {
+                __align__(8) __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool pos = av[k] > 0.f;
-            const float pre = pos ? av[k] * (1.f / SQRT2) : av[k] * (1.f / (0.2f * SQRT2));
-            o[k] = da[k] * (pos ? SQRT2 : 0.2f * SQRT2);
-            acc_d[k] += o[k] * (pre - nz - bv[k]) / dv[k];
-        }
-        if (dpre) *reinterpret_cast<float4*>(dpre + off) = make_float4(o[0], o[1], o[2], o[3]);
-        if (g_split) {
-            __align__(8) __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) split_bf16(o[k] * dv[k], hi[k], lo[k]);
-            __nv_bfloat16* sp = g_split + ((size_t)n * P + p) * (size_t)(C * 2) + (size_t)(q >> 3) * 64 + ((q & 7) << 2);
-            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
-            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+                for (int k = 0; k < 4; ++k) split_bf16(o[k] * dv[k], hi[k], lo[k]);
+                __nv_bfloat16* sp = g_split + ((size_t)n * P + p) * (size_t)(C * 2) + (size_t)(q >> 3) * 64 + ((q & 7) << 2);
+                *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+                *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+            }
         }
     }
     reduce_quads_to_global(acc_d, sm, C, C4, PL, dd + (size_t)n * C);

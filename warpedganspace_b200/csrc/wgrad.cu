@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                 const __grid_constant__ WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = 2 * WG_BLOCK_BYTES, b_bytes = p.NB * WG_BLOCK_BYTES;
     uint8_t* smem_a = smem;
