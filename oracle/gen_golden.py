@@ -447,6 +447,79 @@ def pin_traversal():
                                     steps=steps, path=path, codes=codes, shifts=shifts))
 
 
+def pin_trainer_loop():
+    """The UNMODIFIED reference driver (lib/trainer.py:24-319) on config 1 for a few iterations under a fixed global
+    seed, on the CPU: pins the host draw order, the statistics written to stats.json, the checkpoint layout and the
+    parameters after several Adam steps.  tests/test_trainer_gpu.py runs warpedganspace_b200.Trainer on the same
+    seed and compares."""
+    import argparse
+    import json
+    import tempfile
+    import oracle.support_sets as o_ss
+    import oracle.sngan as o_sn
+    import oracle.reconstructor as o_rec
+    lib = importlib.import_module('lib')
+    sn_ref = importlib.import_module('models.SNGAN.sn_gen_resnet')
+    dist = importlib.import_module('models.SNGAN.distribution')
+    gan_load = importlib.import_module('models.gan_load')
+    print('[reference Trainer.train, config 1]')
+    K, D, d, B, iters = 32, 16, 128, 4, 6
+    g_sd = o_sn.init_state('sn_resnet32', 1, generator=gen(101))
+    s_sd = o_ss.init_state(K, D, d, generator=gen(102))
+    r_sd = o_rec.init_state('LeNet', K, 1, generator=gen(103))
+    Gm = sn_ref.make_resnet_generator(sn_ref.SN_RES_GEN_CONFIGS['sn_resnet32'], img_size=32, channels=1,
+                                      distribution=dist.NormalDistribution(128))
+    full = dict(g_sd)
+    for k, v in list(g_sd.items()):
+        for a, b in (('.conv1.', '.model.3.'), ('.conv2.', '.model.6.')):
+            if a in k:
+                full[k.replace(a, b)] = v
+    Gm.model.load_state_dict(full, strict=False)
+    G = gan_load.SNGANWrapper(Gm)
+    S = lib.SupportSets(K, D, d, learn_alphas=False, learn_gammas=True, gamma=1.0 / d)
+    S.load_state_dict(s_sd)
+    R = lib.Reconstructor('LeNet', K, 1)
+    R.load_state_dict(r_sd)
+    params = argparse.Namespace(
+        gan_type='SNGAN_MNIST', z_truncation=None, biggan_target_classes=None, stylegan2_resolution=1024,
+        shift_in_w_space=False, num_support_sets=K, num_support_dipoles=D, learn_alphas=False, learn_gammas=True,
+        gamma=None, support_set_lr=1e-4, reconstructor_type='LeNet', min_shift_magnitude=0.15,
+        max_shift_magnitude=0.25, reconstructor_lr=1e-4, max_iter=iters, batch_size=B, lambda_cls=1.0,
+        lambda_reg=0.25, log_freq=2, ckp_freq=3, tensorboard=False, cuda=False)
+    cwd = os.getcwd()
+    work = tempfile.mkdtemp(prefix='wgs_ref_trainer_')
+    os.chdir(work)
+    try:
+        exp_dir = lib.create_exp_dir(params)
+        trn = lib.Trainer(params=params, exp_dir=exp_dir, use_cuda=False, multi_gpu=False)
+        torch.manual_seed(2024)
+        trn.train(generator=G, support_sets=S, reconstructor=R)
+        wip = os.path.join(work, 'experiments', 'wip', exp_dir)
+        done = os.path.join(work, 'experiments', 'complete', exp_dir)
+        with open(os.path.join(wip, 'stats.json')) as f:
+            stats = json.load(f)
+        ckpt = torch.load(os.path.join(wip, 'models', 'checkpoint.pt'))
+        files_wip = sorted(os.path.relpath(os.path.join(r, f), wip) for r, _, fs in os.walk(wip) for f in fs)
+        files_done = sorted(os.path.relpath(os.path.join(r, f), done) for r, _, fs in os.walk(done) for f in fs)
+        final_s = torch.load(os.path.join(wip, 'models', 'support_sets.pt'))
+        final_r = torch.load(os.path.join(wip, 'models', 'reconstructor.pt'))
+        init_s = torch.load(os.path.join(wip, 'models', 'support_sets_init.pt'))
+    finally:
+        os.chdir(cwd)
+    assert torch.equal(init_s['SUPPORT_SETS'], s_sd['SUPPORT_SETS'])
+    moved = (final_s['SUPPORT_SETS'] - s_sd['SUPPORT_SETS']).abs().amax(dim=1).nonzero().flatten()
+    print('  exp_dir %s; stats keys %s; %d support-set rows moved' % (exp_dir, sorted(stats), moved.numel()))
+    save('trainer_c1.pt', dict(
+        K=K, D=D, d=d, B=B, iters=iters, seeds=(101, 102, 103), train_seed=2024, params=vars(params),
+        checksums=(checksum(g_sd), checksum(s_sd), checksum(r_sd)), exp_dir=exp_dir, stats=stats,
+        files_wip=files_wip, files_complete=files_done, checkpoint_iter=ckpt['iter'],
+        checkpoint_keys={k: sorted(v.keys()) if isinstance(v, dict) else None for k, v in ckpt.items()},
+        moved_rows=moved, final_support_sets_rows=final_s['SUPPORT_SETS'][moved].clone(),
+        final_loggamma=final_s['LOGGAMMA'].clone(),
+        final_head_bias=final_r['path_indices.3.bias'].clone(),
+        final_conv0_weight=final_r['feature_extractor.0.weight'].clone()))
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.chdir('/tmp')
@@ -457,6 +530,7 @@ def main():
     pin_reconstructor()
     pin_step()
     pin_traversal()
+    pin_trainer_loop()
     pin_proggan()
     pin_biggan()
     print('oracle pinned against the reference; fixtures in', OUT)

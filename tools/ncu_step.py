@@ -34,9 +34,21 @@ def wrapped(name, *args):
     return orig(name, *args)
 
 _lib.call = wrapped
+# the conv entry point is called through _lib.check(lib.wgs_conv_split32(...)), not _lib.call: wrap it one level up
+from warpedganspace_b200 import conv as C
+_conv_taps = C.conv_taps
+def conv_wrapped(*a, **k):
+    global orig
+    saved, orig = orig, (lambda name, *aa: _conv_taps(*a, **k))
+    try:
+        return wrapped('wgs_conv_split32')
+    finally:
+        orig = saved
+C.conv_taps = conv_wrapped
+ONLY = set(sys.argv[3].split(',')) if len(sys.argv) > 3 else None
 tr.step(*bs[2], eager=True)
 torch.cuda.synchronize()
-top = sorted([l for l in log if l[2] not in SKIP], reverse=True)[:K]
+top = sorted([l for l in log if l[2] not in SKIP and (ONLY is None or l[2] in ONLY)], reverse=True)[:K]
 for ms, i, name in top:
     print('%4d %-28s %.3f ms' % (i, name, ms))
 print('all calls: %d, total %.2f ms' % (len(log), sum(l[0] for l in log)))

@@ -178,3 +178,193 @@ class PairedTrainer:
         self.flat_s.step_count += 1
         self.flat_r.step_count += 1
         return self._static_out
+
+
+class Trainer(object):
+    """Drop-in for the reference training driver ``lib.trainer.Trainer`` (lib/trainer.py:24-319): same constructor
+    (``params`` = the argparse namespace of train.py:54-90, ``exp_dir``, ``use_cuda``, ``multi_gpu``), the same
+    ``train(generator, support_sets, reconstructor)`` entry point and the same files under
+    ``experiments/{wip,complete}/<exp_dir>/``: ``stats.json`` ({iteration: means of the last log window}),
+    ``models/support_sets_init.pt``, ``models/checkpoint.pt`` ({'iter', 'support_sets', 'reconstructor'} every
+    ``ckp_freq``), ``models/support_sets.pt`` and ``models/reconstructor.pt`` at the end, then wip -> complete
+    without the checkpoint.  Resume restarts at the checkpointed iteration with fresh optimiser state, as the
+    reference does (:83-89).
+
+    What differs, by design:
+      * every iteration is one ``PairedTrainer.step`` (optionally a CUDA-graph replay) instead of ~40 framework
+        calls, and the four statistics stay on the device until a log line needs them (the reference reads three
+        scalars back per iteration, :257-261);
+      * latents, path indices and magnitudes are still drawn on the HOST with the reference's calls in the
+        reference's order (:187, :193, :204-214), so a seeded run consumes the same random stream;
+      * ``multi_gpu`` means one process per GPU under torchrun (torch.distributed) rather than nn.DataParallel:
+        every rank draws the full batch from the same seed and takes its shard, gradients are summed in one
+        all-reduce, rank 0 writes the files;
+      * there is no CPU path: ``use_cuda=False`` raises.
+    """
+
+    def __init__(self, params=None, exp_dir=None, use_cuda=False, multi_gpu=False, root='experiments'):
+        import json
+        import os
+        import os.path as osp
+        if params is None:
+            raise ValueError('Cannot build a Trainer instance with empty params: params={}'.format(params))
+        self.params = params
+        self.use_cuda = use_cuda
+        self.multi_gpu = multi_gpu
+        self.world, self.rank, self.local_rank = wdist.env_world()
+        self.wip_dir = osp.join(root, 'wip', exp_dir)
+        self.complete_dir = osp.join(root, 'complete', exp_dir)
+        self.stats_json = osp.join(self.wip_dir, 'stats.json')
+        self.models_dir = osp.join(self.wip_dir, 'models')
+        self.checkpoint = osp.join(self.models_dir, 'checkpoint.pt')
+        if self.rank == 0:
+            os.makedirs(self.models_dir, exist_ok=True)
+            if not osp.isfile(self.stats_json):
+                with open(self.stats_json, 'w') as out:
+                    json.dump({}, out)
+        from .aux import TrainingStatTracker
+        self.stat_tracker = TrainingStatTracker()
+        self.iter_times = []
+        self.tb_writer = None
+        if getattr(params, 'tensorboard', False) and self.rank == 0:
+            try:                                                          # optional, as in the reference (:56-64)
+                from torch.utils.tensorboard import SummaryWriter
+                tb_dir = osp.join(self.wip_dir, 'tensorboard')
+                os.makedirs(tb_dir, exist_ok=True)
+                self.tb_writer = SummaryWriter(log_dir=tb_dir)
+            except Exception as e:                                        # pragma: no cover
+                print('#. TensorBoard unavailable: %r' % (e,))
+
+    # ---- checkpoint I/O (state dicts are saved as CPU clones: parameters are views into flat buffers) ----
+    @staticmethod
+    def _cpu_state(module):
+        return {k: v.detach().to('cpu', copy=True) for k, v in module.state_dict().items()}
+
+    def get_starting_iteration(self, support_sets, reconstructor):
+        """lib/trainer.py:74-89."""
+        import os.path as osp
+        starting_iter = 1
+        if osp.isfile(self.checkpoint):
+            ckpt = torch.load(self.checkpoint, map_location='cpu')
+            starting_iter = ckpt['iter']
+            support_sets.load_state_dict(ckpt['support_sets'])
+            reconstructor.load_state_dict(ckpt['reconstructor'])
+        return starting_iter
+
+    def _finish(self, quiet=False):
+        import shutil
+        if self.rank != 0:
+            return
+        try:
+            shutil.copytree(src=self.wip_dir, dst=self.complete_dir, ignore=shutil.ignore_patterns('checkpoint.pt'))
+        except IOError as e:
+            if not quiet:
+                print('  \\__Already exists -- {}'.format(e))
+
+    def log_progress(self, iteration, mean_iter_time, elapsed_time, eta):
+        """lib/trainer.py:91-127: fold the window means into stats.json (keyed by iteration) and print them."""
+        import json
+        from .aux import sec2dhms
+        stats = self.stat_tracker.get_means()
+        self.stat_tracker.flush()
+        if self.rank != 0:
+            return stats
+        with open(self.stats_json) as f:
+            stats_dict = json.load(f)
+        stats_dict.update({iteration: {k: float(v) for k, v in stats.items()}})
+        with open(self.stats_json, 'w') as out:
+            json.dump(stats_dict, out)
+        if not getattr(self.params, 'quiet', False):
+            print('  \\__.Training [bs: {}] [iter: {:06d}/{:06d}]'.format(self.params.batch_size, iteration, self.params.max_iter))
+            print('      \\__Batch accuracy      : {:.03f}'.format(stats['accuracy']))
+            print('      \\__Classification loss : {:.08f}'.format(stats['classification_loss']))
+            print('      \\__Regression loss     : {:.08f}'.format(stats['regression_loss']))
+            print('      \\__Total loss          : {:.08f}'.format(stats['total_loss']))
+            print('      \\__Mean iter time      : {:.3f} sec'.format(mean_iter_time))
+            print('      \\__Elapsed time        : {}'.format(sec2dhms(elapsed_time)))
+            print('      \\__ETA                 : {}'.format(sec2dhms(eta)))
+        return stats
+
+    def draw_batch(self, dim_z):
+        """The reference's host draws in the reference's order (lib/trainer.py:187-221): z, path indices, then the
+        magnitude pool and its index-weighted multinomial pick."""
+        from .aux import sample_z
+        p = self.params
+        z = sample_z(batch_size=p.batch_size, dim_z=dim_z, truncation=getattr(p, 'z_truncation', None))
+        indices = torch.randint(0, p.num_support_sets, [p.batch_size])
+        magnitudes = _reference_magnitudes(p.batch_size, p.min_shift_magnitude, p.max_shift_magnitude)
+        return z, indices, magnitudes
+
+    def _device(self):
+        return torch.device('cuda', self.local_rank if self.multi_gpu else torch.cuda.current_device())
+
+    def _make_engine(self, generator, support_sets, reconstructor):
+        p = self.params
+        return PairedTrainer(generator, support_sets, reconstructor, support_set_lr=p.support_set_lr,
+                             reconstructor_lr=p.reconstructor_lr, lambda_cls=p.lambda_cls, lambda_reg=p.lambda_reg,
+                             shift_in_w_space=bool(getattr(p, 'shift_in_w_space', False)))
+
+    def train(self, generator, support_sets, reconstructor):
+        import os.path as osp
+        import sys
+        import time
+        p = self.params
+        if not self.use_cuda:
+            raise RuntimeError('warpedganspace_b200.Trainer needs use_cuda=True: libwgs_b200 has no CPU fallback')
+        if self.rank == 0:
+            torch.save(self._cpu_state(support_sets), osp.join(self.models_dir, 'support_sets_init.pt'))
+        device = self._device()
+        generator.to(device).eval()
+        support_sets.to(device).train()
+        reconstructor.to(device).train()
+        starting_iter = self.get_starting_iteration(support_sets, reconstructor)
+        if starting_iter == p.max_iter:                                            # :169-177
+            print('#. This experiment has already been completed and can be found @ {}'.format(self.wip_dir))
+            self._finish()
+            sys.exit()
+        engine = self._make_engine(generator, support_sets, reconstructor)
+        lo, hi = wdist.shard_range(p.batch_size, self.rank, self.world) if self.multi_gpu else (0, p.batch_size)
+        use_graph = bool(getattr(p, 'cuda_graph', False))
+        window = []                                                                # device-side [acc, cls, reg, loss] rows
+        t0 = time.time()
+        for iteration in range(starting_iter, p.max_iter + 1):
+            iter_t0 = time.time()
+            z, indices, magnitudes = self.draw_batch(generator.dim_z)
+            batch = tuple(t[lo:hi].to(device, non_blocking=True) for t in (z, indices, magnitudes))
+            if use_graph and engine._graph is None and iteration == starting_iter:
+                engine.capture(*batch)
+            out = engine.step(*batch)
+            window.append(torch.stack([out['accuracy'], out['cls'], out['reg'], out['loss']]).clone())
+            if iteration % p.log_freq == 0 or iteration % p.ckp_freq == 0 or iteration == p.max_iter:
+                rows = torch.stack(window)
+                if self.world > 1 and self.multi_gpu:                              # equal shards: mean of rank means
+                    wdist.all_reduce_sum_([rows])
+                    rows /= self.world
+                for acc, cls, reg, tot in rows.cpu().tolist():                     # the only device->host read
+                    self.stat_tracker.update(acc, cls, reg, tot)
+                window = []
+                if self.tb_writer is not None:
+                    for key, value in self.stat_tracker.get_means().items():
+                        self.tb_writer.add_scalar(key, value, iteration)
+            self.iter_times.append(time.time() - iter_t0)
+            elapsed = time.time() - t0
+            if iteration % p.log_freq == 0:
+                eta = elapsed * ((p.max_iter - iteration) / (iteration - starting_iter + 1))
+                self.log_progress(iteration, sum(self.iter_times) / len(self.iter_times), elapsed, eta)
+            if iteration % p.ckp_freq == 0 and self.rank == 0:                     # :288-296
+                torch.save({'iter': iteration, 'support_sets': self._cpu_state(support_sets),
+                            'reconstructor': self._cpu_state(reconstructor)}, self.checkpoint)
+        if self.rank == 0:                                                         # :301-319
+            torch.save(self._cpu_state(support_sets), osp.join(self.models_dir, 'support_sets.pt'))
+            torch.save(self._cpu_state(reconstructor), osp.join(self.models_dir, 'reconstructor.pt'))
+        self._finish(quiet=True)
+        return engine
+
+
+def _reference_magnitudes(batch, min_mag, max_mag):
+    """Host draw of lib/trainer.py:204-214 from the global torch RNG (positive pool first, as there)."""
+    pos = (min_mag - max_mag) * torch.rand(batch) + max_mag
+    neg = (min_mag - max_mag) * torch.rand(batch) - min_mag
+    pool = torch.cat((neg, pos))
+    ids = torch.arange(len(pool), dtype=torch.float)
+    return pool[torch.multinomial(input=ids, num_samples=batch, replacement=False)]
