@@ -94,6 +94,12 @@ typedef struct wgs_conv_desc {
     int out_from_n;          /* fp32 `out` only for images n >= out_from_n (the half that is back-propagated) */
     const float* rgb_w;      /* [out_n][3][cout] modulated ToRGB weights (model.py:270-282) or NULL          */
     float* rgb_out;          /* [out_n][grid_h][grid_w][3] += act . rgb_w  (pre-initialised: bias + skip)    */
+    /* phase-packed output (all output phases of a strided data-gradient / transposed conv in ONE launch): when
+     * group_size > 0 the cout channels are cout/group_size groups of group_size channels; group g = gy*group_w + gx
+     * is written to output pixel (oy*out_ystep+out_y0+gy, ox*out_xstep+out_x0+gx), channel co % group_size, and only
+     * if that pixel lies inside out_h x out_w.  The weights hold one row block per group (zero where a phase has no
+     * tap at a given input shift).  fp32 output only (no out_split / rgb_out / noise).                          */
+    int group_size, group_w, out_h, out_w;
 } wgs_conv_desc;
 
 /* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls
@@ -110,6 +116,25 @@ int wgs_conv_desc_size(void);
 int wgs_linear_small(const float* x, long long x_ld, const float* W, long long w_ld, const float* bias,
                      float* out, long long out_ld, int B, int I, int O, float wscale, float bscale,
                      int in_square, int epi, float eps, int accumulate, void* stream);
+/* Grouped form: ONE launch over `count` independent small linears of the same batch size B (all 17 demodulation
+ * vectors of a StyleGAN2 forward, their backward, the mapping-network backward with the fused-lrelu derivative folded
+ * into the input).  out[b,o] (+)= mul[b,o] * epi(wscale * sum_i f(x[b,i], x2[b,i]) * W[o,i] + bscale * bias[o]);
+ * in_mode 0: x, 1: x^2, 2: x * dlrelu(x2) (x2 = forward output of models/StyleGAN2/model.py:127-128),
+ * 3: x * x2^3 (derivative of the rsqrt in :194-195).  x2, bias, mul may be NULL where unused.                  */
+#define WGS_MAX_LINEAR_GROUP 32
+typedef struct {
+    const float* x;   long long x_ld;
+    const float* x2;  long long x2_ld;
+    const float* W;   long long w_ld;
+    const float* bias;
+    const float* mul; long long mul_ld;
+    float* out;       long long out_ld;
+    int I, O;
+    float wscale, bscale, eps;
+    int in_mode, epi, accumulate;
+} wgs_linear_problem;
+int wgs_linear_group(const wgs_linear_problem* problems, int count, int B, void* stream);
+int wgs_linear_problem_size(void);
 /* PixelNorm over latent rows (model.py:9-15). */
 int wgs_pixelnorm_rows(const float* x, float* out, int B, int d, void* stream);
 /* Separable 4-tap FIR (upfirdn2d up=down=1: Blur, model.py:66-81; op/upfirdn2d_kernel.cu:52-137) fused with

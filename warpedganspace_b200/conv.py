@@ -47,6 +47,7 @@ class ConvDesc(ctypes.Structure):
         ('noise', ctypes.c_void_p), ('noise_w', ctypes.c_float), ('noise_ld', ctypes.c_int),
         ('out_split', ctypes.c_void_p), ('split_scale', ctypes.c_void_p), ('split_scale_ld', ctypes.c_longlong),
         ('out_from_n', ctypes.c_int), ('rgb_w', ctypes.c_void_p), ('rgb_out', ctypes.c_void_p),
+        ('group_size', ctypes.c_int), ('group_w', ctypes.c_int), ('out_h', ctypes.c_int), ('out_w', ctypes.c_int),
     ]
 
 
@@ -89,7 +90,7 @@ def pack_weights(w):
 
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
               alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None,
-              out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None):
+              out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None, groups=None):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -125,6 +126,9 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
     d.alpha = alpha.data_ptr() if alpha is not None else None
     d.beta = beta.data_ptr() if beta is not None else None
     d.act, d.accumulate, d.force_bn = act, int(accumulate), force_bn
+    if groups is not None:                       # phase-packed output: (group_size, group_w), see include/wgs_b200.h
+        d.group_size, d.group_w = groups
+        d.out_h, d.out_w = out.shape[1], out.shape[2]
     if noise is not None:
         assert noise.is_contiguous() and noise.dim() == 2
         d.noise, d.noise_w, d.noise_ld = noise.data_ptr(), float(noise_w), noise.shape[1]
@@ -173,4 +177,75 @@ def conv_transpose2d_s2(x_split, w_split, k, *, out=None, crop=0, **kw_args):
                 continue
             taps = [((py + crop - ky) // 2, (px + crop - kx) // 2, ky * k + kx) for ky in kys for kx in kxs]
             conv_taps(x_split, w_split, taps, out, grid=(gh, gw), out_origin=(py, px), out_step=(2, 2), **kw_args)
+    return out
+
+
+# ---- phase-packed (merged) strided data-gradients / transposed convs -----------------------------------------------
+# Every output phase (py, px) of a stride-s data-gradient or transposed conv is a short tap list over the SAME small
+# set of input shifts.  Launching them separately runs N = C-wide MMAs whose cost is dominated by fetching the
+# 128-row A operand (profiles/r01_conv_ncu_step.md); stacking the phases along N gives one launch with
+# N = s*s*C, one patch load per shift, and zero weight blocks where a phase has no tap at a shift.
+_PHASE_PLANS = {}
+
+
+def _phase_plan(kind, kh, kw, stride, padding, device):
+    """-> (shifts [(sy, sx)], idx int64 [S*G] of tap ids (kh*kw = zero tap), G) for
+    kind 'dgrad': dx[s*q+py] = sum_k dy[q + (py+p-k)/s] w[k];  kind 'convT': out[s*q+py] = sum_k x[q + (py-k)/s] w[k]."""
+    key = (kind, kh, kw, stride, padding, str(device))
+    hit = _PHASE_PLANS.get(key)
+    if hit is not None:
+        return hit
+    s, T = stride, kh * kw
+    off = padding if kind == 'dgrad' else 0
+    ent = {}
+    for py in range(s):
+        for px in range(s):
+            for ky in range(kh):
+                for kx in range(kw):
+                    if (py + off - ky) % s == 0 and (px + off - kx) % s == 0:
+                        ent[((py + off - ky) // s, (px + off - kx) // s, py * s + px)] = ky * kw + kx
+    shifts = sorted({(a, b) for a, b, _ in ent})
+    G = s * s
+    idx = [ent.get((sy, sx, g), T) for sy, sx in shifts for g in range(G)]
+    hit = (shifts, torch.tensor(idx, dtype=torch.int64, device=device), G)
+    _PHASE_PLANS[key] = hit
+    return hit
+
+
+def merged_phase_weights(w_src, idx, S, G):
+    """w_src fp32 [rows, K, T] -> split32 [S, G*rows, ceil(K/32), 64] with block (s, g) = w_src[:, :, idx[s*G+g]]
+    (zero where idx == T)."""
+    rows, K, T = w_src.shape
+    w_ext = torch.cat([w_src, w_src.new_zeros(rows, K, 1)], dim=2)
+    sel = w_ext.index_select(2, idx)                                    # [rows, K, S*G]
+    return pack_split32(sel.permute(2, 0, 1).reshape(S, G * rows, K).contiguous())
+
+
+def conv_dgrad_merged(dys, w, in_hw, stride, padding, out=None, accumulate=False, w_merged=None):
+    """Data gradient of F.conv2d(x, w, stride, padding) for stride > 1 in ONE launch -> dx fp32 [N, H, W, Ci]."""
+    co, ci, kh, kw = w.shape
+    h, wd = in_hw
+    n = dys.shape[0]
+    shifts, idx, G = _phase_plan('dgrad', kh, kw, stride, padding, dys.device)
+    if w_merged is None:
+        w_merged = merged_phase_weights(w.detach().permute(1, 0, 2, 3).reshape(ci, co, kh * kw), idx, len(shifts), G)
+    dx = out if out is not None else torch.empty(n, h, wd, ci, device=dys.device, dtype=torch.float32)
+    taps = [(sy, sx, i) for i, (sy, sx) in enumerate(shifts)]
+    gh, gw = (h + stride - 1) // stride, (wd + stride - 1) // stride
+    conv_taps(dys, w_merged, taps, dx, grid=(gh, gw), out_step=(stride, stride), cout=G * ci, cin=co,
+              accumulate=accumulate, groups=(ci, stride))
+    return dx
+
+
+def conv_transpose2d_s2_merged(x_split, w_merged, k, co, out=None):
+    """F.conv_transpose2d(stride=2, padding=0) for a k x k kernel in ONE launch; w_merged from
+    merged_phase_weights(w[Co, Ci, k*k], *_phase_plan('convT', k, k, 2, 0))."""
+    n, h, w_, _, _ = x_split.shape
+    oh, ow = 2 * (h - 1) + k, 2 * (w_ - 1) + k
+    shifts, _, G = _phase_plan('convT', k, k, 2, 0, x_split.device)
+    if out is None:
+        out = torch.empty(n, oh, ow, co, dtype=torch.float32, device=x_split.device)
+    taps = [(sy, sx, i) for i, (sy, sx) in enumerate(shifts)]
+    conv_taps(x_split, w_merged, taps, out, grid=((oh + 1) // 2, (ow + 1) // 2), out_step=(2, 2), cout=G * co,
+              groups=(co, 2))
     return out

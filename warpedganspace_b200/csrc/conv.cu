@@ -56,6 +56,7 @@ struct ConvKernelParams {
     // halo variant: the (bh + wy - 1) x (bw + wx - 1) input patch of a chunk is loaded once and every tap
     // addresses it through its UMMA descriptor
     int dy0, dx0, halo_h, halo_w, a_stage_bytes;
+    int group_size, group_w, out_h, out_w;   // phase-packed output (0 = off)
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -106,7 +107,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     ptx::mbar_wait(acc_bar, 0);
     ptx::tc_fence_after();
     const bool write_f32 = FUSED ? (p.out != nullptr && n >= p.out_from_n) : true;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const int gsz = FUSED ? 0 : p.group_size;                // phase-packed output: plain epilogue only
+    const bool g_uniform = (gsz == 0) || (gsz % 16 == 0);    // a 16-channel block never straddles two groups
+    const int py0 = oy * p.out_ystep + p.out_y0, px0 = ox * p.out_xstep + p.out_x0;
     const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
     const uint32_t ep_s = ptx::smem_u32(ep);                 // explicit ld.shared: the generic pointer costs LD.E + a stall per use
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
@@ -115,7 +118,17 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
         ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
         const int co = co0 + c;
         if (!valid || co >= p.cout) continue;
-        const bool fast = cs && (co + 16 <= p.cout);         // whole 16-channel group valid, constants staged in smem
+        // destination of this 16-channel block: `dptr + cof` (identity unless the output is phase-packed)
+        float* dptr = dst;
+        int cof = co;
+        if (gsz && g_uniform) {
+            const int g = co / gsz, gy = g / p.group_w, gx = g - gy * p.group_w;
+            if (py0 + gy >= p.out_h || px0 + gx >= p.out_w) continue;
+            dptr = dst + (long long)gy * p.out_sy + (long long)gx * p.out_sx;
+            cof = co - g * gsz;
+        }
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(dptr + cof) & 15) == 0);
+        const bool fast = cs && g_uniform && (co + 16 <= p.cout);   // whole 16-channel block valid, constants staged in smem
         if (fast) {
             const uint32_t ea = ep_s + (uint32_t)c * 4u, eb = ea + (uint32_t)BN * 4u;
 #pragma unroll
@@ -130,12 +143,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                 if (vec_ok) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        const float4 o = *reinterpret_cast<const float4*>(dst + co + i);
+                        const float4 o = *reinterpret_cast<const float4*>(dptr + cof + i);
                         v[i] += o.x; v[i + 1] += o.y; v[i + 2] += o.z; v[i + 3] += o.w;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += dst[co + i];
+                    for (int i = 0; i < 16; ++i) v[i] += dptr[cof + i];
                 }
             }
             if (p.act == 1) {
@@ -148,6 +161,27 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 1.41421356237309515f * (v[i] > 0.f ? v[i] : 0.2f * v[i]);
             }
+        } else if (!g_uniform) {
+            // phase-packed output whose groups are narrower than a 16-channel block (e.g. the 6-channel stem data
+            // gradient): element-wise destination, written here
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int cc = co + i;
+                if (cc >= p.cout) break;
+                const int g = cc / gsz, gy = g / p.group_w, gx = g - gy * p.group_w;
+                if (py0 + gy >= p.out_h || px0 + gx >= p.out_w) continue;
+                float r = v[i];
+                if (cs) r = r * ep[c + i] + nz + ep[BN + c + i];
+                else {
+                    if (alpha) r *= __ldg(alpha + cc);
+                    r += nz;
+                    if (p.beta) r += __ldg(p.beta + cc);
+                }
+                float* d1 = dst + (long long)gy * p.out_sy + (long long)gx * p.out_sx + (cc - g * gsz);
+                if (p.accumulate) r += *d1;
+                *d1 = apply_act(r, p.act);
+            }
+            continue;
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -160,7 +194,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                         r += nz;
                         if (p.beta) r += __ldg(p.beta + cc);
                     }
-                    if (p.accumulate) r += dst[cc];
+                    if (p.accumulate) r += dptr[cof + i];
                     v[i] = apply_act(r, p.act);
                 } else {
                     v[i] = 0.f;
@@ -226,9 +260,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
             if (vec_ok && co + 16 <= p.cout) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4*>(dst + co + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    *reinterpret_cast<float4*>(dptr + cof + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else {
-                for (int i = 0; i < 16 && co + i < p.cout; ++i) dst[co + i] = v[i];
+                for (int i = 0; i < 16 && co + i < p.cout; ++i) dptr[cof + i] = v[i];
             }
         }
     }
@@ -475,8 +509,14 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ in, const __n
                     acc += ah * bh + ah * bl + al * bh;
                 }
         }
-        float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
-                     (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx + co;
+        int gy = 0, gx = 0, cw = co;
+        if (p.group_size) {
+            const int g = co / p.group_size;
+            gy = g / p.group_w; gx = g - gy * p.group_w; cw = co - g * p.group_size;
+            if (oy * p.out_ystep + p.out_y0 + gy >= p.out_h || ox * p.out_xstep + p.out_x0 + gx >= p.out_w) continue;
+        }
+        float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0 + gy) * p.out_sy +
+                     (long long)(ox * p.out_xstep + p.out_x0 + gx) * p.out_sx + cw;
         if (p.alpha) acc *= p.alpha[(size_t)n * p.cout + co];
         if (p.noise)
             acc += p.noise_w * p.noise[(size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0)];
@@ -549,6 +589,15 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.noise = d->noise; p.noise_w = d->noise_w; p.noise_ld = d->noise_ld;
     p.out_split = d->out_split; p.split_scale = d->split_scale; p.split_scale_ld = d->split_scale_ld;
     p.out_from_n = d->out_from_n; p.rgb_w = d->rgb_w; p.rgb_out = d->rgb_out;
+    p.group_size = d->group_size; p.group_w = d->group_w; p.out_h = d->out_h; p.out_w = d->out_w;
+    WGS_REQUIRE(d->group_size >= 0, "conv: bad group_size");
+    if (d->group_size > 0) {
+        WGS_REQUIRE(d->cout % d->group_size == 0 && d->group_w >= 1 && (d->cout / d->group_size) % d->group_w == 0,
+                    "conv: phase-packed output needs cout = groups * group_size with groups % group_w == 0");
+        WGS_REQUIRE(d->out != nullptr && !d->out_split && !d->rgb_out && !d->noise && d->out_from_n == 0,
+                    "conv: phase-packed output is fp32 only");
+        WGS_REQUIRE(d->out_h > 0 && d->out_w > 0, "conv: phase-packed output needs out_h / out_w");
+    }
     WGS_REQUIRE(d->out != nullptr || d->out_split != nullptr || d->rgb_out != nullptr, "conv: no output requested");
     WGS_REQUIRE((!d->out_split && !d->rgb_out) || (d->out_ystep == 1 && d->out_xstep == 1 && d->out_y0 == 0 && d->out_x0 == 0),
                 "conv: fused split32 / ToRGB outputs need the identity output mapping");
@@ -611,10 +660,13 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         int hBN = std::min(64, (d->cout + 15) / 16 * 16);
         const int halo_h = 16 + wy - 1, halo_w = 8 + wx - 1;
         const int a_bytes = (halo_h * halo_w * 128 + 1023) / 1024 * 1024;
-        while (hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > 72 * 1024) hBN /= 2;
+        // 3 CTAs / SM up to 72 KB per stage; long tap lists (the 16 shifts of the merged 7x7/2 stem data-gradient) may
+        // take up to 108 KB (2 CTAs / SM): still far less L2->SM traffic than re-loading the patch per tap
+        const int h_limit = (d->num_taps >= 12 ? 108 : 72) * 1024;
+        while (hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > h_limit) hBN /= 2;
         const int h_stage = a_bytes + d->num_taps * hBN * 128;
         const bool eligible = halo_mode && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
-                              d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && h_stage <= 72 * 1024 &&
+                              d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && h_stage <= h_limit &&
                               (d->c_chunks == 1 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4));
         // (64 -> 64 3x3, two chunks x two channel tiles, measured faster on the per-tap kernel: 0.73 vs 0.89 ms)
         if (eligible) {

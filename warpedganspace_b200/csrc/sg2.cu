@@ -3,36 +3,75 @@
 // the FIR-upsampled skip.  All HBM/latency-bound CUDA-core work.
 #include "common.cuh"
 #include "wgs_b200.h"
+#include <string.h>
+#include <stdlib.h>
 
 namespace wgs {
 
 // ------------------------------------------------------------------------------------------------
-// out[b, o] = epi( wscale * sum_i f(x[b, i]) * W[o, i]  (+ bscale * bias[o]) )       B small, I % 4 == 0
-//   f = identity or square;  epi: 0 linear, 1 sqrt(2)*lrelu(0.2), 2 rsqrt(. + eps)
-// One warp per output feature: the weight row is streamed once with float4 loads and reused for every
-// batch row (EqualLinear, models/StyleGAN2/model.py:110-131; demod :194-195 restated as a linear on s^2).
+// out[b, o] (+)= mul[b, o] * epi( wscale * sum_i f(x[b, i], x2[b, i]) * W[o, i]  (+ bscale * bias[o]) )     B small, I % 4 == 0
+//   f (in_mode): 0 x;  1 x^2;  2 x * dlrelu(x2) with dlrelu = sqrt2 (x2 > 0) or 0.2 sqrt2 (backward of 'fused_lrelu',
+//               x2 = the layer's forward OUTPUT);  3 x * x2^3 (demodulation backward: dd * d^3)
+//   epi: 0 linear, 1 sqrt(2)*lrelu(0.2), 2 rsqrt(. + eps)
+// One warp per output feature: the weight row is streamed once with float4 loads (four in flight per lane) and reused
+// for every batch row (EqualLinear, models/StyleGAN2/model.py:110-131; demod :194-195 restated as a linear on s^2).
+// A launch covers `count` independent problems of the same batch size (blockIdx.x -> problem through block_start).
 constexpr int LIN_BT = 8;
+constexpr int LIN_WARPS = 4;
 
-__global__ void __launch_bounds__(256)
-linear_small_kernel(const float* __restrict__ x, long long x_ld, const float* __restrict__ W, long long w_ld,
-                    const float* __restrict__ bias, float* __restrict__ out, long long out_ld, int B, int I, int O,
-                    float wscale, float bscale, int in_square, int epi, float eps, int accumulate) {
+struct LinearGroup {
+    wgs_linear_problem prob[WGS_MAX_LINEAR_GROUP];
+    int block_start[WGS_MAX_LINEAR_GROUP + 1];
+    int count, B;
+};
+
+__device__ __forceinline__ float4 lin_in(const wgs_linear_problem& q, int b, int i) {
+    float4 x4 = __ldg(reinterpret_cast<const float4*>(q.x + (size_t)b * q.x_ld + i));
+    if (q.in_mode == 1) {
+        x4.x *= x4.x; x4.y *= x4.y; x4.z *= x4.z; x4.w *= x4.w;
+    } else if (q.in_mode == 2) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(q.x2 + (size_t)b * q.x2_ld + i));
+        const float up = 1.41421356237309515f, dn = 0.2f * 1.41421356237309515f;
+        x4.x *= h.x > 0.f ? up : dn; x4.y *= h.y > 0.f ? up : dn; x4.z *= h.z > 0.f ? up : dn; x4.w *= h.w > 0.f ? up : dn;
+    } else if (q.in_mode == 3) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(q.x2 + (size_t)b * q.x2_ld + i));
+        x4.x *= h.x * h.x * h.x; x4.y *= h.y * h.y * h.y; x4.z *= h.z * h.z * h.z; x4.w *= h.w * h.w * h.w;
+    }
+    return x4;
+}
+
+__global__ void __launch_bounds__(LIN_WARPS * 32)
+linear_group_kernel(const __grid_constant__ LinearGroup g) {
+    int pi = 0;
+    while (pi + 1 < g.count && (int)blockIdx.x >= g.block_start[pi + 1]) ++pi;
+    const wgs_linear_problem& q = g.prob[pi];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o = blockIdx.x * 8 + warp;
-    if (o >= O) return;
-    const float* wrow = W + (size_t)o * w_ld;
+    const int o = ((int)blockIdx.x - g.block_start[pi]) * LIN_WARPS + warp;
+    if (o >= q.O) return;
+    const float* wrow = q.W + (size_t)o * q.w_ld;
+    const int B = g.B, I = q.I;
     for (int b0 = 0; b0 < B; b0 += LIN_BT) {
         float acc[LIN_BT];
 #pragma unroll
         for (int t = 0; t < LIN_BT; ++t) acc[t] = 0.f;
-        for (int i = lane * 4; i < I; i += 128) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + i));
+        for (int i0 = lane * 4; i0 < I; i0 += 512) {
+            float4 w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * 128;
+                w4[j] = i < I ? __ldg(reinterpret_cast<const float4*>(wrow + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int t = 0; t < LIN_BT; ++t) {
                 if (b0 + t < B) {
-                    float4 x4 = __ldg(reinterpret_cast<const float4*>(x + (size_t)(b0 + t) * x_ld + i));
-                    if (in_square) { x4.x *= x4.x; x4.y *= x4.y; x4.z *= x4.z; x4.w *= x4.w; }
-                    acc[t] += w4.x * x4.x + w4.y * x4.y + w4.z * x4.z + w4.w * x4.w;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * 128;
+                        if (i < I) {
+                            const float4 x4 = lin_in(q, b0 + t, i);
+                            acc[t] += w4[j].x * x4.x + w4[j].y * x4.y + w4[j].z * x4.z + w4[j].w * x4.w;
+                        }
+                    }
                 }
             }
         }
@@ -42,15 +81,16 @@ linear_small_kernel(const float* __restrict__ x, long long x_ld, const float* __
             float v = 0.f;
 #pragma unroll
             for (int t = 0; t < LIN_BT; ++t) if (t == lane) v = acc[t];
-            v *= wscale;
-            if (epi == 2) {
-                v = rsqrtf(v + eps);
+            v *= q.wscale;
+            if (q.epi == 2) {
+                v = rsqrtf(v + q.eps);
             } else {
-                if (bias) v += bscale * __ldg(bias + o);
-                if (epi == 1) v = 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);
+                if (q.bias) v += q.bscale * __ldg(q.bias + o);
+                if (q.epi == 1) v = 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);
             }
-            float* dst = out + (size_t)(b0 + lane) * out_ld + o;
-            *dst = accumulate ? (*dst + v) : v;
+            if (q.mul) v *= __ldg(q.mul + (size_t)(b0 + lane) * q.mul_ld + o);
+            float* dst = q.out + (size_t)(b0 + lane) * q.out_ld + o;
+            *dst = q.accumulate ? (*dst + v) : v;
         }
     }
 }
@@ -70,9 +110,11 @@ __global__ void pixelnorm_rows_kernel(const float* __restrict__ x, float* __rest
 // Separable 4-tap FIR (upfirdn2d with up = down = 1, op/upfirdn2d_kernel.cu:52-137) fused with the
 // StyledConv tail: out = act(alpha[n,c] * fir(y)[Y,X,c] + noise_w * noise[Y,X] + beta[c]).
 // y: [N, Hin, Win, C] NHWC, out: [N, Hout, Wout, C]; fir(y)[Y,X] = sum_ij kf[i] kf[j] y[Y+i-pad0, X+j-pad0].
-constexpr int FIR_ROWS = 8;                                        // output rows per thread
-
-__global__ void __launch_bounds__(256, 2)
+// FIR_ROWS = output rows per thread: 8 = 5.5 loads per output at 126 registers (2 blocks / SM); 4 = 7 loads per output
+// at <= 64 registers (4 blocks / SM) - the kernel is latency-bound on its loads (55 % long-scoreboard stalls at 3.9
+// warps per scheduler, profiles/r01_step_ncu.md), so occupancy buys more than the extra L1 traffic costs.
+template <int FIR_ROWS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
 fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int Hin, int Win, int Hout, int Wout,
                 int C, int pad0, float k0, float k1, float k2, float k3, const float* __restrict__ alpha,
                 const float* __restrict__ beta, const float* __restrict__ noise, float noise_w, int act,
@@ -300,18 +342,49 @@ torgb_kernel(const float* __restrict__ a, const float* __restrict__ s, long long
 
 using namespace wgs;
 
-extern "C" int wgs_linear_small(const float* x, long long x_ld, const float* W, long long w_ld, const float* bias,
-                                float* out, long long out_ld, int B, int I, int O, float wscale, float bscale,
-                                int in_square, int epi, float eps, int accumulate, void* stream) {
-    WGS_REQUIRE(B >= 0 && I > 0 && O > 0, "linear_small: bad sizes");
-    WGS_REQUIRE(I % 4 == 0 && x_ld % 4 == 0 && w_ld % 4 == 0, "linear_small: I, x_ld, w_ld must be multiples of 4");
-    WGS_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)W & 15) == 0, "linear_small: operands must be 16-byte aligned");
+static int launch_linear_group(const wgs_linear_problem* problems, int count, int B, void* stream) {
+    WGS_REQUIRE(problems != nullptr && count >= 1 && count <= WGS_MAX_LINEAR_GROUP, "linear_group: 1..WGS_MAX_LINEAR_GROUP problems");
+    WGS_REQUIRE(B >= 0, "linear_group: bad batch");
     if (B == 0) return 0;
-    linear_small_kernel<<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x, x_ld, W, w_ld, bias, out, out_ld, B, I, O,
-                                                                         wscale, bscale, in_square, epi, eps, accumulate);
+    LinearGroup g;
+    memset(&g, 0, sizeof(g));
+    g.count = count; g.B = B;
+    int blocks = 0;
+    for (int i = 0; i < count; ++i) {
+        const wgs_linear_problem& q = problems[i];
+        WGS_REQUIRE(q.I > 0 && q.O > 0, "linear: bad sizes");
+        WGS_REQUIRE(q.I % 4 == 0 && q.x_ld % 4 == 0 && q.w_ld % 4 == 0, "linear: I, x_ld, w_ld must be multiples of 4");
+        WGS_REQUIRE(((uintptr_t)q.x & 15) == 0 && ((uintptr_t)q.W & 15) == 0, "linear: operands must be 16-byte aligned");
+        WGS_REQUIRE(q.in_mode >= 0 && q.in_mode <= 3 && q.epi >= 0 && q.epi <= 2, "linear: bad in_mode / epi");
+        WGS_REQUIRE(q.in_mode < 2 || (q.x2 != nullptr && q.x2_ld % 4 == 0 && ((uintptr_t)q.x2 & 15) == 0),
+                    "linear: in_mode 2/3 needs a 16-byte aligned x2 with x2_ld % 4 == 0");
+        WGS_REQUIRE(q.x != nullptr && q.W != nullptr && q.out != nullptr, "linear: null operand");
+        g.prob[i] = q;
+        g.block_start[i] = blocks;
+        blocks += ceil_div(q.O, LIN_WARPS);
+    }
+    g.block_start[count] = blocks;
+    linear_group_kernel<<<blocks, LIN_WARPS * 32, 0, (cudaStream_t)stream>>>(g);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int wgs_linear_problem_size(void) { return (int)sizeof(wgs_linear_problem); }
+
+extern "C" int wgs_linear_group(const wgs_linear_problem* problems, int count, int B, void* stream) {
+    return launch_linear_group(problems, count, B, stream);
+}
+
+extern "C" int wgs_linear_small(const float* x, long long x_ld, const float* W, long long w_ld, const float* bias,
+                                float* out, long long out_ld, int B, int I, int O, float wscale, float bscale,
+                                int in_square, int epi, float eps, int accumulate, void* stream) {
+    wgs_linear_problem q;
+    memset(&q, 0, sizeof(q));
+    q.x = x; q.x_ld = x_ld; q.W = W; q.w_ld = w_ld; q.bias = bias; q.out = out; q.out_ld = out_ld;
+    q.I = I; q.O = O; q.wscale = wscale; q.bscale = bscale; q.eps = eps;
+    q.in_mode = in_square ? 1 : 0; q.epi = epi; q.accumulate = accumulate;
+    return launch_linear_group(&q, 1, B, stream);
 }
 
 extern "C" int wgs_pixelnorm_rows(const float* x, float* out, int B, int d, void* stream) {
@@ -329,11 +402,21 @@ extern "C" int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win,
                             int out_from_n, void* stream) {
     WGS_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "fir4_act: channels must be a multiple of 4");
     WGS_REQUIRE(taps4 != nullptr, "fir4_act: taps4 is a HOST pointer to 4 floats");
-    const long long total = (long long)N * ((Hout + FIR_ROWS - 1) / FIR_ROWS) * Wout * (C / 4);
+    static int rows = 0;
+    if (!rows) {
+        const char* e = getenv("WGS_FIR_ROWS");
+        rows = (e && atoi(e) == 4) ? 4 : 8;                  // measured: 8 rows 196.4 pairs/s, 4 rows 194.4
+    }
+    const long long total = (long long)N * ((Hout + rows - 1) / rows) * Wout * (C / 4);
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 48);
-    fir4_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1],
-                                                              taps4[2], taps4[3], alpha, beta, noise, noise_w, act,
-                                                              (__nv_bfloat16*)out_split, split_scale, split_scale_ld, out_from_n);
+    if (rows == 8)
+        fir4_act_kernel<8, 2><<<blocks, 256, 0, (cudaStream_t)stream>>>(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1],
+                                                                        taps4[2], taps4[3], alpha, beta, noise, noise_w, act,
+                                                                        (__nv_bfloat16*)out_split, split_scale, split_scale_ld, out_from_n);
+    else
+        fir4_act_kernel<4, 3><<<blocks, 256, 0, (cudaStream_t)stream>>>(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1],
+                                                                        taps4[2], taps4[3], alpha, beta, noise, noise_w, act,
+                                                                        (__nv_bfloat16*)out_split, split_scale, split_scale_ld, out_from_n);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

@@ -9,6 +9,7 @@ Every convolution (forward and data-gradient) runs on the tcgen05 tap-list kerne
 (torch ``channels_last``).  BatchNorm keeps the reference's train-mode batch statistics.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -20,6 +21,7 @@ from . import wgrad as WG
 
 
 _FROZEN_PACKS = {}
+MERGE_PHASES = os.environ.get('WGS_MERGE_PHASES', '1') != '0'      # 0 = one launch per output phase (A/B switch)
 
 
 def _packed(w, transposed):
@@ -116,6 +118,9 @@ def conv_dgrad(dys, w, in_hw, stride, padding, out=None, accumulate=False):
     co, ci, kh, kw = w.shape
     h, wd = in_hw
     n, oh, ow = dys.shape[0], dys.shape[1], dys.shape[2]
+    if stride > 1 and MERGE_PHASES and stride * stride * ci <= 1024:
+        # all stride*stride output phases in one launch (phase-packed output, conv.py)
+        return C.conv_dgrad_merged(dys, w, in_hw, stride, padding, out=out, accumulate=accumulate)
     wt = _packed(w, True)                                                   # [kh*kw, Ci, Co]
     dx = out if out is not None else torch.empty(n, h, wd, ci, device=dys.device, dtype=torch.float32)
     for py in range(stride):

@@ -15,6 +15,7 @@ B200-first restatement of the math (verified to 1e-15 in fp64)
 The frozen generator receives no weight gradients; backward only carries the data gradient to the styles.
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -78,6 +79,7 @@ def _to_rgb(ci, style_dim, upsample=True):
     return m
 
 
+MERGE_PHASES = os.environ.get('WGS_MERGE_PHASES', '1') != '0'
 _TAPS = (ctypes.c_float * 4)(0.25, 0.75, 0.75, 0.25)          # [1,3,3,1]/8 * 2 per axis (kernel * 4 overall)
 
 
@@ -151,6 +153,10 @@ class Generator(nn.Module):
                 # data-gradient weights: dx[ci] = sum_{taps,co} dy[co] * W[co,ci,tap]
                 if up:
                     ent['w_bwd'] = C.pack_weights(ws.permute(1, 0, 2, 3).contiguous())         # strided conv, same taps
+                    if co <= 64 and MERGE_PHASES:
+                        # all four output phases of the transposed conv stacked along N (one launch, conv.py)
+                        shifts, idx, G = C._phase_plan('convT', 3, 3, 2, 0, dev)
+                        ent['w_up'] = C.merged_phase_weights(ws.reshape(co, ci, 9).contiguous(), idx, len(shifts), G)
                 else:
                     ent['w_bwd'] = C.pack_weights(torch.flip(ws, [2, 3]).permute(1, 0, 2, 3).contiguous())
                 ent['wsq_t'] = ent['wsq'].t().contiguous()                    # [Ci, Co]
@@ -219,6 +225,53 @@ def _linear(x, W, bias, out, *, wscale=1.0, bscale=1.0, in_square=0, epi=0, eps=
     return out
 
 
+class LinearProblem(ctypes.Structure):
+    """Mirror of wgs_linear_problem (include/wgs_b200.h)."""
+    _fields_ = [('x', ctypes.c_void_p), ('x_ld', ctypes.c_longlong), ('x2', ctypes.c_void_p), ('x2_ld', ctypes.c_longlong),
+                ('W', ctypes.c_void_p), ('w_ld', ctypes.c_longlong), ('bias', ctypes.c_void_p),
+                ('mul', ctypes.c_void_p), ('mul_ld', ctypes.c_longlong), ('out', ctypes.c_void_p), ('out_ld', ctypes.c_longlong),
+                ('I', ctypes.c_int), ('O', ctypes.c_int), ('wscale', ctypes.c_float), ('bscale', ctypes.c_float),
+                ('eps', ctypes.c_float), ('in_mode', ctypes.c_int), ('epi', ctypes.c_int), ('accumulate', ctypes.c_int)]
+
+
+_MAX_GROUP = 32
+_layout_checked = False
+
+
+def _problem(x, W, out, *, x2=None, bias=None, mul=None, wscale=1.0, bscale=1.0, eps=0.0, in_mode=0, epi=0, accumulate=0):
+    """One small linear out[b,o] (+)= mul * epi(wscale * sum_i f(x, x2)[b,i] W[o,i] + bscale * bias[o]) (row-strided views ok)."""
+    for t in (x, W, out, x2, mul):
+        if t is not None:
+            if not t.is_cuda:
+                raise RuntimeError('StyleGAN2 kernels need CUDA tensors (no CPU fallback); got %s' % t.device)
+            assert t.stride(-1) == 1
+    q = LinearProblem()
+    q.x, q.x_ld = x.data_ptr(), x.stride(0)
+    q.x2, q.x2_ld = (x2.data_ptr(), x2.stride(0)) if x2 is not None else (None, 0)
+    q.W, q.w_ld = W.data_ptr(), W.stride(0)
+    q.bias = bias.data_ptr() if bias is not None else None
+    q.mul, q.mul_ld = (mul.data_ptr(), mul.stride(0)) if mul is not None else (None, 0)
+    q.out, q.out_ld = out.data_ptr(), out.stride(0)
+    q.I, q.O = x.shape[1], W.shape[0]
+    q.wscale, q.bscale, q.eps = float(wscale), float(bscale), float(eps)
+    q.in_mode, q.epi, q.accumulate = int(in_mode), int(epi), int(accumulate)
+    return q
+
+
+def _linear_group(problems, B):
+    """All `problems` (same batch size B) in as few launches as the C ABI's group limit allows (one, here)."""
+    global _layout_checked
+    lib = _lib.load()
+    if not _layout_checked:
+        if lib.wgs_linear_problem_size() != ctypes.sizeof(LinearProblem):
+            raise RuntimeError('wgs_linear_problem layout mismatch between header and ctypes mirror')
+        _layout_checked = True
+    for lo in range(0, len(problems), _MAX_GROUP):
+        chunk = problems[lo: lo + _MAX_GROUP]
+        arr = (LinearProblem * len(chunk))(*chunk)
+        _lib.check(lib.wgs_linear_group(arr, len(chunk), int(B), _lib.stream()))
+
+
 def _mapping_forward(G, z):
     """Returns the list [pixelnorm(z), h1, ..., h8 = w] (all kept for the backward pass)."""
     P = G.plan()
@@ -234,17 +287,20 @@ def _mapping_forward(G, z):
 
 
 def styles_and_demod(G, w):
-    """All 26 per-layer styles in one launch, then the 17 demodulation vectors."""
+    """All 26 per-layer styles in one launch, then the 17 demodulation vectors in one grouped launch."""
     P = G.plan()
     B = w.shape[0]
     s_all = torch.empty(B, P['sum_c'], device=w.device, dtype=torch.float32)
     _linear(w, P['mod_w'], P['mod_b'], s_all, wscale=1.0 / math.sqrt(G.style_dim), bscale=1.0)
-    demod = []
+    d_all = torch.empty(B * P['d_total'], device=w.device, dtype=torch.float32)
+    demod, problems, off = [], [], 0
     for e in P['styled']:
-        d = torch.empty(B, e['co'], device=w.device, dtype=torch.float32)
+        d = d_all[off: off + B * e['co']].view(B, e['co'])
+        off += B * e['co']
         s = s_all[:, e['s_off']: e['s_off'] + e['ci']]
-        _linear(s, e['wsq'], None, d, wscale=e['scale'] ** 2, in_square=1, epi=2, eps=1e-8)
+        problems.append(_problem(s, e['wsq'], d, wscale=e['scale'] ** 2, in_mode=1, epi=2, eps=1e-8))
         demod.append(d)
+    _linear_group(problems, B)
     return s_all, demod
 
 
@@ -283,7 +339,10 @@ def synthesis(G, w, tape=None, grad_from=0):
         xs_next = torch.empty(n, oh, ow, e['co'] // 32, 64, device=dev, dtype=torch.bfloat16) if nxt else None
         s_next = style_of(nxt) if nxt else None
         if e['up']:
-            y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3)                       # [B, 2h+1, 2w+1, Co] raw
+            if 'w_up' in e:
+                y = C.conv_transpose2d_s2_merged(xs, e['w_up'], 3, e['co'])    # [B, 2h+1, 2w+1, Co] raw
+            else:
+                y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3)
             _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(a), n, 2 * h + 1, 2 * wd + 1, oh, ow, e['co'], 1,
                       _TAPS, _lib.ptr(demod[li]), _lib.ptr(e['bias']), _lib.ptr(noise), e['noise_w'], 3,
                       _lib.ptr(xs_next), ctypes.c_void_p(s_next.data_ptr()), s_next.stride(0), g0, st())
@@ -325,6 +384,8 @@ def synthesis_backward(G, tape, dimg):
     def sl(t, e):
         return t[:, e['s_off']: e['s_off'] + e['ci']]
 
+    dd_all = torch.zeros(B * P['d_total'], device=dev, dtype=torch.float32)
+    dd_off, demod_bwd = 0, []
     dx_up, up_e = None, None                     # gradient w.r.t. the modulated input of the layer above, and that layer
     for li in range(len(P['styled']) - 1, -1, -1):
         e = P['styled'][li]
@@ -333,7 +394,8 @@ def synthesis_backward(G, tape, dimg):
         npix = h * wd
         has_rgb = not e['up']
         r = P['rgb'][li // 2] if has_rgb else None
-        dd = torch.zeros(n, co, device=dev, dtype=torch.float32)
+        dd = dd_all[dd_off: dd_off + n * co].view(n, co)
+        dd_off += n * co
         if e['up']:
             dpre = torch.empty_like(a)
             gs = None
@@ -367,16 +429,16 @@ def synthesis_backward(G, tape, dimg):
         else:
             dx = C.conv2d(gs, e['w_bwd'], 3, 3, padding=1, cout=e['ci'])
         # demodulation: d = rsqrt(scale^2 sum_i s_i^2 Wsq[o,i] + eps)  ->  ds_i += s_i * sum_o (-dd_o d_o^3 scale^2) Wsq[o,i]
+        # (deferred: all layers in one grouped launch after the loop; every writer of ds_all accumulates)
         s_e, ds_e = sl(s_all, e), sl(ds_all, e)
-        t = (dd * demod[li].pow(3)).mul_(-(e['scale'] ** 2))
-        u = torch.empty(n, e['ci'], device=dev, dtype=torch.float32)
-        _linear(t, e['wsq_t'], None, u)
-        ds_e.add_(u * s_e)
+        demod_bwd.append(_problem(dd, e['wsq_t'], ds_e, x2=demod[li], mul=s_e, wscale=-(e['scale'] ** 2), in_mode=3,
+                                  accumulate=1))
         if li == 0:
             pin = dx.shape[1] * dx.shape[2]
             _lib.call('wgs_sg2_mod_bwd', _lib.ptr(dx), _lib.ptr(P['const']), 1, vp(s_e), s_e.stride(0), None, 0,
                       vp(ds_e), ds_e.stride(0), n, pin, e['ci'], st())
         dx_up, up_e = dx, e
+    _linear_group(demod_bwd, B)
     dw = torch.empty(B, G.style_dim, device=dev, dtype=torch.float32)
     _linear(ds_all, P['mod_w_t'], None, dw, wscale=1.0 / math.sqrt(G.style_dim))
     return dw
@@ -388,10 +450,9 @@ def _mapping_backward(G, acts, dw):
     wscale = (1.0 / math.sqrt(G.style_dim)) * G.lr_mlp
     g = dw
     for i in range(G.n_mlp - 1, -1, -1):
-        h = acts[i + 1]
-        dpre = g * torch.where(h > 0, math.sqrt(2.0), 0.2 * math.sqrt(2.0))
         out = torch.empty_like(acts[i])
-        _linear(dpre.contiguous(), P['map_w_t'][i], None, out, wscale=wscale)
+        # the fused-lrelu derivative (taken from the layer's forward output) is applied to g while it is loaded
+        _linear_group([_problem(g, P['map_w_t'][i], out, x2=acts[i + 1], wscale=wscale, in_mode=2)], g.shape[0])
         g = out
     return g
 

@@ -136,12 +136,34 @@ class PairedTrainer:
     # ---- CUDA-graph mode: the whole step (≈330 of our launches + ≈500 small ATen ones) becomes one graph launch ----
     _graph = None
 
-    def capture(self, z, indices, magnitudes, warmup=3):
+    def _training_state(self):
+        """Everything a step mutates: flat parameters, Adam moments and step counters, R's BatchNorm buffers."""
+        ts = []
+        for f in (self.flat_s, self.flat_r):
+            ts += [f.flat, f.exp_avg, f.exp_avg_sq, f.step_dev]
+        ts += [b for b in self.R.buffers()]
+        return ts
+
+    def capture(self, z, indices, magnitudes, warmup=3, preserve_state=False):
         """Capture forward + backward + all-reduce + both Adam updates for this batch shape.  Afterwards step()
         copies its arguments into the static inputs and replays.  Returns True on success; on failure the trainer
         stays in eager mode (still entirely on the CUDA kernels).  Call it BEFORE any eager backward pass: autograd
         caches each parameter's AccumulateGrad node together with the stream it first ran on, and a node bound to
-        the default stream invalidates the capture."""
+        the default stream invalidates the capture.  The warm-up passes are real training steps on the given batch;
+        with ``preserve_state`` the parameters, optimiser state and BatchNorm buffers are put back afterwards so that
+        capturing does not advance training (the Trainer driver relies on this to follow the reference step for step)."""
+        saved = [(t, t.clone()) for t in self._training_state()] if preserve_state else []
+        counts = (self.flat_s.step_count, self.flat_r.step_count)
+        ok = self._capture(z, indices, magnitudes, warmup)
+        if preserve_state:
+            with torch.no_grad():
+                for t, c in saved:
+                    t.copy_(c)
+            self.flat_s.step_count, self.flat_r.step_count = counts
+            torch.cuda.synchronize()
+        return ok
+
+    def _capture(self, z, indices, magnitudes, warmup):
         self._static_in = (z.clone(), indices.clone(), magnitudes.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -332,7 +354,7 @@ class Trainer(object):
             z, indices, magnitudes = self.draw_batch(generator.dim_z)
             batch = tuple(t[lo:hi].to(device, non_blocking=True) for t in (z, indices, magnitudes))
             if use_graph and engine._graph is None and iteration == starting_iter:
-                engine.capture(*batch)
+                engine.capture(*batch, preserve_state=True)
             out = engine.step(*batch)
             window.append(torch.stack([out['accuracy'], out['cls'], out['reg'], out['loss']]).clone())
             if iteration % p.log_freq == 0 or iteration % p.ckp_freq == 0 or iteration == p.max_iter:
