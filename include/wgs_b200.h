@@ -62,6 +62,9 @@ int wgs_rbf_traverse(const float* support_sets, const float* alphas, const float
 int wgs_pack_split32(const float* src, long long rows, int C, long long ld, const float* scale,
                      long long scale_ld, long long rows_per_group, void* dst, void* stream);
 
+/* Stacked weight layout for narrow layers (see wgs_conv_desc.w_layout): src fp32 [taps*cout, C] rows (stride ld). */
+int wgs_pack_weights_stacked(const float* src, int taps, int cout, int C, long long ld, void* dst, void* stream);
+
 #define WGS_MAX_TAPS 64
 typedef struct wgs_conv_desc {
     /* input activations, split32 [in_n][in_h][in_w][c_chunks][64] */
@@ -100,6 +103,11 @@ typedef struct wgs_conv_desc {
      * if that pixel lies inside out_h x out_w.  The weights hold one row block per group (zero where a phase has no
      * tap at a given input shift).  fp32 output only (no out_split / rgb_out / noise).                          */
     int group_size, group_w, out_h, out_w;
+    /* weight layout: 0 = rows [w_taps][w_cout][c_chunks][hi32|lo32] (wgs_pack_split32);
+     * 1 = stacked [w_taps][c_chunks][2][w_cout][32] (wgs_pack_weights_stacked; hi plane then lo plane, 64-byte rows),
+     * w_cout <= 64 only: hi*hi and hi*lo then come out of ONE N = 2*BN MMA (the A operand is fetched twice per
+     * K slice instead of three times; narrow-N MMAs are bound by that fetch).                                   */
+    int w_layout;
 } wgs_conv_desc;
 
 /* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls

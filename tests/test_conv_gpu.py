@@ -208,3 +208,97 @@ def test_fir4_act_matches_torch(N, H, W, C, pad0, Ho, Wo):
     want = f * alpha[:, :, None, None] + 0.3 * noise[None, None] + beta[None, :, None, None]
     want = 2 ** 0.5 * F.leaky_relu(want, 0.2)
     assert rel(out, want.permute(0, 2, 3, 1)) < 1e-6
+
+
+@pytest.mark.parametrize('N,Ci,H,W,Co,k,pad', [(2, 6, 32, 32, 64, 7, 3), (1, 6, 33, 35, 64, 7, 3), (2, 64, 32, 32, 128, 3, 1),
+                                               (3, 64, 17, 16, 96, 1, 0), (2, 32, 64, 48, 32, 3, 1), (1, 128, 16, 16, 64, 3, 1)])
+def test_strided_dgrad_in_one_launch_matches_torch(N, Ci, H, W, Co, k, pad):
+    """Phase-packed output: all four output phases of a stride-2 data-gradient in one launch (odd sizes, 6-channel
+    groups narrower than a 16-channel block, groups of 32 / 64 / 128 channels, 1x1 with empty phases)."""
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(N + Ci + H + k)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).cuda()
+    y = F.conv2d(x, w, stride=2, padding=pad)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    before = conv._lib.launch_count()
+    got = conv.conv_dgrad_merged(conv.pack_split32(nhwc(dy)), w, (H, W), 2, pad)
+    assert got.shape == (N, H, W, Ci)
+    assert rel(got, nhwc(x.grad)) < 3e-5
+    base = torch.randn(N, H, W, Ci, generator=g).cuda()
+    out = base.clone()
+    conv.conv_dgrad_merged(conv.pack_split32(nhwc(dy)), w, (H, W), 2, pad, out=out, accumulate=True)
+    assert rel(out, nhwc(x.grad) + base) < 3e-5
+    assert conv._lib.launch_count() - before <= 6            # 2 x (pack dy + pack weights + ONE conv)
+
+
+@pytest.mark.parametrize('N,Ci,H,W,Co', [(2, 64, 8, 8, 32), (1, 128, 16, 12, 64), (3, 32, 5, 7, 16)])
+def test_conv_transpose_stride2_in_one_launch(N, Ci, H, W, Co):
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(N + Ci + H)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (Ci * 9) ** 0.5).cuda()                  # StyleGAN2 layout [Co, Ci, 3, 3]
+    want = F.conv_transpose2d(x, w.transpose(0, 1), stride=2, padding=0)                  # model.py:206-212
+    shifts, idx, G = conv._phase_plan('convT', 3, 3, 2, 0, x.device)
+    wm = conv.merged_phase_weights(w.reshape(Co, Ci, 9).contiguous(), idx, len(shifts), G)
+    got = conv.conv_transpose2d_s2_merged(conv.pack_split32(nhwc(x)), wm, 3, Co)
+    assert got.shape == nhwc(want).shape == (N, 2 * H + 1, 2 * W + 1, Co)
+    assert rel(got, nhwc(want)) < 2e-5
+
+
+@pytest.mark.parametrize('Co', [16, 24, 32, 48, 64])
+def test_stacked_weight_layout_matches_row_layout(Co, monkeypatch):
+    """Weights with <= 64 rows run the two-MMA-per-K-slice kernels on the stacked layout; the row layout (three MMAs)
+    must give the same numbers (both are exact products of the same bf16 pieces, fp32 accumulation order aside)."""
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(Co)
+    x = torch.randn(2, 96, 24, 40, generator=g).cuda()
+    w = (torch.randn(Co, 96, 3, 3, generator=g) / (96 * 9) ** 0.5).cuda()
+    xs = conv.pack_split32(nhwc(x))
+    want = nhwc(F.conv2d(x, w, padding=1))
+    assert conv.weight_layout(conv.pack_weights(w)) == 1
+    got = conv.conv2d(xs, conv.pack_weights(w), 3, 3, padding=1)
+    monkeypatch.setattr(conv, 'STACK_MAX_COUT', 0)
+    assert conv.weight_layout(conv.pack_weights(w)) == 0
+    rows = conv.conv2d(xs, conv.pack_weights(w), 3, 3, padding=1)
+    assert rel(got, want) < 2e-5 and rel(rows, want) < 2e-5 and rel(got, rows) < 2e-6
+
+
+def _unsplit(xs):
+    """split32 [..., chunks, 64] bf16 -> fp32 [..., chunks*32] (hi + lo)."""
+    f = xs.float()
+    return (f[..., :32] + f[..., 32:]).flatten(-2)
+
+
+@pytest.mark.parametrize('N,Ci,H,W,Co', [(2, 32, 48, 136, 32), (1, 24, 20, 200, 24), (3, 32, 16, 128, 16)])
+def test_multi_tile_halo_kernel_plain_and_fused(N, Ci, H, W, Co):
+    """Single-chunk layers wide enough for the multi-tile halo kernel (resident tap weights, patch ring, two TMEM
+    accumulators; ragged last tile group, ragged rows): plain epilogue with demod / bias / noise / activation, and the
+    fused epilogue (next layer's split32 operand, ToRGB accumulation, fp32 only for the back-propagated images)."""
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(N + H + W)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (Ci * 9) ** 0.5).cuda()
+    alpha = (torch.rand(N, Co, generator=g) + 0.5).cuda()
+    beta = torch.randn(Co, generator=g).cuda()
+    noise = torch.randn(H, W, generator=g).cuda()
+    xs, ws = conv.pack_split32(nhwc(x)), conv.pack_weights(w)
+    y = nhwc(F.conv2d(x, w, padding=1))
+    want = F.leaky_relu(y * alpha[:, None, None, :] + 0.3 * noise[None, :, :, None] + beta, 0.2) * 2 ** 0.5
+    got = conv.conv2d(xs, ws, 3, 3, padding=1, alpha=alpha, beta=beta, noise=noise, noise_w=0.3, act=3)
+    assert rel(got, want) < 2e-5
+    if Co % 32:
+        return
+    sc = (torch.rand(N, Co, generator=g) + 0.5).cuda()
+    rgb_w = torch.randn(N, 3, Co, generator=g).cuda()
+    rgb0 = torch.randn(N, H, W, 3, generator=g).cuda()
+    rgb = rgb0.clone()
+    out = torch.full((N, H, W, Co), 7.0).cuda()
+    nxt = torch.empty(N, H, W, Co // 32, 64, dtype=torch.bfloat16).cuda()
+    conv.conv2d(xs, ws, 3, 3, padding=1, out=out, alpha=alpha, beta=beta, noise=noise, noise_w=0.3, act=3,
+                out_split=nxt, split_scale=sc, out_from_n=1, rgb_w=rgb_w, rgb_out=rgb)
+    assert float((out[0] - 7.0).abs().max()) == 0.0                       # image 0 is not back-propagated: no fp32 store
+    assert rel(out[1:], want[1:]) < 2e-5
+    assert rel(_unsplit(nxt), want * sc[:, None, None, :]) < 2e-5
+    assert rel(rgb - rgb0, torch.einsum('nhwc,noc->nhwo', want, rgb_w)) < 2e-5

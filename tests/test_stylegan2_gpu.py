@@ -107,3 +107,31 @@ def test_synthesis_gradient_w_leaf():
     (G([wc], input_is_latent=True)[0] * cot.cuda()).sum().backward()
     cos = float(torch.nn.functional.cosine_similarity(wc.grad.flatten().double().cpu(), wo.grad.flatten().double(), dim=0))
     assert cos > 0.9999 and rel(wc.grad, wo.grad) < 5e-3
+
+
+def test_linear_group_modes_match_torch():
+    """wgs_linear_group: several small linears in one launch, every input transform / epilogue the StyleGAN2 style path
+    uses (models/StyleGAN2/model.py:110-131,194-195 and their derivatives)."""
+    from warpedganspace_b200 import stylegan2 as sg
+    g = torch.Generator().manual_seed(3)
+    B = 5
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    x0, W0, b0 = r(B, 512), r(96, 512), r(96)
+    x1, W1 = r(B, 64), r(40, 64).abs()
+    x2, h2, W2 = r(B, 128), r(B, 128), r(512, 128)
+    x3, d3, W3, m3 = r(B, 32), r(B, 32), r(64, 32), r(B, 200)[:, 8:72]
+    o0, o1, o2 = torch.empty(B, 96).cuda(), torch.empty(B, 40).cuda(), torch.empty(B, 512).cuda()
+    acc = r(B, 300)
+    o3 = acc[:, 100:164]
+    want3 = o3.clone() + m3 * (-0.5 * (x3 * d3 ** 3) @ W3.t())
+    sg._linear_group([
+        sg._problem(x0, W0, o0, bias=b0, wscale=0.1, bscale=0.3, epi=1),
+        sg._problem(x1, W1, o1, wscale=0.25, in_mode=1, epi=2, eps=1e-8),
+        sg._problem(x2, W2, o2, x2=h2, wscale=0.7, in_mode=2),
+        sg._problem(x3, W3, o3, x2=d3, mul=m3, wscale=-0.5, in_mode=3, accumulate=1),
+    ], B)
+    w0 = torch.nn.functional.leaky_relu(0.1 * x0 @ W0.t() + 0.3 * b0, 0.2) * 2 ** 0.5
+    w1 = torch.rsqrt(0.25 * (x1 ** 2) @ W1.t() + 1e-8)
+    w2 = 0.7 * (x2 * torch.where(h2 > 0, 2 ** 0.5, 0.2 * 2 ** 0.5)) @ W2.t()
+    for got, want in ((o0, w0), (o1, w1), (o2, w2), (o3, want3)):
+        assert rel(got, want) < 1e-5

@@ -1,6 +1,7 @@
 """Host-side wrappers of the tensor-core convolution entry points (wgs_pack_split32 /
 wgs_conv_split32).  Activations are NHWC; conv operands are "split32" bf16 (see include/wgs_b200.h)."""
 import ctypes
+import os
 
 import torch
 
@@ -48,6 +49,7 @@ class ConvDesc(ctypes.Structure):
         ('out_split', ctypes.c_void_p), ('split_scale', ctypes.c_void_p), ('split_scale_ld', ctypes.c_longlong),
         ('out_from_n', ctypes.c_int), ('rgb_w', ctypes.c_void_p), ('rgb_out', ctypes.c_void_p),
         ('group_size', ctypes.c_int), ('group_w', ctypes.c_int), ('out_h', ctypes.c_int), ('out_w', ctypes.c_int),
+        ('w_layout', ctypes.c_int),
     ]
 
 
@@ -81,11 +83,33 @@ def pack_split32(x, scale=None, rows_per_group=1, out=None):
     return out
 
 
+# Weight tensors with at most STACK_MAX_COUT rows per tap are stored in the STACKED layout
+# [T][chunks][hi | lo][Co][32] (include/wgs_b200.h, wgs_conv_desc.w_layout = 1) and run the two-MMA-per-K-slice
+# kernels; wider ones keep the row layout [T][Co][chunks][hi32 | lo32].  Both are returned with the nominal shape
+# [T, Co, chunks, 64]; every weight pack goes through pack_weight_rows so that conv_taps can infer the layout.
+STACK_MAX_COUT = 64 if os.environ.get('WGS_STACK', '1') != '0' else 0
+
+
+def weight_layout(w_split):
+    return 1 if w_split.shape[1] <= STACK_MAX_COUT else 0
+
+
+def pack_weight_rows(wt):
+    """wt: fp32 [T, Co, Ci] contiguous -> bf16 [T, Co, ceil(Ci/32), 64] in the layout weight_layout() reports."""
+    T, co, ci = wt.shape
+    if co > STACK_MAX_COUT:
+        return pack_split32(wt)
+    if not wt.is_contiguous():
+        wt = wt.contiguous()
+    out = torch.empty(T, co, chunks_of(ci), 64, dtype=torch.bfloat16, device=wt.device)
+    _lib.call('wgs_pack_weights_stacked', _lib.ptr(wt), T, co, ci, ci, _lib.ptr(out), _lib.stream())
+    return out
+
+
 def pack_weights(w):
-    """w: fp32 [Co, Ci, kh, kw] (torch conv layout) -> split32 [kh*kw, Co, ceil(Ci/32), 64]; tap = ky*kw+kx."""
+    """w: fp32 [Co, Ci, kh, kw] (torch conv layout) -> bf16 [kh*kw, Co, ceil(Ci/32), 64]; tap = ky*kw+kx."""
     co, ci, kh, kw = w.shape
-    wt = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
-    return pack_split32(wt)
+    return pack_weight_rows(w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous())
 
 
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
@@ -102,6 +126,7 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
     d.in_n, d.in_h, d.in_w, d.c_chunks = n, h, w_, chunks
     d.w = w_split.data_ptr()
     d.w_taps, d.w_cout = w_split.shape[0], w_split.shape[1]
+    d.w_layout = weight_layout(w_split)
     d.out_n, d.grid_h, d.grid_w, d.in_stride = (out.shape[0] if out is not None else out_n), grid[0], grid[1], in_stride
     d.num_taps = len(taps)
     for i, (dy, dx, tw) in enumerate(taps):
@@ -218,7 +243,7 @@ def merged_phase_weights(w_src, idx, S, G):
     rows, K, T = w_src.shape
     w_ext = torch.cat([w_src, w_src.new_zeros(rows, K, 1)], dim=2)
     sel = w_ext.index_select(2, idx)                                    # [rows, K, S*G]
-    return pack_split32(sel.permute(2, 0, 1).reshape(S, G * rows, K).contiguous())
+    return pack_weight_rows(sel.permute(2, 0, 1).reshape(S, G * rows, K).contiguous())
 
 
 def conv_dgrad_merged(dys, w, in_hw, stride, padding, out=None, accumulate=False, w_merged=None):

@@ -57,6 +57,8 @@ struct ConvKernelParams {
     // addresses it through its UMMA descriptor
     int dy0, dx0, halo_h, halo_w, a_stage_bytes;
     int group_size, group_w, out_h, out_w;   // phase-packed output (0 = off)
+    int tiles_per_cta, x_groups;             // multi-tile halo kernel: consecutive x tiles handled by one CTA
+    int w_cout;                              // rows of the weight tensor (stacked layout addressing, SIMT twin)
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -69,9 +71,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // Epilogue shared by the tensor-core conv kernels (executed by warps 2..5, threads 64..191).
-template <bool FUSED>
+template <bool FUSED, bool STACK>
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep, uint64_t* acc_bar,
-                                              int warp, int lane, int n0, int oy0, int ox0, int co0) {
+                                              int warp, int lane, int n0, int oy0, int ox0, int co0,
+                                              bool stage_consts = true, uint32_t parity = 0) {
     // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -88,7 +91,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     // CTA's channel slice in shared memory once instead of re-loading them per row from global memory.
     const bool cs = (p.bn == 1);
     const int BN = p.BN;
-    if (cs) {
+    if (cs && stage_consts) {
         const bool n_ok = n0 < p.out_n;
         for (int i = threadIdx.x - 64; i < BN; i += 128) {
             const int cc = co0 + i;
@@ -104,7 +107,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    ptx::mbar_wait(acc_bar, 0);
+    ptx::mbar_wait(acc_bar, parity);
     ptx::tc_fence_after();
     const bool write_f32 = FUSED ? (p.out != nullptr && n >= p.out_from_n) : true;
     const int gsz = FUSED ? 0 : p.group_size;                // phase-packed output: plain epilogue only
@@ -115,7 +118,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
     for (int c = 0; c < BN; c += 16) {
         float v[16];
-        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        if constexpr (STACK)      // columns [0, BN) hold hi*hi + lo*hi, columns [BN, 2BN) hold hi*lo
+            ptx::tmem_ld16_sum(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c,
+                               tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), v);
+        else
+            ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
         const int co = co0 + c;
         if (!valid || co >= p.cout) continue;
         // destination of this 16-channel block: `dptr + cof` (identity unless the output is phase-packed)
@@ -274,7 +281,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
 
 // FUSED = false: plain epilogue (demod / noise / bias / activation / accumulate -> fp32), lean register budget.
 // FUSED = true: additionally emits the next layer's split32 operand, ToRGB partial sums, selective fp32 stores.
-template <bool FUSED>
+// STACK = true (stacked weight layout, BN <= 64): per K slice one N = 2*BN MMA a_hi x [b_hi; b_lo] and one N = BN MMA
+// a_lo x b_hi instead of three N = BN MMAs - a narrow MMA costs ~(32 + N/4) cycles of operand fetch, not N/2 of math.
+template <bool FUSED, bool STACK>
 __global__ void __launch_bounds__(CONV_THREADS, 4)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvKernelParams p) {
@@ -328,7 +337,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     ptx::mbar_wait(empty_bar + stage, phase ^ 1);
                     ptx::mbar_expect_tx(full_bar + stage, (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
                     ptx::tma_load_5d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, full_bar + stage, 0, ch, ix, iy, n0);
-                    ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, ch, co0, wt);
+                    if constexpr (STACK)
+                        ptx::tma_load_5d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, co0, 0, ch, wt);
+                    else
+                        ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, ch, co0, wt);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -337,7 +349,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // whole warp with uniform control flow (descriptor arithmetic stays in uniform registers); one elected lane
         // issues the MMAs and commits
         const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
+        const uint32_t idesc2 = ptx::umma_idesc_bf16(128, (uint32_t)(2 * p.BN));
         const uint32_t dhi = (uint32_t)(ptx::umma_desc_sw128(0) >> 32);
+        const uint32_t bhi64 = (uint32_t)(ptx::umma_desc_sw64(0) >> 32);
         const uint32_t a_lo0 = (ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4;
         const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = (uint32_t)b_stage_bytes >> 4;
         int stage = 0;
@@ -346,7 +360,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mbar_wait(full_bar + stage, phase);
             ptx::tc_fence_after();
             const uint32_t da = a_lo0 + (uint32_t)stage * a_step, db = b_lo0 + (uint32_t)stage * b_step;
-            if (ptx::elect_one()) {
+            if constexpr (STACK) {
+                if (ptx::elect_one()) {
+                    // B: 64-byte rows [k0 | k1], BN hi rows then BN lo rows
+                    ptx::mma_f16_lh(tmem_base, da + 0, dhi, db + 0, bhi64, idesc2, kb > 0 ? 1u : 0u);   // a_hi x [b_hi; b_lo]
+                    ptx::mma_f16_lh(tmem_base, da + 2, dhi, db + 2, bhi64, idesc2, 1u);
+                    ptx::mma_f16_lh(tmem_base, da + 4, dhi, db + 0, bhi64, idesc, 1u);                   // a_lo x b_hi
+                    ptx::mma_f16_lh(tmem_base, da + 6, dhi, db + 2, bhi64, idesc, 1u);
+                    ptx::mma_commit(empty_bar + stage);
+                }
+            } else if (ptx::elect_one()) {
                 // 128-byte row = [hi k0 | hi k1 | lo k0 | lo k1], 32 B each -> descriptor address +2 per slot
                 ptx::mma_f16_lh(tmem_base, da + 0, dhi, db + 0, dhi, idesc, kb > 0 ? 1u : 0u);   // hi*hi
                 ptx::mma_f16_lh(tmem_base, da + 2, dhi, db + 2, dhi, idesc, 1u);
@@ -362,7 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (ptx::elect_one()) ptx::mma_commit(acc_bar);       // accumulator complete
         __syncwarp();
     } else {
-        conv_epilogue<FUSED>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
+        conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -382,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // row are eight consecutive rows (one swizzle group), successive output rows are halo_w rows apart.  TMA and UMMA both
 // apply the 128B swizzle as a function of the absolute shared-memory address, so shifted views stay consistent
 // (descriptor base_offset = 0; measured, csrc/experimental/README.md).  One tile per CTA, 3 CTAs per SM.
-template <bool FUSED>
+template <bool FUSED, bool STACK>
 __global__ void __launch_bounds__(CONV_THREADS, 3)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ ConvKernelParams p) {
@@ -433,15 +456,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::mbar_expect_tx(full_bar + stage, bytes);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
                 ptx::tma_load_5d(sa, &tmap_a, full_bar + stage, 0, ch, ox0 + p.dx0, oy0 + p.dy0, n0);
-                for (int tap = 0; tap < p.num_taps; ++tap)
-                    ptx::tma_load_4d(sa + p.a_stage_bytes + (size_t)tap * b_slice, &tmap_b, full_bar + stage, 0, ch, co0,
-                                     (int)p.tap_w[tap]);
+                for (int tap = 0; tap < p.num_taps; ++tap) {
+                    if constexpr (STACK)
+                        ptx::tma_load_5d(sa + p.a_stage_bytes + (size_t)tap * b_slice, &tmap_b, full_bar + stage, 0, co0, 0, ch,
+                                         (int)p.tap_w[tap]);
+                    else
+                        ptx::tma_load_4d(sa + p.a_stage_bytes + (size_t)tap * b_slice, &tmap_b, full_bar + stage, 0, ch, co0,
+                                         (int)p.tap_w[tap]);
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
-        const uint32_t b_hi = (uint32_t)(ptx::umma_desc_sw128(0) >> 32);
+        const uint32_t idesc2 = ptx::umma_idesc_bf16(128, (uint32_t)(2 * p.BN));
+        const uint32_t b_hi = (uint32_t)((STACK ? ptx::umma_desc_sw64(0) : ptx::umma_desc_sw128(0)) >> 32);
         // A: K-major SW128, SBO = patch row pitch, version 1, base_offset 0
         const uint32_t a_hi = (uint32_t)((((uint64_t)((uint32_t)p.halo_w * 128u >> 4) << 32) | ((uint64_t)1 << 46) |
                                           ((uint64_t)2 << 61)) >> 32);
@@ -457,7 +486,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int tap = 0; tap < p.num_taps; ++tap) {
                 const uint32_t da = a_lo + tap_off[tap];
                 const uint32_t db = b_lo0 + (uint32_t)tap * b_step;
-                if (ptx::elect_one()) {
+                if constexpr (STACK) {
+                    if (ptx::elect_one()) {
+                        ptx::mma_f16_lh(tmem_base, da + 0, a_hi, db + 0, b_hi, idesc2, accum);  // a_hi x [b_hi; b_lo]
+                        ptx::mma_f16_lh(tmem_base, da + 2, a_hi, db + 2, b_hi, idesc2, 1u);
+                        ptx::mma_f16_lh(tmem_base, da + 4, a_hi, db + 0, b_hi, idesc, 1u);      // a_lo x b_hi
+                        ptx::mma_f16_lh(tmem_base, da + 6, a_hi, db + 2, b_hi, idesc, 1u);
+                    }
+                } else if (ptx::elect_one()) {
                     ptx::mma_f16_lh(tmem_base, da + 0, a_hi, db + 0, b_hi, idesc, accum);   // hi*hi
                     ptx::mma_f16_lh(tmem_base, da + 2, a_hi, db + 2, b_hi, idesc, 1u);
                     ptx::mma_f16_lh(tmem_base, da + 0, a_hi, db + 4, b_hi, idesc, 1u);      // hi*lo
@@ -475,7 +511,141 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (ptx::elect_one()) ptx::mma_commit(acc_bar);
         __syncwarp();
     } else {
-        conv_epilogue<FUSED>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
+        conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-tile halo kernel for single-chunk layers (<= 32 input channels: the 32 -> 32 convs at 1024^2 and their
+// data-gradients).  The one-tile-per-CTA kernel above is bound by its own serial chain (set-up, TMA round trip, MMAs,
+// epilogue: ~6.5 us per CTA at 3 CTAs / SM, tensor pipe 22 % active, profiles/r01_conv_ncu_step.md).  Here a CTA
+// walks `tiles_per_cta` x-adjacent tiles of one image row band with
+//   * the tap weights resident in shared memory (loaded once: they were 60 % of the per-tile L2->SM bytes),
+//   * a ring of input patches filled ahead by the TMA warp,
+//   * two TMEM accumulators, so the MMAs of tile i+1 overlap the epilogue of tile i.
+// Stacked weight layout only (two MMAs per K slice).  2 CTAs / SM.
+constexpr int MT_STAGES = 3;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(CONV_THREADS, 2)
+conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ ConvKernelParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_slice = p.BN * 128;
+    const int w_bytes = p.num_taps * b_slice;                              // multiple of 1024 (BN >= 16 -> 2 KB slices)
+    uint8_t* smem_w = smem;
+    uint8_t* smem_p = smem + w_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_p + (size_t)MT_STAGES * p.a_stage_bytes);
+    uint64_t* empty_bar = full_bar + MT_STAGES;
+    uint64_t* tfull_bar = empty_bar + MT_STAGES;                           // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;                                  // [2] accumulator drained
+    uint64_t* w_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    uint32_t* tap_off = tmem_slot + 4;
+    float* ep = reinterpret_cast<float*>(tap_off + WGS_MAX_TAPS);
+    ep += ((16u - (ptx::smem_u32(ep) & 15u)) & 15u) >> 2;
+
+    int t = blockIdx.x;
+    const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;
+    const int xg = t % p.x_groups; t /= p.x_groups;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    const int n0 = t;
+    const int tx0 = xg * p.tiles_per_cta;
+    const int n_tiles = min(p.tiles_per_cta, p.tiles_x - tx0);
+    const int oy0 = ty * p.bh, co0 = co_tile * p.BN;
+    const uint32_t acc_cols = (uint32_t)(2 * p.BN);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < MT_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar + a, 1); ptx::mbar_init(tempty_bar + a, 4); }
+        ptx::mbar_init(w_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (threadIdx.x >= 64 && threadIdx.x - 64 < p.num_taps) {
+        const int i = threadIdx.x - 64;
+        tap_off[i] = (uint32_t)(((p.tap_dy[i] - p.dy0) * p.halo_w + (p.tap_dx[i] - p.dx0)) * 128) >> 4;
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(w_bar, (uint32_t)w_bytes);
+            for (int tap = 0; tap < p.num_taps; ++tap)
+                ptx::tma_load_5d(smem_w + (size_t)tap * b_slice, &tmap_b, w_bar, 0, co0, 0, 0, (int)p.tap_w[tap]);
+            const uint32_t bytes = (uint32_t)(p.halo_h * p.halo_w * 128);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_tiles; ++i) {
+                ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+                ptx::mbar_expect_tx(full_bar + stage, bytes);
+                ptx::tma_load_5d(smem_p + (size_t)stage * p.a_stage_bytes, &tmap_a, full_bar + stage, 0, 0,
+                                 (tx0 + i) * p.bw + p.dx0, oy0 + p.dy0, n0);
+                if (++stage == MT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)p.BN);
+        const uint32_t idesc2 = ptx::umma_idesc_bf16(128, (uint32_t)(2 * p.BN));
+        const uint32_t b_hi = (uint32_t)(ptx::umma_desc_sw64(0) >> 32);
+        const uint32_t a_hi = (uint32_t)((((uint64_t)((uint32_t)p.halo_w * 128u >> 4) << 32) | ((uint64_t)1 << 46) |
+                                          ((uint64_t)2 << 61)) >> 32);
+        const uint32_t w_lo0 = (ptx::smem_u32(smem_w) & 0x3FFFFu) >> 4;
+        const uint32_t p_lo0 = (ptx::smem_u32(smem_p) & 0x3FFFFu) >> 4;
+        const uint32_t st_step = (uint32_t)p.a_stage_bytes >> 4, b_step = (uint32_t)b_slice >> 4;
+        ptx::mbar_wait(w_bar, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int acc = i & 1;
+            const uint32_t use = (uint32_t)(i >> 1) & 1u;
+            ptx::mbar_wait(tempty_bar + acc, use ^ 1);                     // the epilogue has drained this accumulator
+            ptx::mbar_wait(full_bar + stage, phase);
+            ptx::tc_fence_after();
+            const uint32_t a_lo = p_lo0 + (uint32_t)stage * st_step;
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+            uint32_t accum = 0;
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+                const uint32_t da = a_lo + tap_off[tap];
+                const uint32_t db = w_lo0 + (uint32_t)tap * b_step;
+                if (ptx::elect_one()) {
+                    ptx::mma_f16_lh(d_tmem, da + 0, a_hi, db + 0, b_hi, idesc2, accum);   // a_hi x [b_hi; b_lo]
+                    ptx::mma_f16_lh(d_tmem, da + 2, a_hi, db + 2, b_hi, idesc2, 1u);
+                    ptx::mma_f16_lh(d_tmem, da + 4, a_hi, db + 0, b_hi, idesc, 1u);       // a_lo x b_hi
+                    ptx::mma_f16_lh(d_tmem, da + 6, a_hi, db + 2, b_hi, idesc, 1u);
+                }
+                __syncwarp();
+                accum = 1u;
+            }
+            if (ptx::elect_one()) {
+                ptx::mma_commit(empty_bar + stage);                        // patch slot free once these MMAs retire
+                ptx::mma_commit(tfull_bar + acc);                          // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == MT_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        for (int i = 0; i < n_tiles; ++i) {
+            const int acc = i & 1;
+            conv_epilogue<FUSED, true>(p, tmem_base + (uint32_t)acc * acc_cols, ep, tfull_bar + acc, warp, lane, n0, oy0,
+                                       (tx0 + i) * p.bw, co0, i == 0, (uint32_t)(i >> 1) & 1u);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar + acc);
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -487,7 +657,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 // Same contract on CUDA cores (debug / cross-check path; selected with WGS_CONV_IMPL=simt).
 __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ w,
-                                 int in_n, int in_h, int in_w, int w_cout, const ConvKernelParams p) {
+                                 int in_n, int in_h, int in_w, int w_cout, int w_layout, const ConvKernelParams p) {
     const long long total = (long long)p.out_n * p.grid_h * p.grid_w * p.cout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -505,7 +675,13 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ in, const __n
             for (int ch = 0; ch < p.c_chunks; ++ch)
                 for (int c = 0; c < 32; ++c) {
                     const float ah = __bfloat162float(a[ch * 64 + c]), al = __bfloat162float(a[ch * 64 + 32 + c]);
-                    const float bh = __bfloat162float(b[ch * 64 + c]), bl = __bfloat162float(b[ch * 64 + 32 + c]);
+                    float bh, bl;
+                    if (w_layout == 1) {        // stacked [tap][chunk][hi | lo][w_cout][32]
+                        const __nv_bfloat16* bs = w + ((((size_t)p.tap_w[tp] * p.c_chunks + ch) * 2) * w_cout + co) * 32 + c;
+                        bh = __bfloat162float(bs[0]); bl = __bfloat162float(bs[(size_t)w_cout * 32]);
+                    } else {
+                        bh = __bfloat162float(b[ch * 64 + c]); bl = __bfloat162float(b[ch * 64 + 32 + c]);
+                    }
                     acc += ah * bh + ah * bl + al * bh;
                 }
         }
@@ -616,9 +792,13 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     while (BN > 64 && m_tiles * ceil_div(d->cout, BN) < num_sms() && BN % 32 == 0) BN /= 2;
     if (d->force_bn > 0) BN = d->force_bn;
     WGS_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "conv: bad N tile");
+    const bool stack = d->w_layout == 1;
+    WGS_REQUIRE(d->w_layout == 0 || d->w_layout == 1, "conv: bad w_layout");
+    WGS_REQUIRE(!stack || (d->w_cout <= 64 && BN <= 64), "conv: the stacked weight layout is for w_cout <= 64");
     p.BN = BN;
+    p.w_cout = d->w_cout;
     p.n_tiles_co = ceil_div(d->cout, BN);
-    p.tmem_cols = std::max(32, next_pow2(BN));
+    p.tmem_cols = std::max(32, next_pow2(stack ? 2 * BN : BN));
     const int stage_bytes = A_STAGE_BYTES + BN * 128;
     // Short contractions (few taps x chunks) are latency-bound per tile: keep the ring shallow so that several
     // CTAs fit on one SM (smem and TMEM columns permitting) and overlap each other's prologue / epilogue.
@@ -636,7 +816,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         const long long total = (long long)p.out_n * p.grid_h * p.grid_w * p.cout;
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
         conv_simt_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)d->in, (const __nv_bfloat16*)d->w, d->in_n,
-                                                 d->in_h, d->in_w, d->w_cout, p);
+                                                 d->in_h, d->in_w, d->w_cout, d->w_layout, p);
         count_launch();
         WGS_LAUNCH_CHECK();
         return 0;
@@ -644,6 +824,28 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
 
     auto encode = get_encode();
     WGS_REQUIRE(encode != nullptr, "conv: cuTensorMapEncodeTiled entry point not available");
+    // weights: rows layout -> 4-D {64, chunks, cout, taps} SWIZZLE_128B box {64, 1, bn, 1};
+    //          stacked     -> 5-D {32, cout, 2, chunks, taps} SWIZZLE_64B box {32, bn, 2, 1, 1} (bn hi rows then bn lo rows)
+    auto encode_weights = [&](CUtensorMap* tm, int bn) -> CUresult {
+        if (stack) {
+            const cuuint64_t dims[5] = {32, (cuuint64_t)d->w_cout, 2, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_taps};
+            const cuuint64_t s1 = 64, s2 = s1 * d->w_cout, s3 = s2 * 2, s4 = s3 * d->c_chunks;
+            const cuuint64_t strides[4] = {s1, s2, s3, s4};
+            const cuuint32_t box[5] = {32, (cuuint32_t)bn, 2, 1, 1};
+            const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->w), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        const cuuint64_t dims[4] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_cout, (cuuint64_t)d->w_taps};
+        const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->w_cout;
+        const cuuint64_t strides[3] = {s1, s2, s3};
+        const cuuint32_t box[4] = {64, 1, (cuuint32_t)bn, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->w), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
     // ---- halo variant ---------------------------------------------------------------------------------
     {
         int dy0 = 127, dy1 = -127, dx0 = 127, dx1 = -127;
@@ -675,7 +877,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             p.dy0 = dy0; p.dx0 = dx0; p.halo_h = halo_h; p.halo_w = halo_w; p.a_stage_bytes = a_bytes;
             p.BN = hBN;
             p.n_tiles_co = ceil_div(d->cout, hBN);
-            p.tmem_cols = std::max(32, next_pow2(hBN));
+            p.tmem_cols = std::max(32, next_pow2(stack ? 2 * hBN : hBN));
             p.stages = 1;
             alignas(64) CUtensorMap ta, tb;
             {
@@ -691,27 +893,54 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                 WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(input) failed with code " + std::to_string((int)r));
             }
             {
-                const cuuint64_t dims[4] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_cout, (cuuint64_t)d->w_taps};
-                const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->w_cout;
-                const cuuint64_t strides[3] = {s1, s2, s3};
-                const cuuint32_t box[4] = {64, 1, (cuuint32_t)hBN, 1};
-                const cuuint32_t estr[4] = {1, 1, 1, 1};
-                CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->w), dims, strides, box,
-                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                CUresult r = encode_weights(&tb, hBN);
                 WGS_REQUIRE(r == CUDA_SUCCESS, "conv(halo): cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
+            }
+            static int mt_mode = -1;
+            if (mt_mode < 0) {
+                const char* e = getenv("WGS_HALO_MT");                // 0 = off, N = tiles per CTA (default 8)
+                mt_mode = e ? atoi(e) : 8;
+            }
+            const int hgrid_tiles = p.tiles_y * p.tiles_n * p.n_tiles_co;
+            if (mt_mode > 1 && stack && d->c_chunks == 1 && hBN <= 32 && p.tiles_x >= 2 * mt_mode &&
+                d->num_taps * hBN * 128 + MT_STAGES * a_bytes <= 108 * 1024) {
+                p.tiles_per_cta = mt_mode;
+                p.x_groups = ceil_div(p.tiles_x, mt_mode);
+                p.tmem_cols = std::max(32, next_pow2(4 * hBN));          // two stacked accumulators
+                const size_t msmem = (size_t)d->num_taps * hBN * 128 + (size_t)MT_STAGES * a_bytes + (2 * MT_STAGES + 5) * 8 + 32 +
+                                     WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
+                static bool mattr = false;
+                if (!mattr) {
+                    WGS_CUDA(cudaFuncSetAttribute(conv_halo_mt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                    WGS_CUDA(cudaFuncSetAttribute(conv_halo_mt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                    mattr = true;
+                }
+                const bool mfused = d->out_split != nullptr || d->rgb_out != nullptr || d->out_from_n > 0 || d->out == nullptr;
+                const int mgrid = hgrid_tiles * p.x_groups;
+                if (mfused) conv_halo_mt_kernel<true><<<mgrid, CONV_THREADS, msmem, st>>>(ta, tb, p);
+                else conv_halo_mt_kernel<false><<<mgrid, CONV_THREADS, msmem, st>>>(ta, tb, p);
+                count_launch();
+                WGS_LAUNCH_CHECK();
+                return 0;
             }
             const size_t hsmem = (size_t)p.stages * h_stage + (2 * p.stages + 1) * 8 + 32 + WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
             static bool hattr = false;
             if (!hattr) {
-                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+                WGS_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
                 hattr = true;
             }
             const int hgrid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_co;
             const bool hfused = d->out_split != nullptr || d->rgb_out != nullptr || d->out_from_n > 0 || d->out == nullptr;
-            if (hfused) conv_halo_kernel<true><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
-            else conv_halo_kernel<false><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
+            if (stack) {
+                if (hfused) conv_halo_kernel<true, true><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
+                else conv_halo_kernel<false, true><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
+            } else {
+                if (hfused) conv_halo_kernel<true, false><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
+                else conv_halo_kernel<false, false><<<hgrid, CONV_THREADS, hsmem, st>>>(ta, tb, p);
+            }
             count_launch();
             WGS_LAUNCH_CHECK();
             return 0;
@@ -733,27 +962,27 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         WGS_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(input) failed with code " + std::to_string((int)r));
     }
     {
-        const cuuint64_t dims[4] = {64, (cuuint64_t)d->c_chunks, (cuuint64_t)d->w_cout, (cuuint64_t)d->w_taps};
-        const cuuint64_t s1 = 128, s2 = s1 * d->c_chunks, s3 = s2 * d->w_cout;
-        const cuuint64_t strides[3] = {s1, s2, s3};
-        const cuuint32_t box[4] = {64, 1, (cuuint32_t)BN, 1};
-        const cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->w), dims, strides, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = encode_weights(&tmap_b, BN);
         WGS_REQUIRE(r == CUDA_SUCCESS, "conv: cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
     }
     const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 32 + 6 * BN * 4 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
     }
     const int grid = m_tiles * p.n_tiles_co;
     const bool fused = d->out_split != nullptr || d->rgb_out != nullptr || d->out_from_n > 0 || d->out == nullptr;
-    if (fused) conv_tc_kernel<true><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
-    else conv_tc_kernel<false><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+    if (stack) {
+        if (fused) conv_tc_kernel<true, true><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+        else conv_tc_kernel<false, true><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+    } else {
+        if (fused) conv_tc_kernel<true, false><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+        else conv_tc_kernel<false, false><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
+    }
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

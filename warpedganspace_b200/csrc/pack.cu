@@ -59,6 +59,42 @@ extern "C" int wgs_pack_split32(const float* src, long long rows, int C, long lo
     return 0;
 }
 
+// Stacked weight layout [taps][chunks][2][cout][32]: per (tap, chunk) a block of cout 64-byte hi rows followed by cout
+// 64-byte lo rows, so that one TMA box {32, BN, 2} lands as a 2*BN-row K-major SWIZZLE_64B operand.
+namespace wgs {
+__global__ void pack_weights_stacked_kernel(const float* __restrict__ src, int taps, int cout, int C, long long ld,
+                                            __nv_bfloat16* __restrict__ dst, int chunks) {
+    const long long total = (long long)taps * cout * chunks * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i & 7);
+        long long rc = i >> 3;
+        const int ch = (int)(rc % chunks); rc /= chunks;
+        const int co = (int)(rc % cout);
+        const int t = (int)(rc / cout);
+        const int c0 = ch * 32 + g * 4;
+        const float* sp = src + ((long long)t * cout + co) * ld + c0;
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16(c0 + k < C ? __ldg(sp + k) : 0.f, hi[k], lo[k]);
+        __nv_bfloat16* d = dst + ((((size_t)t * chunks + ch) * 2) * cout + co) * 32 + g * 4;
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(hi);
+        *reinterpret_cast<uint2*>(d + (size_t)cout * 32) = *reinterpret_cast<uint2*>(lo);
+    }
+}
+}  // namespace wgs
+
+extern "C" int wgs_pack_weights_stacked(const float* src, int taps, int cout, int C, long long ld, void* dst, void* stream) {
+    WGS_REQUIRE(taps >= 1 && cout >= 1 && cout <= 64 && C >= 1 && ld >= C, "pack_weights_stacked: bad sizes (cout <= 64)");
+    const int chunks = (C + 31) / 32;
+    const long long total = (long long)taps * cout * chunks * 8;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)wgs::num_sms() * 16);
+    wgs::pack_weights_stacked_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, taps, cout, C, ld, (__nv_bfloat16*)dst, chunks);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // im2col straight into split32 for convolutions with very few input channels (the Reconstructor's
 // 7x7/2 stem on 6 channels, lib/reconstructor.py:56-60): K = kh*kw*C gathered per output pixel, so the
