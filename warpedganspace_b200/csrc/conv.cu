@@ -57,6 +57,7 @@ struct ConvKernelParams {
     // addresses it through its UMMA descriptor
     int dy0, dx0, halo_h, halo_w, a_stage_bytes;
     int group_size, group_w, out_h, out_w;   // phase-packed output (0 = off)
+    int coalesce;                            // stage epilogue stores through shared memory (coalesced 64-byte rows)
     int tiles_per_cta, x_groups;             // multi-tile halo kernel: consecutive x tiles handled by one CTA
     int w_cout;                              // rows of the weight tensor (stacked layout addressing, SIMT twin)
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
@@ -70,11 +71,42 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// Warp-collective coalesced store of one 64-byte row per lane.  In the TMEM 32x32b layout a thread owns a pixel, so
+// a direct 128-bit store instruction touches 32 different cache lines, 16 bytes each; with two or three output tensors
+// per tile the LSU/L2 request rate, not bandwidth, bounds the epilogue (fused 32 -> 32 @1024^2: 1.04 ms vs 0.58 ms with
+// the stores removed, profiles/r01_conv_ncu_step.md).  The rows are transposed through a 2 KB per-warp staging
+// buffer (XOR-swizzled 16-byte chunks, conflict-free both ways) so that every store instruction writes 8 rows x 64
+// contiguous bytes.  Chunk c of a row goes to byte offset (c & 1) * 16 + (c >> 1) * hi_stride of that lane's pointer
+// (fp32 block: hi_stride 32 -> 64 contiguous bytes; split32 block: hi_stride 64 -> hi half, lo half).
+__device__ __forceinline__ void warp_store_rows64(uint32_t stg_s, int lane, const uint4 (&q)[4], const void* row_ptr,
+                                                  uint32_t hi_stride) {
+    const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_s + (uint32_t)lane * 64u + (((uint32_t)k ^ sw) << 4)),
+                     "r"(q[k].x), "r"(q[k].y), "r"(q[k].z), "r"(q[k].w) : "memory");
+    __syncwarp();
+    const unsigned long long mine = reinterpret_cast<unsigned long long>(row_ptr);
+    const uint32_t c = (uint32_t)lane & 3u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = j * 8 + (lane >> 2);
+        uint4 t;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                     : "r"(stg_s + (uint32_t)r * 64u + ((c ^ (((uint32_t)r >> 1) & 3u)) << 4)));
+        const unsigned long long pr = __shfl_sync(0xffffffffu, mine, r);
+        if (pr) *reinterpret_cast<uint4*>(pr + (c & 1u) * 16u + (c >> 1) * hi_stride) = t;
+    }
+    __syncwarp();
+}
+
 // Epilogue shared by the tensor-core conv kernels (executed by warps 2..5, threads 64..191).
 template <bool FUSED, bool STACK>
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep, uint64_t* acc_bar,
                                               int warp, int lane, int n0, int oy0, int ox0, int co0,
-                                              bool stage_consts = true, uint32_t parity = 0) {
+                                              uint8_t* stg = nullptr, bool stage_consts = true, uint32_t parity = 0) {
+    // stg: >= 8 KB of shared memory that is free while the epilogue runs (4 warps x 2 KB staging for coalesced stores),
+    // or nullptr for direct per-thread stores
     // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -115,6 +147,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     const int py0 = oy * p.out_ystep + p.out_y0, px0 = ox * p.out_xstep + p.out_x0;
     const size_t pix = ((size_t)n * p.grid_h + oy) * p.grid_w + ox;
     const uint32_t ep_s = ptx::smem_u32(ep);                 // explicit ld.shared: the generic pointer costs LD.E + a stall per use
+    const uint32_t stg_s = stg ? ptx::smem_u32(stg) + (uint32_t)q * 2048u : 0u;
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
     for (int c = 0; c < BN; c += 16) {
         float v[16];
@@ -124,16 +157,18 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
         else
             ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
         const int co = co0 + c;
-        if (!valid || co >= p.cout) continue;
+        if (co >= p.cout) continue;                          // warp-uniform
         // destination of this 16-channel block: `dptr + cof` (identity unless the output is phase-packed)
+        bool lane_ok = valid;
         float* dptr = dst;
         int cof = co;
         if (gsz && g_uniform) {
             const int g = co / gsz, gy = g / p.group_w, gx = g - gy * p.group_w;
-            if (py0 + gy >= p.out_h || px0 + gx >= p.out_w) continue;
+            if (py0 + gy >= p.out_h || px0 + gx >= p.out_w) lane_ok = false;
             dptr = dst + (long long)gy * p.out_sy + (long long)gx * p.out_sx;
             cof = co - g * gsz;
         }
+        if (!stg_s && !lane_ok) continue;                    // direct stores: nothing below is warp-collective
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(dptr + cof) & 15) == 0);
         const bool fast = cs && g_uniform && (co + 16 <= p.cout);   // whole 16-channel block valid, constants staged in smem
         if (fast) {
@@ -146,7 +181,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                 v[i + 2] = fmaf(v[i + 2], al.z, nz) + be.z;
                 v[i + 3] = fmaf(v[i + 3], al.w, nz) + be.w;
             }
-            if (p.accumulate) {
+            if (p.accumulate && lane_ok) {
                 if (vec_ok) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
@@ -174,7 +209,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int cc = co + i;
-                if (cc >= p.cout) break;
+                if (cc >= p.cout || !lane_ok) break;
                 const int g = cc / gsz, gy = g / p.group_w, gx = g - gy * p.group_w;
                 if (py0 + gy >= p.out_h || px0 + gx >= p.out_w) continue;
                 float r = v[i];
@@ -201,7 +236,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                         r += nz;
                         if (p.beta) r += __ldg(p.beta + cc);
                     }
-                    if (p.accumulate) r += dptr[cof + i];
+                    if (p.accumulate && lane_ok) r += dptr[cof + i];
                     v[i] = apply_act(r, p.act);
                 } else {
                     v[i] = 0.f;
@@ -258,12 +293,29 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
             }
             __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
                                 (size_t)(co >> 5) * 64 + (co & 16);
-            reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
-            reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
-            reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
-            reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
+            if (stg_s) {
+                const uint4 q4[4] = {reinterpret_cast<const uint4*>(hi)[0], reinterpret_cast<const uint4*>(hi)[1],
+                                     reinterpret_cast<const uint4*>(lo)[0], reinterpret_cast<const uint4*>(lo)[1]};
+                warp_store_rows64(stg_s, lane, q4, lane_ok ? sp : nullptr, 64u);
+            } else {
+                reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
+                reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
+                reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
+                reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
+            }
         }
-        if (write_f32) {
+        // (write_f32 is per image, hence per lane when a tile spans images; the collective path needs every lane)
+        const bool st_ok = write_f32 && lane_ok;
+        if (stg_s && co + 16 <= p.cout && __all_sync(0xffffffffu, vec_ok || !st_ok)) {
+            if (__any_sync(0xffffffffu, st_ok)) {
+                uint4 q4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    q4[k] = make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]),
+                                       __float_as_uint(v[4 * k + 3]));
+                warp_store_rows64(stg_s, lane, q4, st_ok ? dptr + cof : nullptr, 32u);
+            }
+        } else if (st_ok) {
             if (vec_ok && co + 16 <= p.cout) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4)
@@ -385,7 +437,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (ptx::elect_one()) ptx::mma_commit(acc_bar);       // accumulator complete
         __syncwarp();
     } else {
-        conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
+        // every MMA has retired when the accumulator barrier fires: the operand ring is free and stages the stores
+        conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, p.coalesce ? smem_a : nullptr);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -511,7 +564,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (ptx::elect_one()) ptx::mma_commit(acc_bar);
         __syncwarp();
     } else {
-        conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0);
+        conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, p.coalesce ? smem : nullptr);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -530,7 +583,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 //   * a ring of input patches filled ahead by the TMA warp,
 //   * two TMEM accumulators, so the MMAs of tile i+1 overlap the epilogue of tile i.
 // Stacked weight layout only (two MMAs per K slice).  2 CTAs / SM.
-constexpr int MT_STAGES = 3;
+constexpr int MT_STAGES = 2;
+constexpr int MT_STG_BYTES = 8192;                                 // 4 epilogue warps x 2 KB store staging
 
 template <bool FUSED>
 __global__ void __launch_bounds__(CONV_THREADS, 2)
@@ -543,7 +597,8 @@ conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int w_bytes = p.num_taps * b_slice;                              // multiple of 1024 (BN >= 16 -> 2 KB slices)
     uint8_t* smem_w = smem;
     uint8_t* smem_p = smem + w_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_p + (size_t)MT_STAGES * p.a_stage_bytes);
+    uint8_t* stg = smem_p + (size_t)MT_STAGES * p.a_stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + MT_STG_BYTES);
     uint64_t* empty_bar = full_bar + MT_STAGES;
     uint64_t* tfull_bar = empty_bar + MT_STAGES;                           // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;                                  // [2] accumulator drained
@@ -641,7 +696,7 @@ conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int i = 0; i < n_tiles; ++i) {
             const int acc = i & 1;
             conv_epilogue<FUSED, true>(p, tmem_base + (uint32_t)acc * acc_cols, ep, tfull_bar + acc, warp, lane, n0, oy0,
-                                       (tx0 + i) * p.bw, co0, i == 0, (uint32_t)(i >> 1) & 1u);
+                                       (tx0 + i) * p.bw, co0, p.coalesce ? stg : nullptr, i == 0, (uint32_t)(i >> 1) & 1u);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar + acc);
@@ -792,6 +847,12 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     while (BN > 64 && m_tiles * ceil_div(d->cout, BN) < num_sms() && BN % 32 == 0) BN /= 2;
     if (d->force_bn > 0) BN = d->force_bn;
     WGS_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "conv: bad N tile");
+    static int coalesce_mode = -1;
+    if (coalesce_mode < 0) {
+        const char* e = getenv("WGS_CONV_COALESCE");              // 0 = direct per-thread stores (A/B switch)
+        coalesce_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.coalesce = coalesce_mode;
     const bool stack = d->w_layout == 1;
     WGS_REQUIRE(d->w_layout == 0 || d->w_layout == 1, "conv: bad w_layout");
     WGS_REQUIRE(!stack || (d->w_cout <= 64 && BN <= 64), "conv: the stacked weight layout is for w_cout <= 64");
@@ -898,16 +959,18 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             }
             static int mt_mode = -1;
             if (mt_mode < 0) {
-                const char* e = getenv("WGS_HALO_MT");                // 0 = off, N = tiles per CTA (default 8)
-                mt_mode = e ? atoi(e) : 8;
+                const char* e = getenv("WGS_HALO_MT");                // 0 = off, N = tiles per CTA, default: by row width
+                mt_mode = e ? atoi(e) : -2;
             }
+            // measured on 32 -> 32 @1024^2 x 8 images: 16 tiles per CTA 0.641 ms, 8: 0.665, one-tile kernel: 0.925
+            const int mt_tiles = mt_mode == -2 ? (p.tiles_x >= 64 ? 16 : 8) : mt_mode;
             const int hgrid_tiles = p.tiles_y * p.tiles_n * p.n_tiles_co;
-            if (mt_mode > 1 && stack && d->c_chunks == 1 && hBN <= 32 && p.tiles_x >= 2 * mt_mode &&
-                d->num_taps * hBN * 128 + MT_STAGES * a_bytes <= 108 * 1024) {
-                p.tiles_per_cta = mt_mode;
-                p.x_groups = ceil_div(p.tiles_x, mt_mode);
+            if (mt_tiles > 1 && stack && d->c_chunks == 1 && hBN <= 32 && p.tiles_x >= 2 * mt_tiles &&
+                d->num_taps * hBN * 128 + MT_STAGES * a_bytes + MT_STG_BYTES <= 108 * 1024) {
+                p.tiles_per_cta = mt_tiles;
+                p.x_groups = ceil_div(p.tiles_x, mt_tiles);
                 p.tmem_cols = std::max(32, next_pow2(4 * hBN));          // two stacked accumulators
-                const size_t msmem = (size_t)d->num_taps * hBN * 128 + (size_t)MT_STAGES * a_bytes + (2 * MT_STAGES + 5) * 8 + 32 +
+                const size_t msmem = (size_t)d->num_taps * hBN * 128 + (size_t)MT_STAGES * a_bytes + MT_STG_BYTES + (2 * MT_STAGES + 5) * 8 + 32 +
                                      WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
                 static bool mattr = false;
                 if (!mattr) {
