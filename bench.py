@@ -30,6 +30,17 @@ F_G, F_R = 148.5e9, 80.7e9                       # forward FLOPs per image / per
 ALGO_FLOPS_PER_PAIR = 3 * F_G + 3 * F_R          # 2 G forwards + 1 G data-gradient + R fwd/dgrad/wgrad
 
 
+def recorded_conv_traffic():
+    """Average DRAM bytes (read + write) per tensor-core conv launch of one training step, from the committed ncu
+    capture of this workload (profiles/r01_conv_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    path = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -47,6 +58,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
         self.max_mhz = None
+        self.active = False          # samples are kept only while the timed region runs (NVML init happens before it)
+        self.ready = threading.Event()
 
     def run(self):
         try:
@@ -54,18 +67,26 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.ready.set()
             while not self.stop_flag:
+                if not self.active:
+                    time.sleep(0.002)
+                    continue
                 mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 self.samples.append((mhz, reasons))
-                time.sleep(0.02)
+                time.sleep(0.01)
         except Exception:
             # fall back to nvidia-smi (slow: a few samples only)
             q = 'clocks.sm,clocks.max.sm'
+            self.ready.set()
             while not self.stop_flag:
+                if not self.active:
+                    time.sleep(0.002)
+                    continue
                 try:
                     out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
                                           '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
@@ -220,21 +241,23 @@ def main():
         graphed = trainer.capture(*batches[0])
         if not graphed and rank == 0:
             print('CUDA-graph capture failed, running eagerly: %s' % getattr(trainer, 'capture_error', '?'), file=sys.stderr)
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         trainer.step(*batches[i])
     torch.cuda.synchronize()
+    sampler.ready.wait(timeout=10.0)
     wdist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.active = True
     e0.record()
     for i in range(args.warmup, total):
         trainer.step(*batches[i])
     e1.record()
     torch.cuda.synchronize()
+    sampler.active = False
     wdist.barrier()
-    sampler.stop_flag = True
     ms_total = wdist.max_over_ranks(e0.elapsed_time(e1), device)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
@@ -249,12 +272,15 @@ def main():
         e2e_step(host[i])
     torch.cuda.synchronize()
     wdist.barrier()
+    sampler.active = True
     e0.record()
     for i in range(args.warmup, total):
         e2e_step(host[i])
     e1.record()
     torch.cuda.synchronize()
+    sampler.active = False
     wdist.barrier()
+    sampler.stop_flag = True
     e2e_ms = wdist.max_over_ranks(e0.elapsed_time(e1), device) / args.steps
     e2e = {'value': world * B / (e2e_ms / 1e3), 'unit': 'pairs/s', 'ms_per_step': e2e_ms,
            'h2d_bytes_per_step': B * (DIM * 4 + 8 + 4), 'd2h_bytes_per_step': 4}
@@ -280,14 +306,18 @@ def main():
 
     # ---- roofline of the dominant kernel (tensor-core conv), per launch, from the same timed region -------
     pk = peaks()
+    traffic = recorded_conv_traffic()
     conv = [(fl, a.elapsed_time(b)) for kind, fl, a, b in prof if kind == 'conv']
     wg = [(fl, a.elapsed_time(b)) for kind, fl, a, b in prof if kind == 'wgrad']
     conv_ms = sum(t for _, t in conv)
     conv_fl = sum(f for f, _ in conv)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {
-        'bound': 'tensor', 'kernel': 'wgs::conv_tc_kernel', 'achieved': achieved, 'peak': pk['bf16_tflops'],
-        'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops'], 'traffic': None,
+        'bound': 'tensor', 'kernel': 'wgs::conv_tc_kernel family (conv_tc / conv_halo / conv_halo_mt: one entry point, wgs_conv_split32)',
+        'achieved': achieved, 'peak': pk['bf16_tflops'],
+        'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops'],
+        'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_source': (traffic or {}).get('source'),
+        'algorithmic_bytes_per_launch': (traffic or {}).get('algorithmic_bytes_per_launch'),
         'peak_source': pk['source'],
         'precision': 'fp32-accurate 3xbf16 split: every algorithmic MAC issues 3 bf16 MMAs, so issued tensor work is 3x '
                      'achieved (issued/peak = %.3f)' % (3 * achieved / pk['bf16_tflops']),

@@ -71,4 +71,11 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// two values at once: one packed cvt.rn.bf16x2.f32 per pair for hi and for lo
+__device__ __forceinline__ void split_bf16x2(float a, float b, __nv_bfloat162& hi, __nv_bfloat162& lo) {
+    hi = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(hi);
+    lo = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+}
+
 }  // namespace wgs

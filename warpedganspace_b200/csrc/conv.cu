@@ -280,10 +280,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     const float4 sc4 = ptx::lds128(es + i * 4);
-                    split_bf16(v[i + 0] * sc4.x, hi[i + 0], lo[i + 0]);
-                    split_bf16(v[i + 1] * sc4.y, hi[i + 1], lo[i + 1]);
-                    split_bf16(v[i + 2] * sc4.z, hi[i + 2], lo[i + 2]);
-                    split_bf16(v[i + 3] * sc4.w, hi[i + 3], lo[i + 3]);
+                    split_bf16x2(v[i + 0] * sc4.x, v[i + 1] * sc4.y, reinterpret_cast<__nv_bfloat162*>(hi)[i >> 1],
+                                 reinterpret_cast<__nv_bfloat162*>(lo)[i >> 1]);
+                    split_bf16x2(v[i + 2] * sc4.z, v[i + 3] * sc4.w, reinterpret_cast<__nv_bfloat162*>(hi)[(i >> 1) + 1],
+                                 reinterpret_cast<__nv_bfloat162*>(lo)[(i >> 1) + 1]);
                 }
             } else {
                 const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
@@ -925,12 +925,18 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         const int a_bytes = (halo_h * halo_w * 128 + 1023) / 1024 * 1024;
         // 3 CTAs / SM up to 72 KB per stage; long tap lists (the 16 shifts of the merged 7x7/2 stem data-gradient) may
         // take up to 108 KB (2 CTAs / SM): still far less L2->SM traffic than re-loading the patch per tap
-        const int h_limit = (d->num_taps >= 12 ? 108 : 72) * 1024;
+        static int halo_wide = -1;
+        if (halo_wide < 0) {
+            const char* e = getenv("WGS_HALO_WIDE");            // 1 = also 64 -> 64 two-chunk layers, 108 KB stages (experiment)
+            halo_wide = (e && e[0] == '1') ? 1 : 0;
+        }
+        const int h_limit = ((d->num_taps >= 12 || halo_wide) ? 108 : 72) * 1024;
         while (hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > h_limit) hBN /= 2;
         const int h_stage = a_bytes + d->num_taps * hBN * 128;
         const bool eligible = halo_mode && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
                               d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && h_stage <= h_limit &&
-                              (d->c_chunks == 1 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4));
+                              (d->c_chunks == 1 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4) ||
+                               (halo_wide && d->c_chunks == 2 && d->cout <= 64 && d->num_taps >= 4));
         // (64 -> 64 3x3, two chunks x two channel tiles, measured faster on the per-tap kernel: 0.73 vs 0.89 ms)
         if (eligible) {
             p.bw = 8; p.bh = 16; p.bn = 1;
