@@ -307,8 +307,9 @@ def main():
     # ---- roofline of the dominant kernel (tensor-core conv), per launch, from the same timed region -------
     pk = peaks()
     traffic = recorded_conv_traffic()
-    conv = [(fl, a.elapsed_time(b)) for kind, fl, a, b in prof if kind == 'conv']
-    wg = [(fl, a.elapsed_time(b)) for kind, fl, a, b in prof if kind == 'wgrad']
+    conv = [(r[1], r[2].elapsed_time(r[3])) for r in prof if r[0] == 'conv']
+    conv_bytes = sum(r[4] for r in prof if r[0] == 'conv' and len(r) > 4)
+    wg = [(r[1], r[2].elapsed_time(r[3])) for r in prof if r[0] == 'wgrad']
     conv_ms = sum(t for _, t in conv)
     conv_fl = sum(f for f, _ in conv)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -317,7 +318,7 @@ def main():
         'achieved': achieved, 'peak': pk['bf16_tflops'],
         'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops'],
         'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_source': (traffic or {}).get('source'),
-        'algorithmic_bytes_per_launch': (traffic or {}).get('algorithmic_bytes_per_launch'),
+        'algorithmic_bytes_per_launch': conv_bytes / max(1, len(conv)),
         'peak_source': pk['source'],
         'precision': 'fp32-accurate 3xbf16 split: every algorithmic MAC issues 3 bf16 MMAs, so issued tensor work is 3x '
                      'achieved (issued/peak = %.3f)' % (3 * achieved / pk['bf16_tflops']),

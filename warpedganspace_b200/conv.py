@@ -22,12 +22,12 @@ def _prof_begin():
     return e0
 
 
-def _prof_end(e0, kind, flops):
+def _prof_end(e0, kind, flops, nbytes=0):
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record()
-    PROFILE.append((kind, flops, e0, e1))
+    PROFILE.append((kind, flops, e0, e1, nbytes))
 
 
 class ConvDesc(ctypes.Structure):
@@ -162,7 +162,17 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
             raise RuntimeError('conv needs CUDA tensors; there is no CPU fallback')
     e0 = _prof_begin()
     _lib.check(_lib.load().wgs_conv_split32(ctypes.byref(d), _lib.stream()))
-    _prof_end(e0, 'conv', 2.0 * d.out_n * grid[0] * grid[1] * d.cout * (cin or chunks * 32) * len(taps))
+    if e0 is not None:
+        # algorithmic HBM bytes of this launch: operands once, every output once (accumulate / ToRGB: read + write)
+        npix = d.out_n * grid[0] * grid[1]
+        nbytes = x_split.numel() * 2 + w_split.numel() * 2
+        if out is not None:
+            nbytes += (d.out_n - out_from_n) * grid[0] * grid[1] * d.cout * 4 * (2 if accumulate else 1)
+        if out_split is not None:
+            nbytes += out_split.numel() * 2
+        if rgb_out is not None:
+            nbytes += npix * 3 * 4 * 2
+        _prof_end(e0, 'conv', 2.0 * npix * d.cout * (cin or chunks * 32) * len(taps), nbytes)
     return out
 
 
