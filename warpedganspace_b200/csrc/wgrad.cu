@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "wgs_b200.h"
+#include <stdlib.h>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -27,6 +28,7 @@ struct WgradParams {
     int bw, bh, bn, tiles_x, tiles_y, tiles_n;
     int NB, n_blocks, m_blocks, ksplit, stages, tmem_cols;
     int layout, out_co, out_ci;      // layout 0: dw[T][co_pad][ci_pad]; 1: torch dw[out_co][out_ci][T]
+    int row_mode, xw, b_block;       // row mode: one CTA = one kernel ROW (kw taps) on an x-halo input patch of xw pixels
     float* dw;
 };
 
@@ -42,7 +44,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic LD/ST)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = 2 * WG_BLOCK_BYTES, b_bytes = p.NB * WG_BLOCK_BYTES;
+    const int a_bytes = 2 * WG_BLOCK_BYTES, b_bytes = p.NB * p.b_block;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)p.stages * a_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_bytes);
@@ -54,8 +56,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     const int ks = t % p.ksplit; t /= p.ksplit;
     const int nb = t % p.n_blocks; t /= p.n_blocks;
     const int mb = t % p.m_blocks; t /= p.m_blocks;
-    const int tap = t;
-    const int ky = tap / p.kw, kx = tap % p.kw;
+    const int tap = t;                                            // row mode: t = ky
+    const int ky = p.row_mode ? t : tap / p.kw, kx = p.row_mode ? 0 : tap % p.kw;
+    const int n_acc = p.row_mode ? p.kw : 1;
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int per = (total_tiles + p.ksplit - 1) / p.ksplit;
     const int tile_lo = ks * per, tile_hi = min(total_tiles, tile_lo + per);
@@ -94,7 +97,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                     for (int c = 0; c < 2; ++c)
                         ptx::tma_load_5d(sa + c * WG_BLOCK_BYTES, &tmap_dy, full_bar + stage, 0, mb * 2 + c, ox0, oy0, n0);
                     for (int c = 0; c < p.NB; ++c)
-                        ptx::tma_load_5d(sb + c * WG_BLOCK_BYTES, &tmap_x, full_bar + stage, 0, nb * p.NB + c,
+                        ptx::tma_load_5d(sb + c * p.b_block, &tmap_x, full_bar + stage, 0, nb * p.NB + c,
                                          ox0 * p.stride - p.pad + kx, oy0 * p.stride - p.pad + ky, n0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -105,9 +108,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)(64 * p.NB)) | (1u << 15) | (1u << 16);
             const uint32_t dhi = (uint32_t)(umma_desc_mn_sw128(0, WG_BLOCK_BYTES, 1024) >> 32);
             const uint32_t dlo_extra = (uint32_t)(umma_desc_mn_sw128(0, WG_BLOCK_BYTES, 1024) & 0xFFFFFFFFu);   // LBO bits
+            // B: K groups (8 pixels of one image row) are one patch row apart, chunks one patch apart
+            const uint32_t b_sbo = p.row_mode ? (uint32_t)p.xw * 128u : 1024u;
+            const uint32_t dhi_b = (uint32_t)(umma_desc_mn_sw128(0, (uint32_t)p.b_block, b_sbo) >> 32);
+            const uint32_t dlo_extra_b = (uint32_t)(umma_desc_mn_sw128(0, (uint32_t)p.b_block, b_sbo) & 0xFFFFFFFFu);
             const uint32_t a_lo0 = ((ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4) | dlo_extra;
-            const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4) | dlo_extra;
+            const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4) | dlo_extra_b;
             const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+            const uint32_t b_kstep = (2u * b_sbo) >> 4;               // one K = 16 slice = two K groups
+            const uint32_t acc_cols = (uint32_t)(64 * p.NB);
             int stage = 0;
             uint32_t phase = 0;
             for (int k = 0; k < k_steps; ++k) {
@@ -115,10 +124,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                 ptx::tc_fence_after();
                 const uint32_t a0 = a_lo0 + (uint32_t)stage * a_step, b0 = b_lo0 + (uint32_t)stage * b_step;
                 if (ptx::elect_one()) {
+                    for (int ax = 0; ax < n_acc; ++ax) {
 #pragma unroll
-                    for (int kk = 0; kk < WG_BK / 16; ++kk)
-                        ptx::mma_f16_lh(tmem_base, a0 + kk * (2048 >> 4), dhi, b0 + kk * (2048 >> 4), dhi, idesc,
-                                        (k > 0 || kk > 0) ? 1u : 0u);
+                        for (int kk = 0; kk < WG_BK / 16; ++kk)
+                            ptx::mma_f16_lh(tmem_base + (uint32_t)ax * acc_cols, a0 + kk * (2048 >> 4), dhi,
+                                            b0 + (uint32_t)ax * (128u >> 4) + (uint32_t)kk * b_kstep, dhi_b, idesc,
+                                            (k > 0 || kk > 0) ? 1u : 0u);
+                    }
                     ptx::mma_commit(empty_bar + stage);
                 }
                 __syncwarp();
@@ -131,27 +143,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             const int m = q * 32 + lane;                         // accumulator row
             const int co = (mb * 2 + m / 64) * 32 + (m % 32);    // hi and lo rows of a chunk fold into one co
             const int ci_pad = p.ci_chunks * 32;
-            float* dst_row = p.dw + ((size_t)tap * p.co_chunks * 32 + co) * ci_pad;
             const bool row_ok = (mb * 2 + m / 64) < p.co_chunks && (p.layout == 0 || co < p.out_co);
             const int T = p.kh * p.kw;
             ptx::mbar_wait(acc_bar, 0);
             ptx::tc_fence_after();
-            for (int c = 0; c < p.NB; ++c) {
-                float v[64];
+            for (int ax = 0; ax < n_acc; ++ax) {
+                const int tap_o = p.row_mode ? ky * p.kw + ax : tap;
+                float* dst_row = p.dw + ((size_t)tap_o * p.co_chunks * 32 + co) * ci_pad;
+                for (int c = 0; c < p.NB; ++c) {
+                    float v[64];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 64 + j * 16), v + j * 16);
-                const int chunk = nb * p.NB + c;
-                if (!row_ok || chunk >= p.ci_chunks) continue;
-                if (p.layout == 0) {
-                    float* dst = dst_row + chunk * 32;
+                    for (int j = 0; j < 4; ++j)
+                        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ax * p.NB + c) * 64 + j * 16), v + j * 16);
+                    const int chunk = nb * p.NB + c;
+                    if (!row_ok || chunk >= p.ci_chunks) continue;
+                    if (p.layout == 0) {
+                        float* dst = dst_row + chunk * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j] + v[j + 32]);
-                } else {
-                    float* dst = p.dw + ((size_t)co * p.out_ci + chunk * 32) * T + tap;
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j] + v[j + 32]);
+                    } else {
+                        float* dst = p.dw + ((size_t)co * p.out_ci + chunk * 32) * T + tap_o;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (chunk * 32 + j < p.out_ci) atomicAdd(dst + (size_t)j * T, v[j] + v[j + 32]);
+                        for (int j = 0; j < 32; ++j)
+                            if (chunk * 32 + j < p.out_ci) atomicAdd(dst + (size_t)j * T, v[j] + v[j + 32]);
+                    }
                 }
             }
         }
@@ -228,17 +243,26 @@ extern "C" int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int c
     p.bh = std::min(WG_BK / p.bw, pow2ceil(oh));
     p.bn = WG_BK / (p.bw * p.bh);
     p.tiles_x = ceil_div(ow, p.bw); p.tiles_y = ceil_div(oh, p.bh); p.tiles_n = ceil_div(n, p.bn);
-    p.NB = std::min(4, ci_chunks);
+    static int row_env = -1;
+    if (row_env < 0) {
+        const char* e = getenv("WGS_WGRAD_ROW");                  // 0 = one CTA per tap everywhere (A/B switch)
+        row_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    // row mode keeps kw accumulators of 64*NB columns in the 512 TMEM columns
+    p.row_mode = (row_env && stride == 1 && kw >= 2 && kw * 64 <= 512 && p.bw == 8 && p.bh == 8) ? 1 : 0;
+    p.NB = std::min(p.row_mode ? std::max(1, 512 / (64 * kw)) : 4, std::min(4, ci_chunks));
     p.n_blocks = ceil_div(ci_chunks, p.NB);
     p.m_blocks = ceil_div(co_chunks, 2);
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-    const int base = kh * kw * p.n_blocks * p.m_blocks;
+    p.xw = p.row_mode ? p.bw + kw - 1 : p.bw;
+    p.b_block = p.row_mode ? (p.bh * p.xw * 128 + 1023) / 1024 * 1024 : WG_BLOCK_BYTES;
+    const int base = (p.row_mode ? kh : kh * kw) * p.n_blocks * p.m_blocks;
     int ksplit = std::max(1, (3 * num_sms()) / base);
     ksplit = std::min(ksplit, std::max(1, total_tiles / 8));
     p.ksplit = std::max(1, std::min(ksplit, total_tiles));
-    const int stage_bytes = (2 + p.NB) * WG_BLOCK_BYTES;
+    const int stage_bytes = 2 * WG_BLOCK_BYTES + p.NB * p.b_block;
     p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
-    p.tmem_cols = std::max(32, pow2ceil(64 * p.NB));
+    p.tmem_cols = std::max(32, pow2ceil(64 * p.NB * (p.row_mode ? kw : 1)));
     const cudaStream_t st = (cudaStream_t)stream;
 
     const char* impl = getenv("WGS_CONV_IMPL");
@@ -268,7 +292,7 @@ extern "C" int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int c
         const cuuint64_t dims[5] = {64, (cuuint64_t)ci_chunks, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
         const cuuint64_t s1 = 128, s2 = s1 * ci_chunks, s3 = s2 * w, s4 = s3 * h;
         const cuuint64_t strides[4] = {s1, s2, s3, s4};
-        const cuuint32_t box[5] = {64, 1, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)p.bn};
+        const cuuint32_t box[5] = {64, 1, (cuuint32_t)(p.row_mode ? p.xw : p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)p.bn};
         const cuuint32_t estr[5] = {1, 1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xs), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
