@@ -188,7 +188,7 @@ def test_stem_im2col_path(case):
 
 @pytest.mark.parametrize('N,H,W,C,pad0,Ho,Wo', [(2, 9, 9, 32, 1, 8, 8), (1, 17, 33, 64, 1, 16, 32), (3, 8, 8, 16, 2, 9, 9),
                                                 (1, 6, 10, 8, 2, 7, 11), (2, 5, 7, 4, 1, 4, 6),
-                                                # wide maps: the shared-memory tiled kernel (ragged tiles, both paddings)
+                                                # wide maps (interior fast path, ragged strips, both paddings)
                                                 (2, 33, 65, 32, 1, 32, 64), (1, 16, 40, 64, 2, 17, 41), (1, 19, 50, 32, 1, 18, 49),
                                                 (2, 64, 64, 32, 2, 65, 65)])
 def test_fir4_act_matches_torch(N, H, W, C, pad0, Ho, Wo):

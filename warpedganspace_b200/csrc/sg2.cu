@@ -217,95 +217,8 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
     }
 }
 
-// Shared-memory tiled variant for wide maps (Wout >= 32, C % 32 == 0): a block owns FIRS_TH output rows x 32 output
-// columns x 32 channels.  The (TH + 3) x 35 x 32-channel input window is loaded ONCE with coalesced 16-byte loads
-// (zero-filled outside the map, so the filter loops carry no bounds checks) - about 1.5 loads per output instead of 5.5
-// L1 hits - and each thread then runs the horizontal pass out of shared memory with a rolling window of four
-// horizontally-filtered rows.  (The register-strip kernel above spends 55 % of its stall samples waiting on L1.)
-constexpr int FIRS_TH = 8, FIRS_TW = 32, FIRS_CS = 32;
-constexpr int FIRS_SMEM = (FIRS_TH + 3) * (FIRS_TW + 3) * (FIRS_CS / 4) * 16;
-
-__global__ void __launch_bounds__(256, 3)
-fir4_act_smem_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int Hin, int Win, int Hout, int Wout,
-                     int C, int pad0, float k0, float k1, float k2, float k3, const float* __restrict__ alpha,
-                     const float* __restrict__ beta, const float* __restrict__ noise, float noise_w, int act,
-                     __nv_bfloat16* __restrict__ out_split, const float* __restrict__ split_scale, long long split_scale_ld,
-                     int out_from_n, int tiles_x, int tiles_y, int cslabs) {
-    extern __shared__ float4 fir_tile[];                        // [(TH+3)][35][8 channel quads]
-    constexpr int QN = FIRS_CS / 4, TWH = FIRS_TW + 3;
-    int t = blockIdx.x;
-    const int cs = t % cslabs; t /= cslabs;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int n = t / tiles_y;
-    const int Y0 = ty * FIRS_TH, X0 = tx * FIRS_TW, c0 = cs * FIRS_CS;
-    const float kf[4] = {k3, k2, k1, k0};                       // correlation with the flipped kernel
-    for (int idx = threadIdx.x; idx < (FIRS_TH + 3) * TWH * QN; idx += 256) {
-        const int q = idx % QN, b = (idx / QN) % TWH, a = idx / (QN * TWH);
-        const int yy = Y0 - pad0 + a, xx = X0 - pad0 + b;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (yy >= 0 && yy < Hin && xx >= 0 && xx < Win)
-            v = __ldg(reinterpret_cast<const float4*>(y + (((long long)n * Hin + yy) * Win + xx) * C + c0 + q * 4));
-        fir_tile[idx] = v;
-    }
-    const int q = threadIdx.x % QN, xl = threadIdx.x / QN;
-    const int X = X0 + xl, c = c0 + q * 4;
-    float nzv[FIRS_TH];
-#pragma unroll
-    for (int oy = 0; oy < FIRS_TH; ++oy)
-        nzv[oy] = (noise && Y0 + oy < Hout && X < Wout) ? noise_w * __ldg(noise + (size_t)(Y0 + oy) * Wout + X) : 0.f;
-    float al[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (alpha) al[k] = __ldg(alpha + (size_t)n * C + c + k);
-        if (beta) be[k] = __ldg(beta + c + k);
-        if (split_scale) sc[k] = __ldg(split_scale + (size_t)n * split_scale_ld + c + k);
-    }
-    __syncthreads();
-    if (X >= Wout) return;
-    const bool f32 = out && n >= out_from_n;
-    const int chunk_stride = ((C + 31) >> 5) * 64;
-    float4 h[4];                                                // rolling window of horizontally filtered rows
-#pragma unroll
-    for (int a = 0; a < FIRS_TH + 3; ++a) {
-        const float4* rowp = fir_tile + ((size_t)a * TWH + xl) * QN + q;
-        const float4 v0 = rowp[0], v1 = rowp[QN], v2 = rowp[2 * QN], v3 = rowp[3 * QN];
-        float4 hn;
-        hn.x = kf[0] * v0.x + kf[1] * v1.x + kf[2] * v2.x + kf[3] * v3.x;
-        hn.y = kf[0] * v0.y + kf[1] * v1.y + kf[2] * v2.y + kf[3] * v3.y;
-        hn.z = kf[0] * v0.z + kf[1] * v1.z + kf[2] * v2.z + kf[3] * v3.z;
-        hn.w = kf[0] * v0.w + kf[1] * v1.w + kf[2] * v2.w + kf[3] * v3.w;
-        h[a & 3] = hn;
-        if (a < 3) continue;
-        const int oy = a - 3, Y = Y0 + oy;
-        if (Y >= Hout) break;
-        const float4 h0 = h[(a - 3) & 3], h1 = h[(a - 2) & 3], h2 = h[(a - 1) & 3], h3 = hn;
-        float v4[4];
-        v4[0] = kf[0] * h0.x + kf[1] * h1.x + kf[2] * h2.x + kf[3] * h3.x;
-        v4[1] = kf[0] * h0.y + kf[1] * h1.y + kf[2] * h2.y + kf[3] * h3.y;
-        v4[2] = kf[0] * h0.z + kf[1] * h1.z + kf[2] * h2.z + kf[3] * h3.z;
-        v4[3] = kf[0] * h0.w + kf[1] * h1.w + kf[2] * h2.w + kf[3] * h3.w;
-        const float nz = nzv[oy];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float r = v4[k] * al[k] + nz + be[k];
-            if (act == 3) r = 1.41421356237309515f * (r > 0.f ? r : 0.2f * r);
-            else if (act == 2) r = r > 0.f ? r : 0.2f * r;
-            else if (act == 1) r = r > 0.f ? r : 0.f;
-            v4[k] = r;
-        }
-        const size_t pix = ((size_t)n * Hout + Y) * Wout + X;
-        if (f32) *reinterpret_cast<float4*>(out + pix * C + c) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-        if (out_split) {
-            __align__(8) __nv_bfloat162 hi2[2], lo2[2];
-            split_bf16x2(v4[0] * sc[0], v4[1] * sc[1], hi2[0], lo2[0]);
-            split_bf16x2(v4[2] * sc[2], v4[3] * sc[3], hi2[1], lo2[1]);
-            __nv_bfloat16* sp = out_split + pix * (size_t)chunk_stride + (size_t)(c >> 5) * 64 + (c & 31);
-            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi2);
-            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo2);
-        }
-    }
-}
+// (A shared-memory tiled variant - window loaded once per block, horizontal pass out of shared memory - was measured
+// and dropped: the LDS + STS + barrier instructions it adds outweigh the L1 hits it removes, 202 vs 210 pairs/s.)
 
 // rgb[n,y,x,:] = bias + up2(prev)[n,y,x,:]  — initialises the ToRGB accumulator that the conv epilogue adds into
 __global__ void rgb_init_kernel(const float* __restrict__ bias, const float* __restrict__ prev, float* __restrict__ rgb,
@@ -492,24 +405,6 @@ extern "C" int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win,
                             int out_from_n, void* stream) {
     WGS_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "fir4_act: channels must be a multiple of 4");
     WGS_REQUIRE(taps4 != nullptr, "fir4_act: taps4 is a HOST pointer to 4 floats");
-    static int fir_smem = -1;
-    if (fir_smem < 0) {
-        const char* e = getenv("WGS_FIR_SMEM");                    // 0 = register-strip kernel everywhere (A/B switch)
-        fir_smem = (e && e[0] == '0') ? 0 : 1;
-        if (fir_smem)
-            WGS_CUDA(cudaFuncSetAttribute(fir4_act_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRS_SMEM));
-    }
-    if (fir_smem && C % FIRS_CS == 0 && Wout >= FIRS_TW && Hout >= FIRS_TH) {
-        const int tiles_x = ceil_div(Wout, FIRS_TW), tiles_y = ceil_div(Hout, FIRS_TH), cslabs = C / FIRS_CS;
-        const long long blocks = (long long)N * tiles_y * tiles_x * cslabs;
-        WGS_REQUIRE(blocks < (1ll << 31), "fir4_act: grid too large");
-        fir4_act_smem_kernel<<<(int)blocks, 256, FIRS_SMEM, (cudaStream_t)stream>>>(
-            y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4[0], taps4[1], taps4[2], taps4[3], alpha, beta, noise, noise_w, act,
-            (__nv_bfloat16*)out_split, split_scale, split_scale_ld, out_from_n, tiles_x, tiles_y, cslabs);
-        count_launch();
-        WGS_LAUNCH_CHECK();
-        return 0;
-    }
     static int rows = 0;
     if (!rows) {
         const char* e = getenv("WGS_FIR_ROWS");

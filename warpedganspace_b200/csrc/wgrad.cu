@@ -38,7 +38,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                 const __grid_constant__ WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -147,6 +147,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             const int T = p.kh * p.kw;
             ptx::mbar_wait(acc_bar, 0);
             ptx::tc_fence_after();
+            // Rows m and m + 32 of a 64-row block are the hi and lo halves of the SAME output channels: the lo warp hands its
+            // 32 column sums to the hi warp through shared memory (the operand ring is idle once the accumulator barrier has
+            // fired), so every weight gets one atomic per CTA instead of two - split-K atomics, not MMAs, bound this kernel.
+            float* xch = reinterpret_cast<float*>(smem) + (size_t)(q >> 1) * (32 * 33);
+            const int pair_bar = 1 + (q >> 1);
+            const bool is_lo = (q & 1) != 0;
             for (int ax = 0; ax < n_acc; ++ax) {
                 const int tap_o = p.row_mode ? ky * p.kw + ax : tap;
                 float* dst_row = p.dw + ((size_t)tap_o * p.co_chunks * 32 + co) * ci_pad;
@@ -155,17 +161,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ax * p.NB + c) * 64 + j * 16), v + j * 16);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += v[j + 32];                 // x hi + x lo columns
+                    if (is_lo) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) xch[lane * 33 + j] = v[j];
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                    if (!is_lo) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += xch[lane * 33 + j];
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");    // xch is reused by the next block
                     const int chunk = nb * p.NB + c;
-                    if (!row_ok || chunk >= p.ci_chunks) continue;
+                    if (is_lo || !row_ok || chunk >= p.ci_chunks) continue;
                     if (p.layout == 0) {
                         float* dst = dst_row + chunk * 32;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j] + v[j + 32]);
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
                     } else {
                         float* dst = p.dw + ((size_t)co * p.out_ci + chunk * 32) * T + tap_o;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (chunk * 32 + j < p.out_ci) atomicAdd(dst + (size_t)j * T, v[j] + v[j + 32]);
+                            if (chunk * 32 + j < p.out_ci) atomicAdd(dst + (size_t)j * T, v[j]);
                     }
                 }
             }
@@ -245,8 +263,8 @@ extern "C" int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int c
     p.tiles_x = ceil_div(ow, p.bw); p.tiles_y = ceil_div(oh, p.bh); p.tiles_n = ceil_div(n, p.bn);
     static int row_env = -1;
     if (row_env < 0) {
-        const char* e = getenv("WGS_WGRAD_ROW");                  // 0 = one CTA per tap everywhere (A/B switch)
-        row_env = (e && e[0] == '0') ? 0 : 1;
+        const char* e = getenv("WGS_WGRAD_ROW");                  // 1 = row mode (default: one CTA per tap)
+        row_env = (e && e[0] == '1') ? 1 : 0;                     // measured: no gain (the kernel is bound by its atomics)
     }
     // row mode keeps kw accumulators of 64*NB columns in the 512 TMEM columns
     p.row_mode = (row_env && stride == 1 && kw >= 2 && kw * 64 <= 512 && p.bw == 8 && p.bh == 8) ? 1 : 0;
@@ -257,11 +275,26 @@ extern "C" int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int c
     p.xw = p.row_mode ? p.bw + kw - 1 : p.bw;
     p.b_block = p.row_mode ? (p.bh * p.xw * 128 + 1023) / 1024 * 1024 : WG_BLOCK_BYTES;
     const int base = (p.row_mode ? kh : kh * kw) * p.n_blocks * p.m_blocks;
-    int ksplit = std::max(1, (3 * num_sms()) / base);
+    static int wg_ctas = -1;
+    if (wg_ctas < 0) {
+        const char* e = getenv("WGS_WGRAD_CTAS");                 // CTAs per SM: 1 = deep ring, 2 = two shallower rings
+        wg_ctas = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    // two CTAs per SM overlap one CTA's prologue / atomic epilogue with the other's main loop; row mode with three
+    // 128-column accumulators (384 -> 512 TMEM columns) cannot share an SM
+    const int tmem_need = 64 * p.NB * (p.row_mode ? kw : 1);
+    const int ctas = (wg_ctas == 2 && tmem_need <= 256) ? 2 : 1;
+    // every extra K split adds one atomic per weight: aim for one full wave of CTAs, not several
+    static int wg_waves = -1;
+    if (wg_waves < 0) {
+        const char* e = getenv("WGS_WGRAD_WAVES");                // CTA waves targeted by the K split (x ctas per SM)
+        wg_waves = e ? std::max(1, atoi(e)) : 1;
+    }
+    int ksplit = std::max(1, (wg_waves * ctas * num_sms()) / base);
     ksplit = std::min(ksplit, std::max(1, total_tiles / 8));
     p.ksplit = std::max(1, std::min(ksplit, total_tiles));
     const int stage_bytes = 2 * WG_BLOCK_BYTES + p.NB * p.b_block;
-    p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+    p.stages = std::max(2, std::min(8, ((ctas == 2 ? 104 : 200) * 1024) / stage_bytes));
     p.tmem_cols = std::max(32, pow2ceil(64 * p.NB * (p.row_mode ? kw : 1)));
     const cudaStream_t st = (cudaStream_t)stream;
 
