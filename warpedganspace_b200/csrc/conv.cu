@@ -57,6 +57,7 @@ struct ConvKernelParams {
     // addresses it through its UMMA descriptor
     int dy0, dx0, halo_h, halo_w, a_stage_bytes;
     int group_size, group_w, out_h, out_w;   // phase-packed output (0 = off)
+    int ksplit;                              // cluster split-K: CTAs per output tile (1 = off)
     int coalesce;                            // stage epilogue stores through shared memory (coalesced 64-byte rows)
     int tiles_per_cta, x_groups;             // multi-tile halo kernel: consecutive x tiles handled by one CTA
     int w_cout;                              // rows of the weight tensor (stacked layout addressing, SIMT twin)
@@ -104,7 +105,10 @@ __device__ __forceinline__ void warp_store_rows64(uint32_t stg_s, int lane, cons
 template <bool FUSED, bool STACK>
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep, uint64_t* acc_bar,
                                               int warp, int lane, int n0, int oy0, int ox0, int co0,
-                                              uint8_t* stg = nullptr, bool stage_consts = true, uint32_t parity = 0) {
+                                              uint8_t* stg = nullptr, bool stage_consts = true, uint32_t parity = 0,
+                                              uint32_t peer_s = 0, int n_peers = 0) {
+    // peer_s / n_peers: cluster split-K - CTAs 1..n_peers of the cluster hold their partial accumulators at shared offset
+    // peer_s in [column/4][row] float4 order; this (rank 0) CTA adds them to its own while it reads TMEM
     // stg: >= 8 KB of shared memory that is free while the epilogue runs (4 warps x 2 KB staging for coalesced stores),
     // or nullptr for direct per-thread stores
     // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
@@ -156,6 +160,17 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                                tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), v);
         else
             ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        if (n_peers) {
+            const uint32_t mine = peer_s + (uint32_t)(((c >> 2) * 128 + row) * 16);
+            for (int pr = 1; pr <= n_peers; ++pr) {
+                const uint32_t ra = ptx::map_to_cta(mine, (uint32_t)pr);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 t4 = ptx::ld_dsmem128(ra + (uint32_t)k * 2048u);
+                    v[4 * k] += t4.x; v[4 * k + 1] += t4.y; v[4 * k + 2] += t4.z; v[4 * k + 3] += t4.w;
+                }
+            }
+        }
         const int co = co0 + c;
         if (co >= p.cout) continue;                          // warp-uniform
         // destination of this 16-channel block: `dptr + cof` (identity unless the output is phase-packed)
@@ -352,14 +367,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float* ep = reinterpret_cast<float*>(tmem_slot + 4);
     ep += ((16u - (ptx::smem_u32(ep) & 15u)) & 15u) >> 2;   // [6][BN] per-channel epilogue constants
 
-    // tile coordinates: co tile fastest so CTAs sharing an input patch are co-scheduled (L2 reuse)
+    // tile coordinates: co tile fastest so CTAs sharing an input patch are co-scheduled (L2 reuse).
+    // Cluster split-K (ksplit > 1, launched as clusters of ksplit CTAs along x): the ksplit CTAs of a cluster share one
+    // output tile and each contracts a contiguous range of the (tap, chunk) blocks; ranks 1.. park their accumulators in
+    // their own shared memory and rank 0 adds them through distributed shared memory inside its normal epilogue.  Used
+    // where M is tiny (512-channel layers at 4^2 .. 32^2: 8 CTAs x 144 blocks ran 63 us on 5 % of the SMs).
     int t = blockIdx.x;
+    const int ks = t % p.ksplit; t /= p.ksplit;
     const int co_tile = t % p.n_tiles_co; t /= p.n_tiles_co;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
     const int ty = t % p.tiles_y; t /= p.tiles_y;
     const int tn = t;
     const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = tn * p.bn, co0 = co_tile * p.BN;
-    const int k_blocks = p.num_taps * p.c_chunks;
+    const int k_total = p.num_taps * p.c_chunks;
+    const int k_per = (k_total + p.ksplit - 1) / p.ksplit;
+    const int kb_lo = ks * k_per, kb_hi = min(k_total, kb_lo + k_per);
+    const int k_blocks = kb_hi - kb_lo;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -381,20 +404,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tap = 0; tap < p.num_taps; ++tap) {
+            int tap = kb_lo / p.c_chunks, ch = kb_lo % p.c_chunks;
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
                 const int ix = ox0 * p.in_stride + p.tap_dx[tap];
                 const int iy = oy0 * p.in_stride + p.tap_dy[tap];
                 const int wt = p.tap_w[tap];
-                for (int ch = 0; ch < p.c_chunks; ++ch) {
-                    ptx::mbar_wait(empty_bar + stage, phase ^ 1);
-                    ptx::mbar_expect_tx(full_bar + stage, (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
-                    ptx::tma_load_5d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, full_bar + stage, 0, ch, ix, iy, n0);
-                    if constexpr (STACK)
-                        ptx::tma_load_5d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, co0, 0, ch, wt);
-                    else
-                        ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, ch, co0, wt);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
+                ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+                ptx::mbar_expect_tx(full_bar + stage, (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+                ptx::tma_load_5d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, full_bar + stage, 0, ch, ix, iy, n0);
+                if constexpr (STACK)
+                    ptx::tma_load_5d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, co0, 0, ch, wt);
+                else
+                    ptx::tma_load_4d(smem_b + (size_t)stage * b_stage_bytes, &tmap_b, full_bar + stage, 0, ch, co0, wt);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (++ch == p.c_chunks) { ch = 0; ++tap; }
             }
         }
     } else if (warp == 1) {
@@ -438,7 +461,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         __syncwarp();
     } else {
         // every MMA has retired when the accumulator barrier fires: the operand ring is free and stages the stores
-        conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, p.coalesce ? smem_a : nullptr);
+        if (p.ksplit == 1) {
+            conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, p.coalesce ? smem_a : nullptr);
+        } else if (ks != 0) {
+            // park this CTA's partial accumulator in its (now idle) operand ring: [column / 4][row] float4
+            const int q = warp & 3, row = q * 32 + lane;
+            ptx::mbar_wait(acc_bar, 0);
+            ptx::tc_fence_after();
+            const uint32_t base_s = ptx::smem_u32(smem_a) + (uint32_t)row * 16u;
+            for (int c = 0; c < p.BN; c += 16) {
+                float v[16];
+                ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base_s + (uint32_t)((c >> 2) + k) * 2048u),
+                                 "f"(v[4 * k]), "f"(v[4 * k + 1]), "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
+            }
+        }
+    }
+    if (p.ksplit > 1) {
+        ptx::tc_fence_before();
+        ptx::cluster_sync();                                  // partial accumulators of ranks 1.. are in place
+        if (ks == 0 && warp >= 2)
+            conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, nullptr, true, 0,
+                                        ptx::smem_u32(smem_a), p.ksplit - 1);
+        ptx::cluster_sync();                                  // nobody leaves while rank 0 still reads its peers
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -781,6 +828,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+static int k_blocks_total(const wgs_conv_desc* d) { return d->num_taps * d->c_chunks; }
 
 static int conv_impl_is_simt() {
     static int v = -1;
@@ -853,7 +901,23 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         coalesce_mode = (e && e[0] == '0') ? 0 : 1;
     }
     p.coalesce = coalesce_mode;
+    static int splitk_mode = -1;
+    if (splitk_mode < 0) {
+        const char* e = getenv("WGS_CONV_SPLITK");               // 0 = off (A/B switch)
+        splitk_mode = (e && e[0] == '0') ? 0 : 1;
+    }
     const bool stack = d->w_layout == 1;
+    // Cluster split-K for tiny-M, deep-K launches: widest N tile (math-bound MMAs, one patch load per tile), then as many
+    // K splits as fill about two CTAs per SM (<= 8: portable cluster size)
+    p.ksplit = 1;
+    if (splitk_mode && !stack && d->force_bn == 0 && d->group_size == 0 && k_blocks_total(d) >= 16 &&
+        (BN <= 64 || m_tiles * ceil_div(d->cout, BN) * 2 <= num_sms())) {   // narrow-N tiles or under half a wave
+        const int wide = std::min(256, (d->cout + 15) / 16 * 16);
+        const int tiles = m_tiles * ceil_div(d->cout, wide);
+        int ks = 1;
+        while (ks < 8 && tiles * ks * 2 <= 2 * num_sms() && k_blocks_total(d) / (ks * 2) >= 4) ks *= 2;
+        if (ks > 1) { BN = wide; p.ksplit = ks; }
+    }
     WGS_REQUIRE(d->w_layout == 0 || d->w_layout == 1, "conv: bad w_layout");
     WGS_REQUIRE(!stack || (d->w_cout <= 64 && BN <= 64), "conv: the stacked weight layout is for w_cout <= 64");
     p.BN = BN;
@@ -863,7 +927,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     const int stage_bytes = A_STAGE_BYTES + BN * 128;
     // Short contractions (few taps x chunks) are latency-bound per tile: keep the ring shallow so that several
     // CTAs fit on one SM (smem and TMEM columns permitting) and overlap each other's prologue / epilogue.
-    const int k_blocks = d->num_taps * d->c_chunks;
+    const int k_blocks = ceil_div(d->num_taps * d->c_chunks, p.ksplit);      // per CTA
     int ctas_per_sm = 1;
     if (k_blocks <= 12) ctas_per_sm = 4;
     else if (k_blocks <= 24) ctas_per_sm = 3;
@@ -871,6 +935,8 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     ctas_per_sm = std::max(1, std::min(ctas_per_sm, 512 / p.tmem_cols));
     const int smem_budget = (220 * 1024) / ctas_per_sm - 2048 - 6 * BN * 4;
     p.stages = std::max(2, std::min(std::min(8, k_blocks), smem_budget / stage_bytes));
+    if (p.ksplit > 1)                                            // the ring also parks a 128 x BN fp32 partial accumulator
+        p.stages = std::max(p.stages, ceil_div(128 * BN * 4, stage_bytes));
     const cudaStream_t st = (cudaStream_t)stream;
 
     if (conv_impl_is_simt()) {
@@ -933,7 +999,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         const int h_limit = ((d->num_taps >= 12 || halo_wide) ? 108 : 72) * 1024;
         while (hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > h_limit) hBN /= 2;
         const int h_stage = a_bytes + d->num_taps * hBN * 128;
-        const bool eligible = halo_mode && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
+        const bool eligible = halo_mode && p.ksplit == 1 && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
                               d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && h_stage <= h_limit &&
                               (d->c_chunks == 1 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4) ||
                                (halo_wide && d->c_chunks == 2 && d->cout <= 64 && d->num_taps >= 4));
@@ -1043,9 +1109,25 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         WGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         attr_set = true;
     }
-    const int grid = m_tiles * p.n_tiles_co;
+    const int grid = m_tiles * p.n_tiles_co * p.ksplit;
     const bool fused = d->out_split != nullptr || d->rgb_out != nullptr || d->out_from_n > 0 || d->out == nullptr;
-    if (stack) {
+    if (p.ksplit > 1) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid, 1, 1);
+        cfg.blockDim = dim3(CONV_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.ksplit;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (fused) WGS_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmap_a, tmap_b, p));
+        else WGS_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmap_a, tmap_b, p));
+    } else if (stack) {
         if (fused) conv_tc_kernel<true, true><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
         else conv_tc_kernel<false, true><<<grid, CONV_THREADS, smem, st>>>(tmap_a, tmap_b, p);
     } else {
