@@ -106,9 +106,11 @@ template <bool FUSED, bool STACK>
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep, uint64_t* acc_bar,
                                               int warp, int lane, int n0, int oy0, int ox0, int co0,
                                               uint8_t* stg = nullptr, bool stage_consts = true, uint32_t parity = 0,
-                                              uint32_t peer_s = 0, int n_peers = 0) {
-    // peer_s / n_peers: cluster split-K - CTAs 1..n_peers of the cluster hold their partial accumulators at shared offset
-    // peer_s in [column/4][row] float4 order; this (rank 0) CTA adds them to its own while it reads TMEM
+                                              uint32_t peer_s = 0, int n_ranks = 0, int my_rank = 0) {
+    // peer_s / n_ranks / my_rank: cluster split-K - every CTA of the cluster parks its partial accumulator at shared offset
+    // peer_s in [column/4][row] float4 order; each rank then finishes BN / n_ranks of the columns (a reduce-scatter over
+    // distributed shared memory: one rank summing everything serialised 0.9 MB of remote reads per tile and was slower
+    // than not splitting at all)
     // stg: >= 8 KB of shared memory that is free while the epilogue runs (4 warps x 2 KB staging for coalesced stores),
     // or nullptr for direct per-thread stores
     // epilogue: warp (2..5) may only touch TMEM lanes 32*(warp%4) .. +31
@@ -153,16 +155,18 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     const uint32_t ep_s = ptx::smem_u32(ep);                 // explicit ld.shared: the generic pointer costs LD.E + a stall per use
     const uint32_t stg_s = stg ? ptx::smem_u32(stg) + (uint32_t)q * 2048u : 0u;
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-    for (int c = 0; c < BN; c += 16) {
+    const int c_lo = n_ranks ? my_rank * (BN / n_ranks) : 0, c_hi = n_ranks ? c_lo + BN / n_ranks : BN;
+    for (int c = c_lo; c < c_hi; c += 16) {
         float v[16];
         if constexpr (STACK)      // columns [0, BN) hold hi*hi + lo*hi, columns [BN, 2BN) hold hi*lo
             ptx::tmem_ld16_sum(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c,
                                tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), v);
         else
             ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        if (n_peers) {
+        if (n_ranks) {
             const uint32_t mine = peer_s + (uint32_t)(((c >> 2) * 128 + row) * 16);
-            for (int pr = 1; pr <= n_peers; ++pr) {
+            for (int pr = 0; pr < n_ranks; ++pr) {
+                if (pr == my_rank) continue;
                 const uint32_t ra = ptx::map_to_cta(mine, (uint32_t)pr);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -463,13 +467,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // every MMA has retired when the accumulator barrier fires: the operand ring is free and stages the stores
         if (p.ksplit == 1) {
             conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, p.coalesce ? smem_a : nullptr);
-        } else if (ks != 0) {
+        } else {
             // park this CTA's partial accumulator in its (now idle) operand ring: [column / 4][row] float4
+            // (its own slice of the columns stays in TMEM)
             const int q = warp & 3, row = q * 32 + lane;
             ptx::mbar_wait(acc_bar, 0);
             ptx::tc_fence_after();
             const uint32_t base_s = ptx::smem_u32(smem_a) + (uint32_t)row * 16u;
+            const int own_lo = ks * (p.BN / p.ksplit), own_hi = own_lo + p.BN / p.ksplit;
             for (int c = 0; c < p.BN; c += 16) {
+                if (c >= own_lo && c < own_hi) continue;
                 float v[16];
                 ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
 #pragma unroll
@@ -481,11 +488,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     if (p.ksplit > 1) {
         ptx::tc_fence_before();
-        ptx::cluster_sync();                                  // partial accumulators of ranks 1.. are in place
-        if (ks == 0 && warp >= 2)
+        ptx::cluster_sync();                                  // every rank's partial accumulator is in place
+        if (warp >= 2)
             conv_epilogue<FUSED, STACK>(p, tmem_base, ep, acc_bar, warp, lane, n0, oy0, ox0, co0, nullptr, true, 0,
-                                        ptx::smem_u32(smem_a), p.ksplit - 1);
-        ptx::cluster_sync();                                  // nobody leaves while rank 0 still reads its peers
+                                        ptx::smem_u32(smem_a), p.ksplit, ks);
+        ptx::cluster_sync();                                  // nobody leaves while a peer still reads its shared memory
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -916,6 +923,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         const int tiles = m_tiles * ceil_div(d->cout, wide);
         int ks = 1;
         while (ks < 8 && tiles * ks * 2 <= 2 * num_sms() && k_blocks_total(d) / (ks * 2) >= 4) ks *= 2;
+        while (ks > 1 && (wide % (16 * ks)) != 0) ks /= 2;     // every rank finishes a multiple of 16 columns
         if (ks > 1) { BN = wide; p.ksplit = ks; }
     }
     WGS_REQUIRE(d->w_layout == 0 || d->w_layout == 1, "conv: bad w_layout");
