@@ -307,13 +307,21 @@ def test_multi_tile_halo_kernel_plain_and_fused(N, Ci, H, W, Co):
     assert rel(rgb - rgb0, torch.einsum('nhwc,noc->nhwo', want, rgb_w)) < 2e-5
 
 
-@pytest.mark.parametrize('N,Ci,H,W,Co', [(2, 512, 8, 8, 512), (8, 512, 4, 4, 512), (4, 256, 16, 16, 384), (1, 512, 32, 32, 512),
-                                         (3, 160, 8, 12, 200)])
-def test_cluster_split_k_tiny_m_layers(N, Ci, H, W, Co):
-    """Tiny-M, deep-K launches (the 512-channel layers at 4^2 .. 32^2) run as thread-block clusters: the K range is split
-    over up to 8 CTAs per output tile and rank 0 adds the partial accumulators through distributed shared memory inside
-    its normal epilogue (demod / bias / activation, several images per tile, ragged channel tiles)."""
-    from warpedganspace_b200 import conv
+def test_cluster_split_k_tiny_m_layers():
+    """Opt-in (WGS_CONV_SPLITK=1): tiny-M, deep-K launches (the 512-channel layers at 4^2 .. 32^2) run as thread-block
+    clusters - the K range is split over up to 8 CTAs per output tile, every CTA parks its partial accumulator in shared
+    memory and finishes BN / ksplit of the columns by summing its peers' partials through distributed shared memory
+    inside the normal epilogue (demod / bias / activation, fused outputs, several images per tile, ragged channel tiles)."""
+    import subprocess, sys, os
+    code = """
+import torch, torch.nn.functional as F
+from warpedganspace_b200 import conv
+torch.backends.cudnn.allow_tf32 = False
+nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+unsplit = lambda xs: (xs.float()[..., :32] + xs.float()[..., 32:]).flatten(-2)
+worst = 0.0
+for N, Ci, H, W, Co in [(2, 512, 8, 8, 512), (8, 512, 4, 4, 512), (4, 256, 16, 16, 384), (1, 512, 32, 32, 512), (3, 160, 8, 12, 200)]:
     g = torch.Generator().manual_seed(N + Ci + H + Co)
     x = torch.randn(N, Ci, H, W, generator=g).cuda()
     w = (torch.randn(Co, Ci, 3, 3, generator=g) / (Ci * 9) ** 0.5).cuda()
@@ -321,11 +329,9 @@ def test_cluster_split_k_tiny_m_layers(N, Ci, H, W, Co):
     beta = torch.randn(Co, generator=g).cuda()
     xs, ws = conv.pack_split32(nhwc(x)), conv.pack_weights(w)
     y = nhwc(F.conv2d(x, w, padding=1))
-    got = conv.conv2d(xs, ws, 3, 3, padding=1)
-    assert rel(got, y) < 2e-5
-    got = conv.conv2d(xs, ws, 3, 3, padding=1, alpha=alpha, beta=beta, act=3)
+    worst = max(worst, rel(conv.conv2d(xs, ws, 3, 3, padding=1), y))
     want = F.leaky_relu(y * alpha[:, None, None, :] + beta, 0.2) * 2 ** 0.5
-    assert rel(got, want) < 2e-5
+    worst = max(worst, rel(conv.conv2d(xs, ws, 3, 3, padding=1, alpha=alpha, beta=beta, act=3), want))
     if Co % 32 == 0:
         sc = (torch.rand(N, Co, generator=g) + 0.5).cuda()
         rgb_w = torch.randn(N, 3, Co, generator=g).cuda()
@@ -334,5 +340,12 @@ def test_cluster_split_k_tiny_m_layers(N, Ci, H, W, Co):
         out = torch.empty(N, H, W, Co).cuda()
         conv.conv2d(xs, ws, 3, 3, padding=1, out=out, alpha=alpha, beta=beta, act=3, out_split=nxt, split_scale=sc,
                     rgb_w=rgb_w, rgb_out=rgb)
-        assert rel(out, want) < 2e-5 and rel(_unsplit(nxt), want * sc[:, None, None, :]) < 2e-5
-        assert rel(rgb, torch.einsum('nhwc,noc->nhwo', want, rgb_w)) < 2e-5
+        worst = max(worst, rel(out, want), rel(unsplit(nxt), want * sc[:, None, None, :]),
+                    rel(rgb, torch.einsum('nhwc,noc->nhwo', want, rgb_w)))
+print(worst)
+"""
+    env = dict(os.environ, WGS_CONV_SPLITK='1')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=180,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert float(out.stdout.strip().splitlines()[-1]) < 2e-5
