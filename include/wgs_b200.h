@@ -117,6 +117,15 @@ typedef struct wgs_conv_desc {
 int wgs_conv_split32(const wgs_conv_desc* desc, void* stream);
 int wgs_conv_desc_size(void);
 
+/* ---- output stage ---------------------------------------------------------------------------------- *
+ * tensor2image (traverse_latent_space.py:26-41, sample_gan.py:10-25) on the device: n images of `count` fp32 values each
+ * (any layout; the generators here produce NHWC, which is what PIL wants) -> uint8.  adaptive != 0: per-image
+ * (x - min) / (max - min), else (x + 1) / 2; then uint8(255 * t) by truncation - the reference's fp32 operations in
+ * the reference's order, so the pixels are bit-identical.  workspace: 2 * workspace_pairs floats of scratch
+ * (per-block min/max), workspace_pairs >= n.                                                                    */
+int wgs_image_to_u8(const float* images, int n, long long count, int adaptive, float* workspace, int workspace_pairs,
+                    unsigned char* out, void* stream);
+
 /* ---- StyleGAN2 glue (CUDA cores, HBM/latency-bound) --------------------------------------------- *
  * wgs_linear_small: out[b,o] = epi(wscale * sum_i f(x[b,i]) * W[o,i] + bscale * bias[o]); f = square when
  * in_square; epi 0 linear, 1 sqrt(2)*lrelu(0.2) (EqualLinear 'fused_lrelu', models/StyleGAN2/model.py:110-131),

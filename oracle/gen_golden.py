@@ -520,6 +520,20 @@ def pin_trainer_loop():
         final_conv0_weight=final_r['feature_extractor.0.weight'].clone()))
 
 
+def pin_latent_pool():
+    """Known-answer test for the latent-pool format (sample_gan.py:156-179): the 58 pools shipped with the reference,
+    directory name = sha1 of the [1, dim_z] fp32 tensor bytes."""
+    import glob
+    print('[latent pools shipped with the reference]')
+    entries = {}
+    for path in sorted(glob.glob(os.path.join(REF, 'experiments', 'latent_codes', '*', '*', '*', 'latent_code.pt'))):
+        parts = path.split(os.sep)
+        entries['/'.join(parts[-4:-1])] = torch.load(path, map_location='cpu')
+    assert len(entries) >= 50, len(entries)
+    print('  %d latent codes, dims %s' % (len(entries), sorted({tuple(v.shape) for v in entries.values()})))
+    save('latent_pool.pt', entries)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.chdir('/tmp')
@@ -531,6 +545,7 @@ def main():
     pin_step()
     pin_traversal()
     pin_trainer_loop()
+    pin_latent_pool()
     pin_proggan()
     pin_biggan()
     print('oracle pinned against the reference; fixtures in', OUT)

@@ -50,3 +50,55 @@ def test_traverse_paths_matches_oracle(wspace):
     with torch.no_grad():
         plain = W(z.cuda())
     assert rel(out['images'][:, 0, steps], plain) < 1e-6
+
+
+@pytest.mark.parametrize('adaptive', [True, False])
+@pytest.mark.parametrize('shape', [(3, 3, 33, 47), (1, 1, 32, 32), (2, 3, 256, 256)])
+def test_images_to_uint8_is_bit_identical_to_tensor2image(shape, adaptive):
+    """Device-side tensor2image (traverse_latent_space.py:26-41) vs the reference's host formula on the same fp32 image:
+    same operations in the same order -> identical uint8 pixels (HWC)."""
+    from warpedganspace_b200.image_out import images_to_uint8
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(*shape, generator=g) * 1.3).contiguous(memory_format=torch.channels_last)
+    want = []
+    for t in x:                                                            # the reference's per-image host code
+        t = (t - t.min()) / (t.max() - t.min()) if adaptive else (t + 1) / 2
+        want.append((255 * t).to(torch.uint8).permute(1, 2, 0))
+    got = images_to_uint8(x.cuda(), adaptive=adaptive)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (shape[0], shape[2], shape[3], shape[1])
+    assert torch.equal(got.cpu(), torch.stack(want))
+
+
+def test_traverse_and_save_writes_the_reference_tree(tmp_path):
+    """traverse_latent_space.py:333-490: <hash>/paths_images/path_XXX/NNNNNN.jpg, original_image.jpg,
+    paths_latent_codes.pt [paths, 2*steps+1, dim]; frames decode to the generator's images."""
+    import os
+    from PIL import Image
+    from warpedganspace_b200 import SupportSets, latent_pool
+    from warpedganspace_b200.generators import SNGANGenerator
+    from warpedganspace_b200.gan_load import SNGANWrapper
+    from warpedganspace_b200.traversal import traverse_and_save
+    import oracle.sngan as o_sn
+    import oracle.support_sets as o_ss
+    gen = lambda s: torch.Generator().manual_seed(s)
+    G = SNGANGenerator('sn_resnet32', 32, 1)
+    G.load_state_dict({'model.' + k: v for k, v in o_sn.init_state('sn_resnet32', 1, generator=gen(1)).items()}, strict=False)
+    W = SNGANWrapper(G).cuda().eval()
+    S = SupportSets(4, 2, 128, learn_gammas=True, gamma=1.0 / 128)
+    S.load_state_dict(o_ss.init_state(4, 2, 128, generator=gen(2)))
+    S = S.cuda()
+    zs = torch.randn(2, 128, generator=gen(3))
+    hashes = latent_pool.save_latent_pool(zs, str(tmp_path / 'pool'))
+    done = traverse_and_save(W, S, str(tmp_path / 'pool'), str(tmp_path / 'out'), eps=0.2, shift_steps=3, batch_size=4)
+    assert sorted(done) == sorted(hashes)
+    for h in hashes:
+        root = tmp_path / 'out' / h
+        assert sorted(os.listdir(root)) == ['original_image.jpg', 'paths_images', 'paths_latent_codes.pt']
+        assert sorted(os.listdir(root / 'paths_images')) == ['path_%03d' % i for i in range(4)]
+        assert sorted(os.listdir(root / 'paths_images' / 'path_002')) == ['%06d.jpg' % t for t in range(7)]
+        codes = torch.load(root / 'paths_latent_codes.pt')
+        assert tuple(codes.shape) == (4, 7, 128)
+        z = zs[hashes.index(h)]
+        assert torch.allclose(codes[:, 3], z.expand(4, -1), atol=1e-6)            # centre frame = the pool's code
+        im = Image.open(root / 'paths_images' / 'path_000' / '000003.jpg')
+        assert im.size == (32, 32) and im.mode == 'L'

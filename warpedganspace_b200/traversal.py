@@ -1,5 +1,5 @@
 """Latent-space traversal, the generator-only variant of the hot path
-(traverse_latent_space.py:333-463 of the reference; JPEG/GIF output is out of scope).
+(traverse_latent_space.py:333-490 of the reference; GIF strips are out of scope).
 
 For every (latent, path) pair the reference walks ``shift_steps`` sequential RBF steps in each direction in a
 Python loop (2 * steps launches of ~12 kernels each, per chain) and then renders ``G(code_t, shift_t)``.  Here all
@@ -58,3 +58,45 @@ def shard_latents(z, rank=None, world=None):
     world = w if world is None else world
     lo, hi = wdist.shard_range(z.shape[0], rank, world)
     return z[lo:hi]
+
+
+@torch.no_grad()
+def traverse_and_save(G, S, pool_dir, out_dir, eps=0.15, shift_steps=16, batch_size=8, paths=None, img_size=None,
+                      img_quality=95, shift_in_w_space=None):
+    """The reference traversal script's output tree (traverse_latent_space.py:333-490) for every code of a latent pool:
+
+        <out_dir>/<hash>/paths_images/path_<dim:03d>/<frame:06d>.jpg      2*shift_steps+1 frames, most negative first
+        <out_dir>/<hash>/original_image.jpg                               centre frame of path 0, quality 95
+        <out_dir>/<hash>/paths_latent_codes.pt                            [num_paths, 2*shift_steps+1, dim]
+
+    Chains come from one launch of the traversal kernel, frames from the generator's inference path, pixels from the
+    device-side tensor2image; only uint8 crosses PCIe."""
+    import os
+    import os.path as osp
+    from .image_out import images_to_uint8, save_jpeg, save_jpegs
+    from .latent_pool import load_latent_pool
+    hashes, zs = load_latent_pool(pool_dir)
+    dev = next(S.parameters()).device
+    for h, z in zip(hashes, zs):
+        code_dir = osp.join(out_dir, h)
+        os.makedirs(osp.join(code_dir, 'paths_images'), exist_ok=True)
+        res = traverse_paths(G, S, z[None].to(dev), paths=paths, eps=eps, shift_steps=shift_steps, batch_size=batch_size,
+                             shift_in_w_space=shift_in_w_space, return_images=False,
+                             on_frames=None)
+        codes, shifts = res['codes'][0], res['shifts'][0]                      # [P, F, d]
+        P, F_ = codes.shape[0], codes.shape[1]
+        wspace = bool(getattr(G, 'shift_in_w_space', False)) if shift_in_w_space is None else shift_in_w_space
+        for pi in range(P):
+            pdir = osp.join(code_dir, 'paths_images', 'path_%03d' % pi)
+            os.makedirs(pdir, exist_ok=True)
+            pix = []
+            for lo in range(0, F_, batch_size):
+                c, s_ = codes[pi, lo: lo + batch_size], shifts[pi, lo: lo + batch_size]
+                img = G(c, shift=s_, latent_is_w=True) if wspace else G(c, shift=s_)
+                pix.append(images_to_uint8(img, adaptive=True))
+            pix = torch.cat(pix)
+            save_jpegs(pix, [osp.join(pdir, '%06d.jpg' % t) for t in range(F_)], quality=img_quality, img_size=img_size)
+            if pi == 0:
+                save_jpeg(pix[F_ // 2].cpu(), osp.join(code_dir, 'original_image.jpg'), quality=95, img_size=img_size)
+        torch.save(codes.cpu(), osp.join(code_dir, 'paths_latent_codes.pt'))
+    return hashes
