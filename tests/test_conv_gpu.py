@@ -349,3 +349,37 @@ print(worst)
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0, out.stderr[-2000:]
     assert float(out.stdout.strip().splitlines()[-1]) < 2e-5
+
+
+def test_fused_epilogue_multi_image_tiles_under_memcheck():
+    """compute-sanitizer over the fused epilogue on tiles that span more images than the batch holds (4x4 and 8x8 maps,
+    batch 2 and 3): lanes beyond the batch take part in the warp-collective stores and must not read per-image constants
+    out of bounds (a stale read that only faults when the allocator has nothing mapped behind the tensor)."""
+    import shutil, subprocess, sys, os
+    tool = shutil.which('compute-sanitizer') or '/usr/local/cuda/bin/compute-sanitizer'
+    if not os.path.exists(tool):
+        pytest.skip('compute-sanitizer not installed')
+    code = """
+import torch
+from warpedganspace_b200 import conv
+for N, H, C in ((2, 4, 64), (3, 8, 32), (2, 16, 32)):
+    g = torch.Generator().manual_seed(N + H)
+    x = torch.randn(N, H, H, C, generator=g).cuda()
+    w = (torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5).cuda()
+    xs, ws = conv.pack_split32(x), conv.pack_weights(w)
+    alpha = torch.rand(N, C, generator=g).cuda() + 0.5
+    sc = torch.rand(N, C, generator=g).cuda()
+    rgb_w = torch.randn(N, 3, C, generator=g).cuda()
+    rgb = torch.zeros(N, H, H, 3).cuda()
+    nxt = torch.empty(N, H, H, C // 32, 64, dtype=torch.bfloat16).cuda()
+    out = torch.empty(N, H, H, C).cuda()
+    conv.conv2d(xs, ws, 3, 3, padding=1, out=out, alpha=alpha, act=3, out_split=nxt, split_scale=sc, out_from_n=1,
+                rgb_w=rgb_w, rgb_out=rgb)
+    conv.conv2d(xs, ws, 3, 3, padding=1, alpha=alpha, act=1)
+torch.cuda.synchronize()
+print('ok')
+"""
+    out = subprocess.run([tool, '--error-exitcode', '23', '--print-limit', '5', sys.executable, '-c', code],
+                         capture_output=True, text=True, timeout=600,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and 'ok' in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])

@@ -121,7 +121,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     const bool valid = (n < p.out_n) && (oy < p.grid_h) && (ox < p.grid_w);
     float* dst = p.out + (long long)n * p.out_sn + (long long)(oy * p.out_ystep + p.out_y0) * p.out_sy +
                  (long long)(ox * p.out_xstep + p.out_x0) * p.out_sx;
-    const float* alpha = p.alpha ? p.alpha + (size_t)(valid ? n : 0) * p.cout : nullptr;
+    // lanes of a multi-image tile beyond the batch stay in the warp-collective store path: their per-image reads use a
+    // clamped image index (the values are never stored)
+    const int n_rd = n < p.out_n ? n : p.out_n - 1;
+    const float* alpha = p.alpha ? p.alpha + (size_t)n_rd * p.cout : nullptr;
     const float nz = (p.noise && valid)
         ? p.noise_w * __ldg(p.noise + (size_t)(oy * p.out_ystep + p.out_y0) * p.noise_ld + (ox * p.out_xstep + p.out_x0))
         : 0.f;
@@ -281,7 +284,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                     rgb2 += v[i] * ep[5 * BN + c + i];
                 }
             } else {
-                const float* wm = p.rgb_w + (size_t)n * 3 * p.cout + co;
+                const float* wm = p.rgb_w + (size_t)n_rd * 3 * p.cout + co;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     if (co + i < p.cout) {
@@ -305,7 +308,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                                  reinterpret_cast<__nv_bfloat162*>(lo)[(i >> 1) + 1]);
                 }
             } else {
-                const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n * p.split_scale_ld + co : nullptr;
+                const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n_rd * p.split_scale_ld + co : nullptr;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
