@@ -94,3 +94,82 @@ def test_two_rank_gradient_allreduce(tmp_path):
     assert rel(got['gs'], exp_s) < 1e-4, rel(got['gs'], exp_s)
     assert rel(got['gr'], exp_r) < 1e-4, rel(got['gr'], exp_r)
     assert got['slowest'] == 2.0
+
+
+# ---- the training driver under two ranks (host logic only: the CUDA engine is replaced by a stub) ----------------------
+class _StubEngine:
+    """Reports statistics that depend on the rank's shard, so the cross-rank mean in stats.json can be checked."""
+    _graph = None
+
+    def __init__(self):
+        self.seen = []
+
+    def step(self, z, indices, magnitudes):
+        self.seen.append((z.clone(), indices.clone(), magnitudes.clone()))
+        m = z.mean()
+        return dict(accuracy=torch.tensor(0.5), cls=m, reg=2 * m, loss=3 * m)
+
+
+def _trainer_worker(rank, world, port, root, out_dir):
+    import argparse
+    from torch import nn
+    from warpedganspace_b200.trainer import Trainer
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    wdist.init_from_env(backend='gloo')
+    params = argparse.Namespace(batch_size=6, num_support_sets=8, min_shift_magnitude=0.1, max_shift_magnitude=0.2,
+                                z_truncation=None, support_set_lr=1e-4, reconstructor_lr=1e-4, lambda_cls=1.0, lambda_reg=0.25,
+                                max_iter=4, log_freq=2, ckp_freq=4, tensorboard=False, quiet=True)
+
+    class _M(nn.Module):
+        dim_z = 16
+
+        def __init__(self):
+            super().__init__()
+            self.p = nn.Parameter(torch.zeros(3))
+
+    T = Trainer(params, 'exp', use_cuda=True, multi_gpu=True, root=root)
+    eng = _StubEngine()
+    T._device = lambda: torch.device('cpu')
+    T._make_engine = lambda g, s, r: eng
+    torch.manual_seed(11)                                         # every rank draws the FULL batch from the same seed
+    T.train(_M(), _M(), _M())
+    torch.save(eng.seen, os.path.join(out_dir, 'seen_%d.pt' % rank))
+    wdist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_trainer_shards_draws_and_averages_statistics(tmp_path):
+    import json
+    from warpedganspace_b200.trainer import _reference_magnitudes
+    world = 2
+    root, out_dir = str(tmp_path / 'experiments'), str(tmp_path)
+    mp.spawn(_trainer_worker, args=(world, _free_port(), root, out_dir), nprocs=world, join=True)
+    seen = [torch.load(os.path.join(out_dir, 'seen_%d.pt' % r)) for r in range(world)]
+    # the single-process draw sequence (reference order) ...
+    torch.manual_seed(11)
+    full = []
+    for _ in range(4):
+        z = torch.randn(6, 16)
+        idx = torch.randint(0, 8, [6])
+        full.append((z, idx, _reference_magnitudes(6, 0.1, 0.2)))
+    # ... is what the two ranks saw, split 3 + 3
+    for it in range(4):
+        for r in range(world):
+            lo, hi = wdist.shard_range(6, r, world)
+            for got, want in zip(seen[r][it], full[it]):
+                assert torch.equal(got, want[lo:hi])
+    # rank 0 alone wrote the files; every window holds the mean over ranks and iterations
+    wip = os.path.join(root, 'wip', 'exp')
+    stats = json.load(open(os.path.join(wip, 'stats.json')))
+    assert sorted(stats) == ['2', '4']
+    for key, its in (('2', (0, 1)), ('4', (2, 3))):
+        want = sum(float(full[i][0][lo:hi].mean()) for i in its for lo, hi in (wdist.shard_range(6, r, world) for r in range(world))) / 4
+        assert stats[key]['classification_loss'] == pytest.approx(want, rel=1e-5, abs=1e-7)
+        assert stats[key]['total_loss'] == pytest.approx(3 * want, rel=1e-5, abs=1e-7)
+        assert stats[key]['accuracy'] == pytest.approx(0.5)
+    assert sorted(os.listdir(os.path.join(wip, 'models'))) == ['checkpoint.pt', 'reconstructor.pt', 'support_sets.pt',
+                                                                'support_sets_init.pt']
+    assert os.path.isdir(os.path.join(root, 'complete', 'exp'))
