@@ -148,3 +148,33 @@ def test_no_cpu_path(golden, tmp_path):
         T.train(_G(), _S(), _R())
     with pytest.raises(ValueError):
         Trainer(None, 'x')
+
+
+def test_checkpoint_to_models_and_load_experiment(golden, tmp_path, monkeypatch):
+    """checkpoint2model.py and the experiment loader of traverse_latent_space.py:252-297 on a driver-written tree."""
+    from warpedganspace_b200 import SupportSets
+    from warpedganspace_b200.checkpoint import checkpoint_to_models, load_experiment
+    fx = golden('trainer_c1.pt')
+    root = str(tmp_path / 'experiments')
+    p = _params(fx, max_iter=3, quiet=True)
+    aux.create_exp_dir(p, root=root)
+    S = SupportSets(fx['K'], fx['D'], fx['d'], learn_gammas=True, gamma=1.0 / fx['d'])
+    T = Trainer(p, fx['exp_dir'], use_cuda=True, root=root)
+    monkeypatch.setattr(T, '_device', lambda: torch.device('cpu'))
+    monkeypatch.setattr(T, '_make_engine', lambda g, s, r: _StubEngine(s, _R()))
+    T.train(_G(), S, _R())
+    wip = os.path.join(root, 'wip', fx['exp_dir'])
+    assert checkpoint_to_models(wip) == 3
+    ckpt = torch.load(os.path.join(wip, 'models', 'checkpoint.pt'))
+    assert torch.equal(torch.load(os.path.join(wip, 'models', 'support_sets-3.pt'))['SUPPORT_SETS'],
+                       ckpt['support_sets']['SUPPORT_SETS'])
+    args, S2 = load_experiment(wip)
+    assert args.num_support_sets == fx['K'] and S2.support_vectors_dim == fx['d'] and S2.learn_gammas
+    assert torch.equal(S2.SUPPORT_SETS.detach(), torch.load(os.path.join(wip, 'models', 'support_sets.pt'))['SUPPORT_SETS'])
+    _, S3 = load_experiment(wip, iteration=3)
+    assert torch.equal(S3.SUPPORT_SETS.detach(), ckpt['support_sets']['SUPPORT_SETS'])
+    with pytest.raises(NotADirectoryError):
+        checkpoint_to_models(str(tmp_path / 'nope'))
+    with pytest.raises(FileNotFoundError):
+        os.makedirs(tmp_path / 'e2' / 'models')
+        checkpoint_to_models(str(tmp_path / 'e2'))
