@@ -50,3 +50,25 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_struct_mirrors_match_the_header_layout():
+    """The ctypes mirrors of wgs_conv_desc / wgs_linear_problem have the size the compiled library reports (no GPU needed:
+    the size functions are plain host code)."""
+    from warpedganspace_b200 import conv, stylegan2
+    l = _lib.load()
+    assert l.wgs_conv_desc_size() == ctypes.sizeof(conv.ConvDesc)
+    assert l.wgs_linear_problem_size() == ctypes.sizeof(stylegan2.LinearProblem)
+
+
+def test_every_product_module_refuses_cpu_tensors():
+    """No CPU fallback anywhere on the product path: each public entry raises on CPU input instead of computing."""
+    from warpedganspace_b200 import conv, image_out
+    from warpedganspace_b200.reconstructor import Reconstructor
+    with pytest.raises(RuntimeError):
+        conv.pack_split32(torch.randn(4, 32))
+    with pytest.raises(RuntimeError):
+        image_out.images_to_uint8(torch.randn(1, 3, 8, 8))
+    R = Reconstructor('LeNet', 4, 1)
+    with pytest.raises(RuntimeError):
+        R(torch.randn(2, 1, 32, 32), torch.randn(2, 1, 32, 32))
