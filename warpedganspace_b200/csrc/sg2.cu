@@ -139,7 +139,7 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
         const int yy0 = Y0 - pad0, xx0 = X - pad0;
         const float* base = y + ((long long)n * Hin + yy0) * row_stride + (long long)xx0 * C + c;
         // noise of the 8 output rows up front: loading it inside the row loop serialises 8 global-load latencies
-        // behind the stores (47 % of this kernel's stall samples, profiles/r01_bandwidth_kernels_ncu.md)
+        // behind the stores (47 % of this kernel's stall samples, profiles/r01_misc_ncu.md)
         float nzv[FIR_ROWS];
 #pragma unroll
         for (int oy = 0; oy < FIR_ROWS; ++oy)

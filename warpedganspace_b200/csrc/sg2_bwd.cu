@@ -186,7 +186,7 @@ sg2_layer_bwd_kernel(const float* __restrict__ dx_up, const float* __restrict__ 
     }
     float acc_u[4] = {0.f, 0.f, 0.f, 0.f}, acc_r[4] = {0.f, 0.f, 0.f, 0.f}, acc_d[4] = {0.f, 0.f, 0.f, 0.f};
     // LBW_U pixels per trip with every load issued before the first use: one pixel per trip leaves a single batch of
-    // loads in flight per thread and 66 % of the stall samples on the two first uses (profiles/r01_bandwidth_kernels_ncu.md)
+    // loads in flight per thread and 66 % of the stall samples on the two first uses (profiles/r01_misc_ncu.md)
     constexpr int LBW_U = 4;
     for (long long pb = p0 + pl; pb < p1; pb += (long long)PL * LBW_U) {
         float4 a4[LBW_U], g4[LBW_U];
