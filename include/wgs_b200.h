@@ -29,7 +29,8 @@ int  wgs_device_info(int* sms, int* cc);         /* fails unless the current dev
  *   grad_f = -2 * sum_j alpha[k,j] * gamma_k * exp(-gamma_k * |z - s_kj|^2) * (z - s_kj),  k = idx[b].
  * support_sets [K, n_vec*d] (n_vec = 2 * num_support_dipoles), alphas [K, n_vec], loggamma [K] or NULL
  * (then gamma = fixed_gamma, the learn_gammas=False branch :93), idx [B] int64, z [B, d],
- * mag [B] or NULL (= 1, the bare module output), out [B, d].  d % 4 == 0, d <= 1024.             */
+ * mag [B] or NULL (= 1, the bare module output), out [B, d].  d <= 1024 (128-bit row loads when d % 4 == 0,
+ * guarded scalar loads otherwise: BigGAN-256 has dim_z = 119).                                     */
 int wgs_rbf_warp_forward(const float* support_sets, const float* alphas, const float* loggamma,
                          float fixed_gamma, const long long* idx, const float* z, const float* mag,
                          float* out, int B, int K, int n_vec, int d, void* stream);
@@ -49,6 +50,24 @@ int wgs_rbf_warp_backward(const float* support_sets, const float* alphas, const 
 int wgs_rbf_traverse(const float* support_sets, const float* alphas, const float* loggamma,
                      float fixed_gamma, const long long* path, const float* start, float eps, int steps,
                      float* codes, float* shifts, int chains, int K, int n_vec, int d, void* stream);
+
+/* ---- op-level boundary: the reference's two native extensions ------------------------------------- *
+ * wgs_fused_bias_act replaces `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)`
+ * (models/StyleGAN2/op/fused_bias_act.cpp:11-20; kernel op/fused_bias_act_kernel.cu:18-49):
+ *   out[i] = f(x[i] + b[(i / step_b) % size_b]) * scale,  f selected by act (1 linear, 3 leaky ReLU with slope alpha)
+ *   and grad (0 value; 1 first derivative taken at the sign of ref[i], the forward OUTPUT; 2 second derivative = 0).
+ * b may be NULL (no bias), ref may be NULL when grad == 0.  n elements; step_b = product of the dims after the channel
+ * dim, size_b = channels (op/fused_bias_act_kernel.cu:66-71).
+ * wgs_upfirdn2d replaces `upfirdn2d_op.upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0,
+ * pad_y1)` (op/upfirdn2d.cpp:12-22; kernel op/upfirdn2d_kernel.cu:52-272): in [major, in_h, in_w, minor] ->
+ * out [major, out_h, out_w, minor], out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1 (same for w); zero-insert
+ * up-sampling, padding (negative = crop), correlation with the FLIPPED kernel [kh, kw], decimation.  Any up / down /
+ * kernel size (the reference silently reads an uninitialised tile size outside its six modes).   */
+int wgs_fused_bias_act(const float* x, const float* b, const float* ref, float* out, long long n, long long step_b,
+                       int size_b, int act, int grad, float alpha, float scale, void* stream);
+int wgs_upfirdn2d(const float* in, const float* kernel, float* out, int major, int in_h, int in_w, int minor,
+                  int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                  int pad_y1, void* stream);
 
 /* ---- tensor-core convolution -------------------------------------------------------------------- *
  * "split32" operand format: every 32 fp32 channels become one 128-byte row of 64 bf16 —

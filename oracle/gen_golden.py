@@ -192,6 +192,125 @@ def pin_stylegan2(model, up_mod):
         save('stylegan2_%d.pt' % size, fx)
 
 
+
+def _sample_grad(g, limit=20000):
+    """Whole tensor when small, else a fixed strided sample (fixtures stay small)."""
+    flat = g.reshape(-1)
+    if flat.numel() <= limit:
+        return dict(stride=1, values=flat.clone())
+    stride = flat.numel() // limit + 1
+    return dict(stride=stride, values=flat[::stride].clone())
+
+
+def pin_stylegan2_1024_step(model):
+    """BASELINE config 3 at FULL size (StyleGAN2-1024, K=128, D=32, ResNet-18 R at 1024^2), batch 2: the reference
+    modules' own loop body (lib/trainer.py:190-250) with injected draws, in Z space; plus a W-space forward pair.
+    Gradients are additionally computed by the oracle in fp64: ReLU / leaky-ReLU / max-pool kinks make fp32 gradients of
+    ANY two implementations of this graph differ at the 1e-3 level (millions of activations, a few within rounding of
+    a kink), so every stored gradient carries the reference-fp32-vs-fp64 distance as its yardstick."""
+    import oracle.stylegan2 as o
+    import oracle.support_sets as o_ss
+    import oracle.reconstructor as o_rec
+    import oracle.step as o_step
+    ss_ref = importlib.import_module('lib.support_sets')
+    rec_ref = importlib.import_module('lib.reconstructor')
+    gan_load = importlib.import_module('models.gan_load')
+    print('[stylegan2-1024 paired step, config 3 at full size]')
+    K, D, d, B, size = 128, 32, 512, 2, 1024
+    seeds = (111, 112, 113)
+    g_sd = o.init_state(size=size, generator=gen(seeds[0]))
+    s_sd = o_ss.init_state(K, D, d, generator=gen(seeds[1]))
+    r_sd = o_rec.init_state('ResNet', K, 3, generator=gen(seeds[2]))
+    G = model.Generator(size, 512, 8)
+    res = G.load_state_dict(g_sd, strict=False)
+    assert not res.unexpected_keys and all(k.endswith('.kernel') for k in res.missing_keys), res
+    G.eval()
+    W = gan_load.StyleGAN2Wrapper(G, shift_in_w_space=False)
+    S = ss_ref.SupportSets(K, D, d, learn_alphas=False, learn_gammas=True, gamma=1.0 / d)
+    S.load_state_dict(s_sd)
+    R = rec_ref.Reconstructor('ResNet', K, 3)
+    R.load_state_dict(r_sd)
+    S.train(); R.train()
+    for p in G.parameters():
+        p.requires_grad_(False)          # the reference leaves these on and discards the result (SURVEY mismatch 4)
+    g = gen(114)
+    z = torch.randn(B, d, generator=g)
+    idx = torch.tensor([5, 77])
+    mag = torch.tensor([0.15, -0.12])
+    mask = o_ss.one_hot(idx, K)
+    img = W(z)
+    shift = mag.reshape(-1, 1) * S(mask, z)
+    img_shifted = W(z, shift)
+    logits, pred = R(img, img_shifted)
+    cls = torch.nn.CrossEntropyLoss()(logits, idx)
+    reg = torch.mean(torch.abs(pred - mag))
+    loss = 1.0 * cls + 0.25 * reg
+    loss.backward()
+    d_ss = S.SUPPORT_SETS.grad.clone()
+    d_lg = S.LOGGAMMA.grad.clone()
+    r_grads = {k: p.grad.clone() for k, p in R.named_parameters() if p.grad is not None}
+    running = {k: v.clone() for k, v in R.state_dict().items() if 'running' in k}
+    print('  reference fp32 step done: loss %.6f' % float(loss))
+    # oracle fp32 (pins the restatement at full size)
+    gen_fn, _ = o_step.make_generator('StyleGAN2', g_sd, size=size)
+    o32 = o_step.paired_step(gen_fn, s_sd, r_sd, z, idx, mag, reconstructor_type='ResNet')
+    check('img', o32['img'], img.detach(), 2e-5)
+    check('img_shifted', o32['img_shifted'], img_shifted.detach(), 2e-5)
+    check('logits', o32['logits'], logits.detach(), 1e-4)
+    check('loss', o32['loss'], loss.detach(), 1e-5)
+    # oracle fp64: the gradient yardstick
+    to64 = lambda sd: {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    g64, s64, r64 = to64(g_sd), to64(s_sd), to64(r_sd)
+    gen64, _ = o_step.make_generator('StyleGAN2', g64, size=size)
+    o64 = o_step.paired_step(gen64, s64, r64, z.double(), idx, mag.double(), reconstructor_type='ResNet')
+    print('  oracle fp64 step done: loss %.6f' % float(o64['loss']))
+    # oracle fp32 under the kernels' arithmetic model (bf16 hi+lo operands in every dense forward conv): how far the
+    # gradients of this graph move for a ~1e-5 forward perturbation (oracle/emulate.py)
+    import oracle.emulate as o_emul
+    with o_emul.split17_convs(o, o_rec):
+        oem = o_step.paired_step(gen_fn, s_sd, r_sd, z, idx, mag, reconstructor_type='ResNet')
+    print('  oracle fp32 with split17 operand rounding done: img_shifted rel err %.2e' % rel_err(oem['img_shifted'], o64['img_shifted']))
+    rows = torch.unique(idx)
+    yard_emul = {'SUPPORT_SETS': rel_err(oem['grads']['S']['SUPPORT_SETS'][rows], o64['grads']['S']['SUPPORT_SETS'][rows]),
+                 'LOGGAMMA': rel_err(oem['grads']['S']['LOGGAMMA'][rows], o64['grads']['S']['LOGGAMMA'][rows]),
+                 'img_shifted': rel_err(oem['img_shifted'], o64['img_shifted']), 'logits': rel_err(oem['logits'], o64['logits'])}
+    yard = {'SUPPORT_SETS': rel_err(d_ss[rows], o64['grads']['S']['SUPPORT_SETS'][rows]),
+            'LOGGAMMA': rel_err(d_lg[rows], o64['grads']['S']['LOGGAMMA'][rows]),
+            'img_shifted': rel_err(img_shifted.detach(), o64['img_shifted']), 'logits': rel_err(logits.detach(), o64['logits'])}
+    rg = {}
+    for k, v in r_grads.items():
+        e = rel_err(v, o64['grads']['R'][k])
+        rg[k] = dict(norm=float(o64['grads']['R'][k].norm()), fp32_vs_fp64=e,
+                     split17_vs_fp64=rel_err(oem['grads']['R'][k], o64['grads']['R'][k]), **_sample_grad(o64['grads']['R'][k].float()))
+    worst = max(v['fp32_vs_fp64'] for v in rg.values())
+    print('  reference-fp32 vs oracle-fp64: dSUPPORT_SETS %.2e, dLOGGAMMA %.2e, worst dR %.2e, logits %.2e'
+          % (yard['SUPPORT_SETS'], yard['LOGGAMMA'], worst, yard['logits']))
+    print('  split17 model  vs oracle-fp64: dSUPPORT_SETS %.2e, dLOGGAMMA %.2e, worst dR %.2e, logits %.2e'
+          % (yard_emul['SUPPORT_SETS'], yard_emul['LOGGAMMA'], max(v['split17_vs_fp64'] for v in rg.values()), yard_emul['logits']))
+    # W-space pair (forward only)
+    Ww = gan_load.StyleGAN2Wrapper(G, shift_in_w_space=True)
+    with torch.no_grad():
+        wshift = 0.15 * F.normalize(torch.randn(B, d, generator=g), dim=1)
+        img_w = Ww(z, wshift)
+        check('img W-space', o.generate(g_sd, z, wshift, size, True), img_w, 2e-5)
+    st = 8
+    samp = lambda t: t.detach()[:, :, ::st, ::st].clone()
+    save('stylegan2_1024_step.pt', dict(
+        K=K, D=D, d=d, B=B, size=size, seeds=seeds, checksums=(checksum(g_sd), checksum(s_sd), checksum(r_sd)),
+        z=z, idx=idx, mag=mag, wshift=wshift, stride=st,
+        img=samp(img), img_shifted=samp(img_shifted), img_w=samp(img_w),
+        img_mean=float(img.double().mean()), img_std=float(img.double().std()),
+        img_shifted_std=float(img_shifted.double().std()), img_w_std=float(img_w.double().std()),
+        img_row=img.detach()[:, :, 517, :].clone(), img_shifted_row=img_shifted.detach()[:, :, 517, :].clone(),
+        shift=shift.detach(), logits=logits.detach(), pred=pred.detach(), cls=cls.detach(), reg=reg.detach(),
+        loss=loss.detach(), rows=rows,
+        logits64=o64['logits'].float(), loss64=float(o64['loss']),
+        d_support_sets_rows=d_ss[rows].clone(), d_support_sets_rows64=o64['grads']['S']['SUPPORT_SETS'][rows].float(),
+        d_loggamma=d_lg.clone(), d_loggamma64=o64['grads']['S']['LOGGAMMA'].float(),
+        r_grads64=rg, yardstick=yard, yardstick_split17=yard_emul,
+        running_sample={k: running[k] for k in ('features_extractor.bn1.running_mean', 'features_extractor.bn1.running_var',
+                                                'features_extractor.layer4.1.bn2.running_var')}))
+
 def pin_proggan():
     import oracle.proggan as o
     ref = importlib.import_module('models.ProgGAN.model')
@@ -538,6 +657,12 @@ def main():
     torch.set_num_threads(os.cpu_count())
     os.chdir('/tmp')
     model, up_mod = import_reference()
+    only = sys.argv[1:]
+    if only:                                     # e.g. python -m oracle.gen_golden stylegan2_1024_step
+        for name in only:
+            fn = globals()['pin_' + name]
+            fn(*((model, up_mod) if name == 'stylegan2' else (model,) if name == 'stylegan2_1024_step' else ()))
+        return
     pin_support_sets()
     pin_stylegan2(model, up_mod)
     pin_sngan()
@@ -548,6 +673,7 @@ def main():
     pin_latent_pool()
     pin_proggan()
     pin_biggan()
+    pin_stylegan2_1024_step(model)
     print('oracle pinned against the reference; fixtures in', OUT)
 
 

@@ -47,9 +47,10 @@ def sample_shift_magnitudes(batch, min_mag, max_mag, generator=None):
 
 
 def paired_step(gen, s_state, r_state, z, indices, magnitudes, *, reconstructor_type='ResNet',
-                learn_gammas=True, lambda_cls=1.0, lambda_reg=0.25, get_w=None, running=None):
+                learn_gammas=True, lambda_cls=1.0, lambda_reg=0.25, get_w=None, running=None, train_bn=True):
     """Forward + backward of one step.  Returns dict(img, img_shifted, shift, logits, pred_mag,
-    cls_loss, reg_loss, loss, accuracy, grads={'S': {...}, 'R': {...}})."""
+    cls_loss, reg_loss, loss, accuracy, grads={'S': {...}, 'R': {...}}).  train_bn=False evaluates the Reconstructor's
+    BatchNorm with its running statistics (R.eval()) - used by the well-conditioned whole-graph gradient test."""
     K = s_state['SUPPORT_SETS'].shape[0]
     s_leaf = {k: v.detach().clone().requires_grad_(k != 'ALPHAS') for k, v in s_state.items()}
     if not learn_gammas:
@@ -65,7 +66,7 @@ def paired_step(gen, s_state, r_state, z, indices, magnitudes, *, reconstructor_
     direction = o_ss.forward(s_leaf, mask, where, learn_gammas=learn_gammas)
     shift = magnitudes.reshape(-1, 1) * direction                           # :235
     img_shifted = gen(z, shift)                                             # :239
-    logits, pred = o_rec.forward(r_leaf, img, img_shifted, reconstructor_type, True, running)   # :242
+    logits, pred = o_rec.forward(r_leaf, img, img_shifted, reconstructor_type, train_bn, running)   # :242
     cls = F.cross_entropy(logits, indices)                                  # :245
     reg = torch.mean(torch.abs(pred - magnitudes))                          # :246
     loss = lambda_cls * cls + lambda_reg * reg                              # :249

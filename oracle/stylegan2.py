@@ -44,7 +44,7 @@ def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0)):
         x = y.reshape(n, c, h * up, w * up)
     x = F.pad(x, [max(p0, 0), max(p1, 0), max(p0, 0), max(p1, 0)])
     x = x[:, :, max(-p0, 0): x.shape[2] - max(-p1, 0), max(-p0, 0): x.shape[3] - max(-p1, 0)]
-    wgt = torch.flip(kernel, [0, 1]).to(x.dtype).view(1, 1, kh, kw).expand(c, 1, kh, kw)
+    wgt = torch.flip(kernel, [0, 1]).to(device=x.device, dtype=x.dtype).view(1, 1, kh, kw).expand(c, 1, kh, kw)
     x = F.conv2d(x, wgt, groups=c)
     return x[:, :, ::down, ::down]
 

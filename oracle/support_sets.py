@@ -45,7 +45,7 @@ def forward(state, mask, z, learn_gammas=True, gamma=None):
         gammas = torch.exp(mask @ LG).unsqueeze(2)            # :91
     else:
         g = gamma if gamma is not None else 1.0 / d
-        gammas = torch.full((z.shape[0], n, 1), g, dtype=z.dtype)   # :93
+        gammas = torch.full((z.shape[0], n, 1), g, dtype=z.dtype, device=z.device)   # :93
     diff = z.unsqueeze(1) - sets                              # :96
     sq = torch.norm(diff, dim=2) ** 2                         # :98 (norm()**2, as the reference)
     grad = -2.0 * (alphas * gammas * torch.exp(-gammas * sq.unsqueeze(2)) * diff).sum(dim=1)
@@ -54,6 +54,6 @@ def forward(state, mask, z, learn_gammas=True, gamma=None):
 
 def one_hot(indices, num_support_sets, dtype=torch.float32):
     """The mask lib/trainer.py:227-231 builds with a Python loop."""
-    m = torch.zeros(indices.shape[0], num_support_sets, dtype=dtype)
-    m[torch.arange(indices.shape[0]), indices] = 1.0
+    m = torch.zeros(indices.shape[0], num_support_sets, dtype=dtype, device=indices.device)
+    m[torch.arange(indices.shape[0], device=indices.device), indices] = 1.0
     return m

@@ -59,7 +59,8 @@ def test_fixture_benchmark_shape(golden):
 
 
 @pytest.mark.parametrize('K,D,d,B', [(32, 16, 128, 4), (120, 256, 120, 8), (200, 64, 512, 12), (7, 1, 4, 3),
-                                     (16, 5, 1024, 2), (128, 32, 512, 64)])
+                                     (16, 5, 1024, 2), (128, 32, 512, 64),
+                                     (120, 256, 119, 8), (9, 3, 7, 3), (5, 2, 130, 2)])     # d % 4 != 0: BigGAN-256's dim_z = 119
 def test_against_oracle(K, D, d, B):
     sd, S = make(K, D, d, 100 + K)
     g = gen(7 + d)
@@ -130,3 +131,19 @@ def test_traversal_many_chains():
     n = torch.cat([n[:, :steps], n[:, steps + 1:]], dim=1)
     assert torch.allclose(n, torch.full_like(n, eps), atol=1e-6)
     assert float(shifts[:, steps].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('d,leap', [(512, 1), (512, 4), (119, 3)])
+def test_traversal_shift_leap_and_unaligned_dims(d, leap):
+    """--shift_leap (traverse_latent_space.py:404,434): only every leap-th step of each direction is kept; also the
+    scalar-tail path for latent dimensions that are not a multiple of 4 (BigGAN-256: dim_z = 119)."""
+    K, D, steps, eps = 12, 6, 12, 0.2
+    sd, S = make(K, D, d, 70 + d)
+    g = gen(71)
+    start = torch.randn(5, d, generator=g)
+    paths = torch.randint(0, K, (5,), generator=g)
+    codes, shifts = S.traverse(start.cuda(), paths.cuda(), eps, steps, shift_leap=leap)
+    assert codes.shape == (5, 2 * (steps // leap) + 1, d)
+    for c in range(5):
+        wc, ws = o_step.traverse_chain(sd, start[c:c + 1], int(paths[c]), eps, steps, shift_leap=leap)
+        assert rel(codes[c], wc) < 1e-5 and rel(shifts[c], ws) < 1e-4

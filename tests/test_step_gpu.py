@@ -98,7 +98,8 @@ def test_adam_kernel_matches_oracle():
     po, mo, vo = p0.clone(), torch.zeros(n), torch.zeros(n)
     for step in range(1, 4):
         gr = torch.randn(n, generator=g) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))
-        _lib.call('wgs_adam_step', _lib.ptr(p), _lib.ptr(gr.cuda()), _lib.ptr(m), _lib.ptr(v), n, 1e-4, 0.9, 0.999, 1e-8,
+        gr_dev = gr.cuda()                 # keep a reference: _lib.ptr() of a temporary would free it before the launch
+        _lib.call('wgs_adam_step', _lib.ptr(p), _lib.ptr(gr_dev), _lib.ptr(m), _lib.ptr(v), n, 1e-4, 0.9, 0.999, 1e-8,
                   step, 1.0, None, _lib.stream())
         o_step.adam_update(po, gr, mo, vo, step)
     assert rel(p.cpu() - p0, po - p0) < 1e-4

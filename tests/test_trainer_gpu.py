@@ -20,6 +20,11 @@ def gen(seed):
     return torch.Generator().manual_seed(seed)
 
 
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
 def _build(fx):
     from warpedganspace_b200 import SupportSets
     from warpedganspace_b200.generators import SNGANGenerator
@@ -77,3 +82,83 @@ def test_trainer_matches_reference_driver(golden, tmp_path, graph):
     ckpt = torch.load(os.path.join(wip, 'models', 'checkpoint.pt'))
     assert ckpt['iter'] == fx['checkpoint_iter']
     assert {k: sorted(v.keys()) if isinstance(v, dict) else None for k, v in ckpt.items()} == fx['checkpoint_keys']
+
+
+def test_reference_shaped_loop_over_the_repo_modules_matches_paired_trainer():
+    """the reference's own loop body (lib/trainer.py:190-254) - one-hot mask built row by row,
+    module forwards, loss.backward(), two torch.optim.Adam - written against the repo's drop-in modules must train like
+    PairedTrainer (indices + fused magnitude, batched pair, flat fused Adam) on the same init and the same draws."""
+    import torch.nn as nn
+    import oracle.support_sets as o_ss
+    import oracle.stylegan2 as o_sg2
+    import oracle.reconstructor as o_rec
+    import oracle.step as o_step
+    from warpedganspace_b200 import SupportSets
+    from warpedganspace_b200.stylegan2 import Generator
+    from warpedganspace_b200.gan_load import StyleGAN2Wrapper
+    from warpedganspace_b200.reconstructor import Reconstructor
+    from warpedganspace_b200.trainer import PairedTrainer
+    ch = {4: 64, 8: 64, 16: 32, 32: 32}
+    K, D, B, size, iters = 16, 4, 4, 32, 3
+    gen = lambda s: torch.Generator().manual_seed(s)
+    g_sd = o_sg2.init_state(size=size, generator=gen(301), channels=ch)
+    s_sd = o_ss.init_state(K, D, 512, generator=gen(302))
+    r_sd = o_rec.init_state('ResNet', K, 3, generator=gen(303))
+
+    def modules():
+        G = Generator(size, 512, 8, channels=ch)
+        G.load_state_dict(g_sd, strict=False)
+        S = SupportSets(K, D, 512, learn_alphas=False, learn_gammas=True, gamma=1.0 / 512)
+        S.load_state_dict(s_sd)
+        R = Reconstructor('ResNet', K, 3)
+        R.load_state_dict(r_sd)
+        return StyleGAN2Wrapper(G, shift_in_w_space=False).cuda().eval(), S.cuda().train(), R.cuda().train()
+
+    g = gen(304)
+    draws = [(torch.randn(B, 512, generator=g), torch.randint(0, K, (B,), generator=g),
+              o_step.sample_shift_magnitudes(B, 0.1, 0.2, generator=g)) for _ in range(iters)]
+    # --- the reference loop, verbatim in structure
+    G, S, R = modules()
+    s_opt = torch.optim.Adam(S.parameters(), lr=1e-4)
+    r_opt = torch.optim.Adam(R.parameters(), lr=1e-4)
+    cross_entropy = nn.CrossEntropyLoss()
+    ref_losses, ref_grad = [], None
+    for z, idx, mag in draws:
+        z, idx, mag = z.cuda(), idx.cuda(), mag.cuda()
+        G.zero_grad(); S.zero_grad(); R.zero_grad()
+        img = G(z)
+        mask = torch.zeros([B, S.num_support_sets]).cuda()
+        for i, index in enumerate(idx):
+            mask[i][index] += 1.0
+        shift = mag.reshape(-1, 1) * S(mask, z)
+        img_shifted = G(z, shift)
+        logits, pred = R(img, img_shifted)
+        loss = 1.0 * cross_entropy(logits, idx) + 0.25 * torch.mean(torch.abs(pred - mag))
+        loss.backward()
+        if ref_grad is None:
+            ref_grad = (S.SUPPORT_SETS.grad.clone(), R.path_indices.weight.grad.clone(),
+                        R.features_extractor.conv1.weight.grad.clone())
+        s_opt.step(); r_opt.step()
+        ref_losses.append(float(loss))
+    ref_S = S.SUPPORT_SETS.detach().clone()
+    # --- the engine
+    G, S, R = modules()
+    T = PairedTrainer(G, S, R)
+    eng_losses, eng_grad = [], None
+    for z, idx, mag in draws:
+        out = T.forward_backward(z.cuda(), idx.cuda(), mag.cuda())
+        if eng_grad is None:
+            eng_grad = (S.SUPPORT_SETS.grad.clone(), R.path_indices.weight.grad.clone(),
+                        R.features_extractor.conv1.weight.grad.clone())
+        T.optimizer_step()
+        eng_losses.append(float(out['loss']))
+    print('reference-shaped loop losses', ref_losses, 'engine losses', eng_losses)
+    assert abs(ref_losses[0] - eng_losses[0]) < 1e-5 * abs(ref_losses[0])
+    # same forward inputs, same kernels underneath: only the accumulation order of atomically-reduced sums differs
+    for a, b in zip(ref_grad, eng_grad):
+        assert rel(a, b) < 1e-3
+    for a, b in zip(ref_losses, eng_losses):
+        assert abs(a - b) < 2e-3 * abs(a)
+    moved = (ref_S.cpu() - s_sd['SUPPORT_SETS']).abs().amax(dim=1) > 0
+    assert set(moved.nonzero().flatten().tolist()) == set(torch.cat([d[1] for d in draws]).tolist())
+    assert rel(S.SUPPORT_SETS, ref_S) < 1e-4

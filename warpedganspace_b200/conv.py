@@ -22,12 +22,14 @@ def _prof_begin():
     return e0
 
 
-def _prof_end(e0, kind, flops, nbytes=0):
+def _prof_end(e0, kind, flops, nbytes=0, issued=None, tag=''):
+    """flops = ALGORITHMIC FLOPs of the launch (real taps, true channel counts); issued = logical FLOPs the kernel
+    actually contracts (zero weight blocks of phase-packed launches and channel padding to 32 included)."""
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record()
-    PROFILE.append((kind, flops, e0, e1, nbytes))
+    PROFILE.append((kind, flops, e0, e1, nbytes, flops if issued is None else issued, tag))
 
 
 class ConvDesc(ctypes.Structure):
@@ -114,7 +116,8 @@ def pack_weights(w):
 
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
               alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None,
-              out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None, groups=None):
+              out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None, groups=None,
+              algo_macs_per_pixel=None):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -172,7 +175,15 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
             nbytes += out_split.numel() * 2
         if rgb_out is not None:
             nbytes += npix * 3 * 4 * 2
-        _prof_end(e0, 'conv', 2.0 * npix * d.cout * (cin or chunks * 32) * len(taps), nbytes)
+        # algorithmic work: real taps x true channels (phase-packed launches pass the MACs per grid pixel of their real,
+        # non-zero weight blocks); issued work: what the MMAs contract, padding and zero blocks included
+        macs = algo_macs_per_pixel if algo_macs_per_pixel is not None else \
+            d.cout * (cin or chunks * 32) * len(taps)
+        issued = 2.0 * npix * ((d.cout + 15) // 16 * 16) * chunks * 32 * len(taps)
+        tag = '%s%d->%d k%d s%d @%dx%d n%d%s' % ('packed ' if groups else '', cin or chunks * 32,
+                                                 groups[0] if groups else d.cout, len(taps), in_stride, grid[0], grid[1], d.out_n,
+                                                 ' fused' if (out_split is not None or rgb_out is not None) else '')
+        _prof_end(e0, 'conv', 2.0 * npix * macs, nbytes, issued, tag)
     return out
 
 
@@ -247,6 +258,18 @@ def _phase_plan(kind, kh, kw, stride, padding, device):
     return hit
 
 
+_REAL_BLOCKS = {}
+
+
+def _real_blocks(idx, T):
+    """Number of (shift, phase) blocks of a phase plan that hold a real tap (host-side, cached: no device sync per launch)."""
+    key = (idx.data_ptr(), T)
+    hit = _REAL_BLOCKS.get(key)
+    if hit is None:
+        hit = _REAL_BLOCKS[key] = int((idx != T).sum())
+    return hit
+
+
 def merged_phase_weights(w_src, idx, S, G):
     """w_src fp32 [rows, K, T] -> split32 [S, G*rows, ceil(K/32), 64] with block (s, g) = w_src[:, :, idx[s*G+g]]
     (zero where idx == T)."""
@@ -268,19 +291,19 @@ def conv_dgrad_merged(dys, w, in_hw, stride, padding, out=None, accumulate=False
     taps = [(sy, sx, i) for i, (sy, sx) in enumerate(shifts)]
     gh, gw = (h + stride - 1) // stride, (wd + stride - 1) // stride
     conv_taps(dys, w_merged, taps, dx, grid=(gh, gw), out_step=(stride, stride), cout=G * ci, cin=co,
-              accumulate=accumulate, groups=(ci, stride))
+              accumulate=accumulate, groups=(ci, stride), algo_macs_per_pixel=_real_blocks(idx, kh * kw) * ci * co)
     return dx
 
 
-def conv_transpose2d_s2_merged(x_split, w_merged, k, co, out=None):
+def conv_transpose2d_s2_merged(x_split, w_merged, k, co, out=None, cin=None):
     """F.conv_transpose2d(stride=2, padding=0) for a k x k kernel in ONE launch; w_merged from
     merged_phase_weights(w[Co, Ci, k*k], *_phase_plan('convT', k, k, 2, 0))."""
     n, h, w_, _, _ = x_split.shape
     oh, ow = 2 * (h - 1) + k, 2 * (w_ - 1) + k
-    shifts, _, G = _phase_plan('convT', k, k, 2, 0, x_split.device)
+    shifts, idx, G = _phase_plan('convT', k, k, 2, 0, x_split.device)
     if out is None:
         out = torch.empty(n, oh, ow, co, dtype=torch.float32, device=x_split.device)
     taps = [(sy, sx, i) for i, (sy, sx) in enumerate(shifts)]
     conv_taps(x_split, w_merged, taps, out, grid=((oh + 1) // 2, (ow + 1) // 2), out_step=(2, 2), cout=G * co,
-              groups=(co, 2))
+              groups=(co, 2), algo_macs_per_pixel=_real_blocks(idx, k * k) * co * (cin or x_split.shape[3] * 32), cin=cin)
     return out

@@ -18,13 +18,40 @@ constexpr int RBF_WARPS = RBF_THREADS / 32;
 template <int NV>
 struct LaneVec { float4 v[NV]; };
 
-// lane owns float4 #(i*32 + lane), i < NV, of a d-vector (d % 4 == 0)
+// lane owns elements [(i*32 + lane)*4, +4), i < NV, of a d-vector.  d % 4 == 0 (every row 16-byte aligned): one 128-bit
+// load per slot; otherwise (BigGAN-256's dim_z = 119, models/BigGAN/BigGAN.py:103-108) four guarded scalar loads, zeros
+// beyond d.  Shared-memory rows are padded to dp = round_up(d, 4) so the float4 staging below stays aligned either way.
 template <int NV>
 __device__ __forceinline__ void load_vec(const float* __restrict__ p, int d, int lane, LaneVec<NV>& r) {
+    if ((d & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int e = (i * 32 + lane) * 4;
-        r.v[i] = (e < d) ? __ldg(reinterpret_cast<const float4*>(p + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < NV; ++i) {
+            const int e = (i * 32 + lane) * 4;
+            r.v[i] = (e < d) ? __ldg(reinterpret_cast<const float4*>(p + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = (i * 32 + lane) * 4;
+            r.v[i].x = (e + 0 < d) ? __ldg(p + e + 0) : 0.f;
+            r.v[i].y = (e + 1 < d) ? __ldg(p + e + 1) : 0.f;
+            r.v[i].z = (e + 2 < d) ? __ldg(p + e + 2) : 0.f;
+            r.v[i].w = (e + 3 < d) ? __ldg(p + e + 3) : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ int pad4(int d) { return (d + 3) & ~3; }
+
+// store one lane slot to a global d-vector (vector store when rows are 16-byte aligned)
+__device__ __forceinline__ void store_slot(float* __restrict__ p, int d, int e, const float4& v) {
+    if ((d & 3) == 0) {
+        *reinterpret_cast<float4*>(p + e) = v;
+    } else {
+        if (e + 0 < d) p[e + 0] = v.x;
+        if (e + 1 < d) p[e + 1] = v.y;
+        if (e + 2 < d) p[e + 2] = v.z;
+        if (e + 3 < d) p[e + 3] = v.w;
     }
 }
 
@@ -59,17 +86,18 @@ __device__ __forceinline__ void rbf_accumulate(const float* __restrict__ set, co
 // thread's own float4 slots, `sm` is [RBF_WARPS][d] floats. Returns ||g||^2 via block_sum.
 template <int NV>
 __device__ __forceinline__ float rbf_reduce(LaneVec<NV>& acc, float* sm, float* red, int d, int warp, int lane) {
+    const int dp = pad4(d);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int e = (i * 32 + lane) * 4;
-        if (e < d) *reinterpret_cast<float4*>(sm + (size_t)warp * d + e) = acc.v[i];
+        if (e < d) *reinterpret_cast<float4*>(sm + (size_t)warp * dp + e) = acc.v[i];
     }
     __syncthreads();
     float nrm = 0.f;
     for (int e = threadIdx.x; e < d; e += RBF_THREADS) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < RBF_WARPS; ++w) t += sm[(size_t)w * d + e];
+        for (int w = 0; w < RBF_WARPS; ++w) t += sm[(size_t)w * dp + e];
         t *= -2.f;
         sm[e] = t;                      // row 0 of sm now holds g (each e is touched by exactly one thread)
         nrm += t * t;
@@ -128,7 +156,8 @@ rbf_backward_kernel(const float* __restrict__ support_sets, const float* __restr
     for (int e = threadIdx.x; e < d; e += RBF_THREADS) dot += sm[e] * inv_n * (m * __ldg(dout + (size_t)b * d + e));
     dot = block_sum(dot, red);
     // dg into sm row 1 (sm has RBF_WARPS >= 2 rows)
-    float* dg_s = sm + d;
+    const int dp = pad4(d);
+    float* dg_s = sm + dp;
     for (int e = threadIdx.x; e < d; e += RBF_THREADS)
         dg_s[e] = (m * __ldg(dout + (size_t)b * d + e) - sm[e] * inv_n * dot) * inv_n;
     __syncthreads();
@@ -136,7 +165,13 @@ rbf_backward_kernel(const float* __restrict__ support_sets, const float* __restr
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int e = (i * 32 + lane) * 4;
-        dg.v[i] = (e < d) ? *reinterpret_cast<const float4*>(dg_s + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dg.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < d) {                                    // (elements beyond d inside the last slot: D_j is 0 there)
+            dg.v[i] = *reinterpret_cast<const float4*>(dg_s + e);
+            if (e + 1 >= d) dg.v[i].y = 0.f;
+            if (e + 2 >= d) dg.v[i].z = 0.f;
+            if (e + 3 >= d) dg.v[i].w = 0.f;
+        }
         dzacc.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();                                   // sm is reused below for the dz reduction
@@ -168,7 +203,10 @@ rbf_backward_kernel(const float* __restrict__ support_sets, const float* __restr
             dzacc.v[i].x += g4.x; dzacc.v[i].y += g4.y; dzacc.v[i].z += g4.z; dzacc.v[i].w += g4.w;
             if (ds_row && e < d) {
                 float* p = ds_row + (size_t)j * d + e;     // rows may repeat inside a batch -> atomics
-                atomicAdd(p + 0, -g4.x); atomicAdd(p + 1, -g4.y); atomicAdd(p + 2, -g4.z); atomicAdd(p + 3, -g4.w);
+                atomicAdd(p + 0, -g4.x);
+                if (e + 1 < d) atomicAdd(p + 1, -g4.y);
+                if (e + 2 < d) atomicAdd(p + 2, -g4.z);
+                if (e + 3 < d) atomicAdd(p + 3, -g4.w);
             }
         }
         if (lane == 0) {
@@ -184,13 +222,13 @@ rbf_backward_kernel(const float* __restrict__ support_sets, const float* __restr
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int e = (i * 32 + lane) * 4;
-            if (e < d) *reinterpret_cast<float4*>(sm + (size_t)warp * d + e) = dzacc.v[i];
+            if (e < d) *reinterpret_cast<float4*>(sm + (size_t)warp * dp + e) = dzacc.v[i];
         }
         __syncthreads();
         for (int e = threadIdx.x; e < d; e += RBF_THREADS) {
             float t = 0.f;
 #pragma unroll
-            for (int w = 0; w < RBF_WARPS; ++w) t += sm[(size_t)w * d + e];
+            for (int w = 0; w < RBF_WARPS; ++w) t += sm[(size_t)w * dp + e];
             dz[(size_t)b * d + e] = t;
         }
     }
@@ -236,10 +274,13 @@ rbf_traverse_kernel(const float* __restrict__ support_sets, const float* __restr
                 if (e < d) {
                     float4 g4 = *reinterpret_cast<const float4*>(sm + e);
                     g4.x *= scale; g4.y *= scale; g4.z *= scale; g4.w *= scale;
+                    if (e + 1 >= d) g4.y = 0.f;              // keep the padding lanes of the code at zero
+                    if (e + 2 >= d) g4.z = 0.f;
+                    if (e + 3 >= d) g4.w = 0.f;
                     zv.v[i].x += g4.x; zv.v[i].y += g4.y; zv.v[i].z += g4.z; zv.v[i].w += g4.w;
                     if (warp == 0) {
-                        *reinterpret_cast<float4*>(shifts_c + (size_t)frame * d + e) = g4;
-                        *reinterpret_cast<float4*>(codes_c + (size_t)frame * d + e) = zv.v[i];
+                        store_slot(shifts_c + (size_t)frame * d, d, e, g4);
+                        store_slot(codes_c + (size_t)frame * d, d, e, zv.v[i]);
                     }
                 }
             }
@@ -266,9 +307,8 @@ extern "C" int wgs_rbf_warp_forward(const float* support_sets, const float* alph
                                     float fixed_gamma, const long long* idx, const float* z, const float* mag,
                                     float* out, int B, int K, int n_vec, int d, void* stream) {
     WGS_REQUIRE(B >= 0 && K > 0 && n_vec > 0 && d > 0, "rbf_warp_forward: bad sizes");
-    WGS_REQUIRE(d % 4 == 0, "rbf_warp_forward: latent dimension must be a multiple of 4");
     if (B == 0) return 0;
-    const size_t smem = (size_t)RBF_WARPS * d * sizeof(float);
+    const size_t smem = (size_t)RBF_WARPS * ((d + 3) & ~3) * sizeof(float);
     return dispatch_nv(d, [&](auto nv) -> int {
         constexpr int NV = decltype(nv)::value;
         rbf_forward_kernel<NV><<<B, RBF_THREADS, smem, (cudaStream_t)stream>>>(
@@ -284,9 +324,8 @@ extern "C" int wgs_rbf_warp_backward(const float* support_sets, const float* alp
                                      const float* dout, float* d_support_sets, float* d_loggamma, float* d_alphas,
                                      float* dz, int B, int K, int n_vec, int d, void* stream) {
     WGS_REQUIRE(B >= 0 && K > 0 && n_vec > 0 && d > 0, "rbf_warp_backward: bad sizes");
-    WGS_REQUIRE(d % 4 == 0, "rbf_warp_backward: latent dimension must be a multiple of 4");
     if (B == 0) return 0;
-    const size_t smem = (size_t)RBF_WARPS * d * sizeof(float);
+    const size_t smem = (size_t)RBF_WARPS * ((d + 3) & ~3) * sizeof(float);
     return dispatch_nv(d, [&](auto nv) -> int {
         constexpr int NV = decltype(nv)::value;
         rbf_backward_kernel<NV><<<B, RBF_THREADS, smem, (cudaStream_t)stream>>>(
@@ -302,9 +341,8 @@ extern "C" int wgs_rbf_traverse(const float* support_sets, const float* alphas, 
                                 float fixed_gamma, const long long* path, const float* start, float eps, int steps,
                                 float* codes, float* shifts, int chains, int K, int n_vec, int d, void* stream) {
     WGS_REQUIRE(chains >= 0 && K > 0 && n_vec > 0 && d > 0 && steps >= 0, "rbf_traverse: bad sizes");
-    WGS_REQUIRE(d % 4 == 0, "rbf_traverse: latent dimension must be a multiple of 4");
     if (chains == 0) return 0;
-    const size_t smem = (size_t)RBF_WARPS * d * sizeof(float);
+    const size_t smem = (size_t)RBF_WARPS * ((d + 3) & ~3) * sizeof(float);
     return dispatch_nv(d, [&](auto nv) -> int {
         constexpr int NV = decltype(nv)::value;
         rbf_traverse_kernel<NV><<<chains, RBF_THREADS, smem, (cudaStream_t)stream>>>(

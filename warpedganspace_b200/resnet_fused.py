@@ -54,8 +54,12 @@ def _bn_backward(dz, z, y, stats, gamma, relu, want_res):
 
 
 def _grad_target(w):
-    """The parameter's existing .grad (the trainer's flat, pre-zeroed buffer) when the wgrad kernel can accumulate into it."""
+    """The trainer's flat, pre-zeroed gradient buffer when the wgrad kernel may accumulate straight into it.  Opt-in:
+    only parameters re-homed by trainer.FlatParams carry `_wgs_flat_grad`; for everything else (a plain
+    `loss.backward()` + torch.optim loop, torch.autograd.grad, hooks, GradScaler) the gradient is returned to autograd."""
     g = w.grad
+    if not getattr(w, '_wgs_flat_grad', False):
+        return None
     return g if (g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.shape == w.shape) else None
 
 
@@ -153,7 +157,8 @@ class ResNetFeatures(torch.autograd.Function):
             dcur = dx
         xcol, y0, z0, st0, pool_idx, (n, ci, h, w) = tape['stem']
         dz0 = torch.empty_like(z0)
-        _lib.call('wgs_maxpool3s2_bwd', _lib.ptr(dcur.contiguous()), _lib.ptr(pool_idx), z0.shape[0], z0.shape[1], z0.shape[2],
+        dcur = dcur.contiguous()           # (held in a name: _lib.ptr() of a temporary would free it before the launch)
+        _lib.call('wgs_maxpool3s2_bwd', _lib.ptr(dcur), _lib.ptr(pool_idx), z0.shape[0], z0.shape[1], z0.shape[2],
                   z0.shape[3], _lib.ptr(dz0), _lib.stream())
         dy0s, _, dg0, db0 = _bn_backward(dz0, z0, y0, st0, net.bn1.weight, True, want_res=False)
         grads[net.bn1.weight], grads[net.bn1.bias] = dg0, db0

@@ -46,8 +46,9 @@ class _RBFWarp(torch.autograd.Function):
         d_g = torch.zeros_like(loggamma) if (need_g and ctx.learn_gammas) else None
         d_z = torch.empty_like(z) if need_z else None
         lg = loggamma.reshape(-1) if ctx.learn_gammas else None
+        dout = dout.contiguous()                    # (a named tensor: _lib.ptr() of a temporary would free it before the launch)
         _lib.call('wgs_rbf_warp_backward', _lib.ptr(support_sets), _lib.ptr(alphas), _lib.ptr(lg),
-                  ctx.fixed_gamma, _lib.ptr(idx), _lib.ptr(z), _lib.ptr(mag), _lib.ptr(dout.contiguous()),
+                  ctx.fixed_gamma, _lib.ptr(idx), _lib.ptr(z), _lib.ptr(mag), _lib.ptr(dout),
                   _lib.ptr(d_s), _lib.ptr(d_g), _lib.ptr(d_a), _lib.ptr(d_z), B, K, n_vec, d, _lib.stream())
         return d_s, d_a, d_g, d_z, None, None, None, None
 
@@ -94,17 +95,26 @@ class SupportSets(nn.Module):
         return self.warp(indices, z)
 
     @torch.no_grad()
-    def traverse(self, start, paths, eps, shift_steps):
+    def traverse(self, start, paths, eps, shift_steps, shift_leap=1):
         """All traversal chains of traverse_latent_space.py:369-438 in one launch.
 
         start [C, d] latent (or w) codes, paths [C] int64.  Returns (codes, shifts), each
-        [C, 2*shift_steps+1, d], most negative step first."""
+        [C, 2*(shift_steps // shift_leap)+1, d], most negative step first; with shift_leap > 1 only every
+        shift_leap-th step of each direction is kept (:404, :434), the walk itself still takes shift_steps steps."""
         C, d = start.shape
+        paths = paths.to(torch.int64).contiguous()
+        start = start.contiguous()
         codes = start.new_empty(C, 2 * shift_steps + 1, d)
         shifts = torch.empty_like(codes)
         lg = self.LOGGAMMA.reshape(-1) if self.learn_gammas else None
         _lib.call('wgs_rbf_traverse', _lib.ptr(self.SUPPORT_SETS), _lib.ptr(self.ALPHAS), _lib.ptr(lg),
-                  float(self.gamma), _lib.ptr(paths.to(torch.int64).contiguous()), _lib.ptr(start.contiguous()),
+                  float(self.gamma), _lib.ptr(paths), _lib.ptr(start),
                   float(eps), int(shift_steps), _lib.ptr(codes), _lib.ptr(shifts), C, self.num_support_sets,
                   2 * self.num_support_dipoles, d, _lib.stream())
+        if shift_leap > 1:
+            n = shift_steps // shift_leap
+            keep = [shift_steps - shift_leap * j for j in range(n, 0, -1)] + [shift_steps] + \
+                   [shift_steps + shift_leap * j for j in range(1, n + 1)]
+            keep = torch.tensor(keep, device=codes.device)
+            codes, shifts = codes.index_select(1, keep), shifts.index_select(1, keep)
         return codes, shifts

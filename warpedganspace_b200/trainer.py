@@ -45,6 +45,7 @@ class FlatParams:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.grad[off: off + p.numel()].view_as(p)
+                p._wgs_flat_grad = True          # resnet_fused may accumulate weight gradients straight into this view
                 off += sz
         self.step_count = 0
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)      # device-side step counter (graph replay)

@@ -14,7 +14,7 @@ from . import dist as wdist
 
 @torch.no_grad()
 def traverse_paths(G, S, z, paths=None, eps=0.15, shift_steps=16, batch_size=8, shift_in_w_space=None,
-                   return_images=True, on_frames=None):
+                   return_images=True, on_frames=None, shift_leap=1):
     """z [Z, dim_z]; paths: iterable of path indices (default: all).  Returns dict with
     ``codes`` [Z, K, 2*steps+1, d] (the reference's paths_latent_codes.pt per latent), ``shifts`` (same shape) and,
     when return_images, ``images`` [Z, K, 2*steps+1, C, H, W].  `on_frames(zi, ki, frames)` can consume frames
@@ -28,8 +28,8 @@ def traverse_paths(G, S, z, paths=None, eps=0.15, shift_steps=16, batch_size=8, 
     start = G.get_w(z) if shift_in_w_space else z                             # traverse_latent_space.py:370
     chains_start = start.repeat_interleave(P, dim=0).contiguous()             # chain c = (latent c // P, path c % P)
     chains_path = paths.repeat(Z).contiguous()
-    codes, shifts = S.traverse(chains_start, chains_path, eps, shift_steps)   # [Z*P, F, d]
-    F_ = 2 * shift_steps + 1
+    codes, shifts = S.traverse(chains_start, chains_path, eps, shift_steps, shift_leap)   # [Z*P, F, d]
+    F_ = codes.shape[1]                                                       # 2 * (shift_steps // shift_leap) + 1
     out = {'codes': codes.view(Z, P, F_, -1), 'shifts': shifts.view(Z, P, F_, -1)}
     if not (return_images or on_frames):
         return out
@@ -62,7 +62,7 @@ def shard_latents(z, rank=None, world=None):
 
 @torch.no_grad()
 def traverse_and_save(G, S, pool_dir, out_dir, eps=0.15, shift_steps=16, batch_size=8, paths=None, img_size=None,
-                      img_quality=95, shift_in_w_space=None):
+                      img_quality=95, shift_in_w_space=None, shift_leap=1):
     """The reference traversal script's output tree (traverse_latent_space.py:333-490) for every code of a latent pool:
 
         <out_dir>/<hash>/paths_images/path_<dim:03d>/<frame:06d>.jpg      2*shift_steps+1 frames, most negative first
@@ -82,7 +82,7 @@ def traverse_and_save(G, S, pool_dir, out_dir, eps=0.15, shift_steps=16, batch_s
         os.makedirs(osp.join(code_dir, 'paths_images'), exist_ok=True)
         res = traverse_paths(G, S, z[None].to(dev), paths=paths, eps=eps, shift_steps=shift_steps, batch_size=batch_size,
                              shift_in_w_space=shift_in_w_space, return_images=False,
-                             on_frames=None)
+                             on_frames=None, shift_leap=shift_leap)
         codes, shifts = res['codes'][0], res['shifts'][0]                      # [P, F, d]
         P, F_ = codes.shape[0], codes.shape[1]
         wspace = bool(getattr(G, 'shift_in_w_space', False)) if shift_in_w_space is None else shift_in_w_space
