@@ -27,6 +27,13 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_training_shards_must_be_equal_and_non_empty():
+    assert wdist.shard_range(32, 3, 8, require_equal=True) == (12, 16)
+    for n, world in ((6, 4), (3, 8), (0, 2)):
+        with pytest.raises(ValueError):
+            wdist.shard_range(n, 0, world, require_equal=True)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -133,7 +140,7 @@ def _trainer_worker(rank, world, port, root, out_dir):
     eng = _StubEngine()
     T._device = lambda: torch.device('cpu')
     T._make_engine = lambda g, s, r: eng
-    torch.manual_seed(11)                                         # every rank draws the FULL batch from the same seed
+    torch.manual_seed(11 + 100 * rank)                            # ranks need NOT share a seed: rank 0's draws are broadcast
     T.train(_M(), _M(), _M())
     torch.save(eng.seen, os.path.join(out_dir, 'seen_%d.pt' % rank))
     wdist.barrier()

@@ -27,8 +27,13 @@ def init_from_env(backend=None):
     return world, rank, local
 
 
-def shard_range(n, rank, world):
-    """Contiguous [lo, hi) slice of n latents owned by `rank` (sizes differ by at most one)."""
+def shard_range(n, rank, world, require_equal=False):
+    """Contiguous [lo, hi) slice of n latents owned by `rank` (sizes differ by at most one).  Training passes
+    require_equal=True: each rank's loss is the mean over its own shard and the gradients are summed and scaled by
+    1/world, which equals the reference's global batch mean (lib/trainer.py:245-249) only for equal, non-empty shards."""
+    if require_equal and (n % world != 0 or n < world):
+        raise ValueError('batch size %d does not split into %d equal non-empty shards: the mean of per-rank losses would '
+                         'not be the batch mean (pick a batch size that is a multiple of the number of ranks)' % (n, world))
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
@@ -39,6 +44,18 @@ def all_reduce_sum_(tensors, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in tensors:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return tensors
+
+
+def is_parallel(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def broadcast_(tensors, src=0, group=None):
+    """In-place broadcast of each tensor from rank `src` (no-op without a process group)."""
+    if is_parallel(group):
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
     return tensors
 
 

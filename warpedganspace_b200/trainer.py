@@ -95,6 +95,15 @@ class PairedTrainer:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Make every rank a replica of rank 0: S / R parameters and R's BatchNorm buffers are broadcast (the reference's
+        DataParallel re-broadcasts rank 0's modules on every forward, lib/trainer.py:164-165; only gradients are reduced
+        afterwards, so replicas that start apart never converge).  No-op on one rank."""
+        if self.world > 1:
+            with torch.no_grad():
+                wdist.broadcast_([self.flat_s.flat, self.flat_r.flat] + [b for b in self.R.buffers()], src=0, group=self.pg)
 
     def forward_backward(self, z, indices, magnitudes):
         """One forward + backward; gradients land in the flat buffers.  Returns a dict of device tensors."""
@@ -108,18 +117,44 @@ class PairedTrainer:
             with torch.no_grad():
                 img = self.G(z)
             img_shifted = self.G(z, shift)
-        logits, pred = self.R(img.detach(), img_shifted)                             # :242
+        # loss.backward() (:250) in two legs cut at the Reconstructor's input: after the first leg every gradient of R is
+        # final, so its all-reduce (45 MB) runs on a side stream underneath the generator's data-gradient pass (~3 ms);
+        # only the S gradients, final after the very last kernel, are reduced in the open (all_reduce_gradients).
+        x2 = img_shifted.detach().requires_grad_(True)
+        logits, pred = self.R(img.detach(), x2)                                      # :242
         cls = F.cross_entropy(logits, indices)                                       # :245
         reg = torch.mean(torch.abs(pred - magnitudes))                               # :246
         loss = self.lambda_cls * cls + self.lambda_reg * reg                         # :249
-        loss.backward()                                                              # :250
+        loss.backward()                                                              # R's leg of :250
+        self._start_r_reduce()
+        img_shifted.backward(x2.grad)                                                # G data-gradient + RBF leg
         acc = (logits.argmax(dim=1) == indices).float().mean()
         return dict(loss=loss.detach(), cls=cls.detach(), reg=reg.detach(), accuracy=acc, logits=logits.detach(),
                     pred=pred.detach(), shift=shift.detach(), img=img.detach(), img_shifted=img_shifted.detach())
 
+    _side = None
+    _r_reduce_pending = False
+
+    def _start_r_reduce(self):
+        """Sum R's flat gradient over ranks on a side stream (forked from / joined to the current stream with events, so
+        the same code is captured into the CUDA graph)."""
+        if self.world <= 1:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            wdist.all_reduce_sum_([self.flat_r.grad], group=self.pg)
+        self._r_reduce_pending = True
+
     def all_reduce_gradients(self):
+        """Two NCCL all-reduces per step: R's (started inside forward_backward, overlapped) and S's (here)."""
         if self.world > 1:
-            wdist.all_reduce_sum_([self.flat_s.grad, self.flat_r.grad], group=self.pg)
+            if not self._r_reduce_pending:                     # gradients produced outside forward_backward
+                self._start_r_reduce()
+            wdist.all_reduce_sum_([self.flat_s.grad], group=self.pg)
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._r_reduce_pending = False
 
     def optimizer_step(self):
         scale = 1.0 / self.world
@@ -345,22 +380,34 @@ class Trainer(object):
             print('#. This experiment has already been completed and can be found @ {}'.format(self.wip_dir))
             self._finish()
             sys.exit()
+        parallel = self.multi_gpu and self.world > 1
+        if parallel:
+            # one process per GPU under torchrun: the process group must exist BEFORE the engine is built (the engine reads
+            # its world size from it); a WORLD_SIZE > 1 environment without one would silently train N independent models
+            wdist.init_from_env()
+            if not wdist.is_parallel():
+                raise RuntimeError('multi_gpu=True with WORLD_SIZE=%d but torch.distributed could not be initialised' % self.world)
         engine = self._make_engine(generator, support_sets, reconstructor)
-        lo, hi = wdist.shard_range(p.batch_size, self.rank, self.world) if self.multi_gpu else (0, p.batch_size)
+        if parallel and getattr(engine, 'world', self.world) != self.world:
+            raise RuntimeError('engine spans %d rank(s) but the launcher started %d' % (engine.world, self.world))
+        lo, hi = wdist.shard_range(p.batch_size, self.rank, self.world, require_equal=True) if parallel else (0, p.batch_size)
         use_graph = bool(getattr(p, 'cuda_graph', False))
         window = []                                                                # device-side [acc, cls, reg, loss] rows
         t0 = time.time()
         for iteration in range(starting_iter, p.max_iter + 1):
             iter_t0 = time.time()
             z, indices, magnitudes = self.draw_batch(generator.dim_z)
-            batch = tuple(t[lo:hi].to(device, non_blocking=True) for t in (z, indices, magnitudes))
+            full = [t.to(device, non_blocking=True) for t in (z, indices, magnitudes)]
+            if parallel:                         # rank 0's host draws are THE draws (ranks need not share a seed)
+                wdist.broadcast_(full, src=0)
+            batch = tuple(t[lo:hi] for t in full)
             if use_graph and engine._graph is None and iteration == starting_iter:
                 engine.capture(*batch, preserve_state=True)
             out = engine.step(*batch)
             window.append(torch.stack([out['accuracy'], out['cls'], out['reg'], out['loss']]).clone())
             if iteration % p.log_freq == 0 or iteration % p.ckp_freq == 0 or iteration == p.max_iter:
                 rows = torch.stack(window)
-                if self.world > 1 and self.multi_gpu:                              # equal shards: mean of rank means
+                if parallel:                                                       # equal shards: mean of rank means
                     wdist.all_reduce_sum_([rows])
                     rows /= self.world
                 for acc, cls, reg, tot in rows.cpu().tolist():                     # the only device->host read
