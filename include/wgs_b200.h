@@ -69,6 +69,29 @@ int wgs_upfirdn2d(const float* in, const float* kernel, float* out, int major, i
                   int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
                   int pad_y1, void* stream);
 
+/* ---- ProgGAN glue ----------------------------------------------------------------------------------- *
+ * PixelNormLayer (models/ProgGAN/model.py:17-18) fused with the operand pack of the conv that follows it:
+ *   a [R, C] fp32 (NHWC rows) -> split32( a / sqrt(mean_c a^2 + eps) ) [R, ceil(C/32), 64] and / or fp32 [R, C].
+ * C % 4 == 0, C <= 512.                                                                              */
+int wgs_pixelnorm_pack(const float* a, long long R, int C, float eps, void* out_split, float* out_f32, void* stream);
+/* Backward of the above, fused with the LeakyReLU backward of the block that produced `a` (models/ProgGAN/model.py:48,62)
+ * and the pack of the next data-gradient conv's operand:  g = r (dxn - xn mean_c(dxn xn)),  xn = a r,
+ * r = rsqrt(mean_c a^2 + eps);  if lrelu_slope >= 0: g *= (a > 0 ? 1 : lrelu_slope).  Writes split32(g) and / or fp32 g. */
+int wgs_pixelnorm_bwd_pack(const float* dxn, const float* a, long long R, int C, float eps, float lrelu_slope,
+                           void* out_split, float* out_f32, void* stream);
+
+/* ---- BigGAN glue: class-conditional BatchNorm (eval) + ReLU + operand pack ------------------------------ *
+ * models/BigGAN/layers.py:303-322 (ccbn) and :395-405 (GBlock): with the generator frozen in eval mode, ccbn is the
+ * per-sample affine map o[n,p,c] = A[n,c] * x[n,p,c] + B[n,c] (A = gain/sqrt(var+eps), B = bias - mean*A, formed by the host).
+ * wgs_affine_act_pack: x [R, C] fp32 (R = groups * rows_per_group NHWC rows) -> [relu](A x + B) as split32 and / or fp32.
+ * A, B [groups, C] or both NULL (plain [relu +] pack).  The same kernel serves per-channel eval BatchNorm (groups = 1). */
+int wgs_affine_act_pack(const float* x, const float* A, const float* B, long long R, int C, long long rows_per_group,
+                        int relu, void* out_split, float* out_f32, void* stream);
+/* Backward: dpre = dz * [A x + B > 0]; dx = dpre * A written as split32 (operand of the next data-gradient conv) and / or
+ * fp32; dA[n,c] += sum_p dpre * x, dB[n,c] += sum_p dpre (atomics; zero them first; NULL to skip).                      */
+int wgs_affine_act_bwd(const float* dz, const float* x, const float* A, const float* B, int N, long long rows_per_group,
+                       int C, int relu, void* dx_split, float* dx_f32, float* dA, float* dB, void* stream);
+
 /* ---- tensor-core convolution -------------------------------------------------------------------- *
  * "split32" operand format: every 32 fp32 channels become one 128-byte row of 64 bf16 —
  * [hi(32) | lo(32)], x = hi + lo — so a tensor of C channels (padded to a multiple of 32) is
@@ -83,6 +106,26 @@ int wgs_pack_split32(const float* src, long long rows, int C, long long ld, cons
 
 /* Stacked weight layout for narrow layers (see wgs_conv_desc.w_layout): src fp32 [taps*cout, C] rows (stride ld). */
 int wgs_pack_weights_stacked(const float* src, int taps, int cout, int C, long long ld, void* dst, void* stream);
+
+/* Grouped weight pack: every conv weight of a network in one launch, gathered from the torch [Co, Ci, kh, kw] layout.
+ *   mode 0  forward taps          dst [kh*kw][Co][Ci]                 (tap = ky*kw + kx)
+ *   mode 1  transposed taps       dst [kh*kw][Ci][Co]                 (data gradient of a stride-1 conv; taps flipped by the tap list)
+ *   mode 2  im2col matrix         dst [1][Co][kh*kw*Ci], K = (ky, kx, c) (few-input-channel stem, wgs_im2col_split32)
+ *   mode 3  phase-merged dgrad    dst [S][G*Ci][Co], block (s, g) = tap idx[s*G+g] transposed, idx < 0 = zero block
+ *                                 (all stride^2 output phases of a strided data gradient stacked along N, wgs_conv_desc.group_size)
+ * layout 0 = rows [T][rows][chunks][hi32 | lo32], 1 = stacked [T][chunks][hi | lo][rows][32] (rows <= 64).
+ * h_problems is a HOST array (copied into the launch parameters).                                                     */
+#define WGS_PACK_GROUP_MAX 24
+typedef struct {
+    const float* src;
+    void* dst;
+    int co, ci, kh, kw;
+    int mode, layout, S, G;
+    signed char idx[64];
+} wgs_pack_problem;
+int wgs_pack_weights_group(const wgs_pack_problem* h_problems, int count, void* stream);
+int wgs_pack_problem_size(void);
+
 
 #define WGS_MAX_TAPS 64
 typedef struct wgs_conv_desc {
@@ -103,7 +146,7 @@ typedef struct wgs_conv_desc {
     int cout;
     const float* alpha;      /* [out_n, cout] per-sample per-channel scale (demodulation) or NULL */
     const float* beta;       /* [cout] bias or NULL */
-    int act;                 /* 0 none, 1 relu, 2 leaky relu 0.2, 3 sqrt(2)*leaky relu 0.2 (FusedLeakyReLU) */
+    int act;                 /* 0 none, 1 relu, 2 leaky relu 0.2, 3 sqrt(2)*leaky relu 0.2 (FusedLeakyReLU), 4 tanh */
     int accumulate;          /* add to the existing output instead of overwriting */
     int force_bn;            /* 0 = choose the channel tile automatically */
     const float* noise;      /* per-pixel noise plane indexed by OUTPUT pixel [y*noise_ld + x], or NULL  */
@@ -238,9 +281,14 @@ int wgs_im2col_split32(const float* x, int N, int H, int W, int C, int kh, int k
 /* ---- Reconstructor BatchNorm (train mode) fused with residual / ReLU / operand packing (csrc/bn.cu) -------------- *
  * Replaces cuDNN batch_norm fwd/bwd + ATen relu / add around every torchvision BasicBlock conv
  * (lib/reconstructor.py:54-69; train mode per lib/trainer.py:150).  Tensors are NHWC [R = N*H*W, C] fp32.         */
-int wgs_bn_stats(const float* y, long long R, int C, float* sum, float* sumsq, void* stream);   /* accumulates */
-int wgs_bn_finalize(const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
-                    float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+int wgs_bn_stats(const float* y, long long R, int C, float* sum, float* sumsq, void* stream);   /* accumulates sums of (y - y[0,c]) and (y - y[0,c])^2: shifted statistics, shift = first row */
+int wgs_bn_finalize(const float* sum, const float* sumsq, const float* shift, long long R, int C, float eps,
+                    float momentum, float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+/* bn_finalize folded into bn_act_fwd: mean / rstd are derived inside the apply kernel from the sums of wgs_bn_stats over the
+ * same y (block 0 writes them out for the backward pass and updates the running statistics).                         */
+int wgs_bn_fwd_fused(const float* y, const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
+                     const float* gamma, const float* beta, const float* residual, int relu, float* z, void* zs,
+                     float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
 int wgs_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                    const float* residual, int relu, float* z, void* zs, long long R, int C, void* stream);
 int wgs_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,

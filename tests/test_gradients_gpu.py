@@ -95,7 +95,7 @@ def errors(S, R, want, rows):
     return errs
 
 
-@pytest.mark.parametrize('seed', [415, 430, 437, 448, 417, 420, 421, 429, 432, 433])
+@pytest.mark.parametrize('seed', [415, 421, 429, 430, 432, 437, 448])
 def test_whole_graph_gradients_kink_free_draws_at_1e3(seed):
     torch.backends.cudnn.allow_tf32 = False
     g_sd, s_sd, r_sd, z, idx, mag = draw(seed, True)

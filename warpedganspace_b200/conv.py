@@ -108,6 +108,55 @@ def pack_weight_rows(wt):
     return out
 
 
+class PackProblem(ctypes.Structure):
+    """Mirror of wgs_pack_problem (include/wgs_b200.h)."""
+    _fields_ = [('src', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('co', ctypes.c_int), ('ci', ctypes.c_int),
+                ('kh', ctypes.c_int), ('kw', ctypes.c_int), ('mode', ctypes.c_int), ('layout', ctypes.c_int),
+                ('S', ctypes.c_int), ('G', ctypes.c_int), ('idx', ctypes.c_byte * 64)]
+
+
+PACK_FWD, PACK_TRANSPOSED, PACK_IM2COL, PACK_MERGED_DGRAD = 0, 1, 2, 3
+_pack_layout_checked = False
+
+
+def pack_weights_group(specs):
+    """Every weight pack of a network in one launch (wgs_pack_weights_group).  specs: list of (w [Co, Ci, kh, kw] fp32
+    contiguous CUDA tensor, mode, extra) with extra = (stride, padding) for PACK_MERGED_DGRAD, None otherwise.
+    Returns the packed tensors with nominal shape [T, rows, chunks, 64] (same as pack_weights / merged_phase_weights)."""
+    global _pack_layout_checked
+    lib = _lib.load()
+    if not _pack_layout_checked:
+        if lib.wgs_pack_problem_size() != ctypes.sizeof(PackProblem):
+            raise RuntimeError('wgs_pack_problem layout mismatch between header and ctypes mirror')
+        _pack_layout_checked = True
+    arr = (PackProblem * len(specs))()
+    outs = []
+    for q, (w, mode, extra) in zip(arr, specs):
+        if not (w.is_cuda and w.is_contiguous() and w.dtype == torch.float32):
+            raise RuntimeError('pack_weights_group needs contiguous fp32 CUDA weights (no CPU fallback)')
+        co, ci, kh, kw = w.shape
+        q.src, q.co, q.ci, q.kh, q.kw, q.mode = w.data_ptr(), co, ci, kh, kw, mode
+        if mode == PACK_FWD:
+            T, rows, K = kh * kw, co, ci
+        elif mode == PACK_TRANSPOSED:
+            T, rows, K = kh * kw, ci, co
+        elif mode == PACK_IM2COL:
+            T, rows, K = 1, co, kh * kw * ci
+        else:
+            stride, padding = extra
+            shifts, idx, G = _phase_plan('dgrad', kh, kw, stride, padding, w.device)
+            T, rows, K = len(shifts), G * ci, co
+            q.S, q.G = T, G
+            for i, t in enumerate(_phase_idx_host('dgrad', kh, kw, stride, padding)):
+                q.idx[i] = t
+        q.layout = 1 if rows <= STACK_MAX_COUT else 0
+        out = torch.empty(T, rows, chunks_of(K), 64, dtype=torch.bfloat16, device=w.device)
+        q.dst = out.data_ptr()
+        outs.append(out)
+    _lib.check(lib.wgs_pack_weights_group(arr, len(specs), _lib.stream()))
+    return outs
+
+
 def pack_weights(w):
     """w: fp32 [Co, Ci, kh, kw] (torch conv layout) -> bf16 [kh*kw, Co, ceil(Ci/32), 64]; tap = ky*kw+kx."""
     co, ci, kh, kw = w.shape
@@ -267,6 +316,27 @@ def _real_blocks(idx, T):
     hit = _REAL_BLOCKS.get(key)
     if hit is None:
         hit = _REAL_BLOCKS[key] = int((idx != T).sum())
+    return hit
+
+
+_PHASE_IDX_HOST = {}
+
+
+def _phase_idx_host(kind, kh, kw, stride, padding):
+    """The tap table of _phase_plan as a host list (-1 = zero block), for wgs_pack_problem.idx."""
+    key = (kind, kh, kw, stride, padding)
+    hit = _PHASE_IDX_HOST.get(key)
+    if hit is None:
+        s, T = stride, kh * kw
+        ent = {}
+        for py in range(s):
+            for px in range(s):
+                for ky in range(kh):
+                    for kx in range(kw):
+                        if (py + padding - ky) % s == 0 and (px + padding - kx) % s == 0:
+                            ent[((py + padding - ky) // s, (px + padding - kx) // s, py * s + px)] = ky * kw + kx
+        shifts = sorted({(a, b) for a, b, _ in ent})
+        hit = _PHASE_IDX_HOST[key] = [ent.get((sy, sx, g), -1) for sy, sx in shifts for g in range(s * s)]
     return hit
 
 

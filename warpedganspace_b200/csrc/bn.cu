@@ -27,7 +27,10 @@ __device__ __forceinline__ void bn_reduce2_to_global(const float a[4], const flo
     }
 }
 
-// sum[c] += sum_r y[r,c];  sumsq[c] += sum_r (y[r,c] - shift[c])^2-free form: plain sum of squares (fp32; |mean| ~ std here)
+// SHIFTED single-pass statistics: sum[c] += sum_r (y[r,c] - s_c), sumsq[c] += sum_r (y[r,c] - s_c)^2 with the shift
+// s_c = y[0, c] (the channel's first sample, so |mean - s_c| ~ std): var = E[(y-s)^2] - E[y-s]^2 then loses O(1) digits to
+// cancellation instead of O(mean^2 / var) - a large-mean channel (|mean| >> std, e.g. after a bias) would otherwise lose
+// all of its fp32 variance digits (cuDNN / ATen use Welford for the same reason).
 __global__ void __launch_bounds__(BN_THREADS)
 bn_stats_kernel(const float* __restrict__ y, long long R, int C, float* __restrict__ sum, float* __restrict__ sumsq) {
     extern __shared__ float sm[];
@@ -36,8 +39,10 @@ bn_stats_kernel(const float* __restrict__ y, long long R, int C, float* __restri
     const long long per = (R + gridDim.x - 1) / gridDim.x;
     const long long r0 = blockIdx.x * per, r1 = min(R, r0 + per);
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(y + q * 4));            // row 0
     for (long long r = r0 + pl; r < r1; r += PL) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + q * 4));
+        float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + q * 4));
+        v.x -= sh.x; v.y -= sh.y; v.z -= sh.z; v.w -= sh.w;
         a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
         b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
     }
@@ -45,16 +50,27 @@ bn_stats_kernel(const float* __restrict__ y, long long R, int C, float* __restri
 }
 
 // mean / rstd from the sums, running-stat update (momentum, unbiased variance), one thread per channel
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long R, int C,
-                                   float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+__device__ __forceinline__ void bn_moments(float sum, float sumsq, float shift, long long R, float eps, float& mean, float& rstd,
+                                           double& var_out) {
+    const double ms = (double)sum / (double)R;                    // mean of (y - shift)
+    double var = (double)sumsq / (double)R - ms * ms;
+    if (var < 0.0) var = 0.0;
+    mean = (float)(ms + (double)shift);
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+    var_out = var;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ shift,
+                                   long long R, int C, float eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double m = (double)sum[c] / (double)R;
-    double var = (double)sumsq[c] / (double)R - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[c] = (float)m;
-    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    double var;
+    float mf, rf;
+    bn_moments(sum[c], sumsq[c], shift ? shift[c] : 0.f, R, eps, mf, rf, var);
+    const double m = (double)mf;
+    mean[c] = mf;
+    rstd[c] = rf;
     if (running_mean) {
         const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
@@ -63,24 +79,56 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 }
 
 // z = [relu]( gamma * (y - mean) * rstd + beta [+ residual] );  writes z (fp32, optional) and split32(z) (optional)
+// FINALIZE = true: mean / rstd are derived here from the shifted sums of bn_stats (every thread owns one channel quad for
+// its whole grid-stride loop: C/4 divides the stride), block 0 publishes them for the backward pass and updates the
+// running statistics - the separate one-thread-per-channel finalize launch between bn_stats and this kernel is gone.
+template <bool FINALIZE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
-                  int relu, float* __restrict__ z, __nv_bfloat16* __restrict__ zs, long long R, int C) {
+                  int relu, float* __restrict__ z, __nv_bfloat16* __restrict__ zs, long long R, int C,
+                  const float* __restrict__ sum, const float* __restrict__ sumsq, float eps, float momentum,
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ running_mean,
+                  float* __restrict__ running_var) {
     const int C4 = C >> 2;
     const long long total = R * C4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(i % C4);
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int q = (int)(i0 % C4), c = q * 4;                       // fixed per thread (host guarantees stride % C4 == 0)
+    float4 m4, s4;
+    if (FINALIZE) {
+        const float4 su = __ldg(reinterpret_cast<const float4*>(sum + c)), sq = __ldg(reinterpret_cast<const float4*>(sumsq + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(y + c));
+        double v0, v1, v2, v3;
+        bn_moments(su.x, sq.x, sh.x, R, eps, m4.x, s4.x, v0);
+        bn_moments(su.y, sq.y, sh.y, R, eps, m4.y, s4.y, v1);
+        bn_moments(su.z, sq.z, sh.z, R, eps, m4.z, s4.z, v2);
+        bn_moments(su.w, sq.w, sh.w, R, eps, m4.w, s4.w, v3);
+        if (blockIdx.x == 0 && threadIdx.x < C4) {
+            *reinterpret_cast<float4*>(mean_out + c) = m4;
+            *reinterpret_cast<float4*>(rstd_out + c) = s4;
+            if (running_mean) {
+                const double ub = R > 1 ? (double)R / (double)(R - 1) : 1.0;
+                const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const double vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    running_mean[c + k] = (1.f - momentum) * running_mean[c + k] + momentum * mm[k];
+                    running_var[c + k] = (1.f - momentum) * running_var[c + k] + momentum * (float)(vv[k] * ub);
+                }
+            }
+        }
+    } else {
+        m4 = __ldg(reinterpret_cast<const float4*>(mean + c));
+        s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    }
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 k4 = make_float4(s4.x * g4.x, s4.y * g4.y, s4.z * g4.z, s4.w * g4.w);
+    for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / C4;
-        const int c = q * 4;
         const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
-        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c));
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
-        float o[4] = {(v.x - m4.x) * s4.x * g4.x + b4.x, (v.y - m4.y) * s4.y * g4.y + b4.y,
-                      (v.z - m4.z) * s4.z * g4.z + b4.z, (v.w - m4.w) * s4.w * g4.w + b4.w};
+        float o[4] = {(v.x - m4.x) * k4.x + b4.x, (v.y - m4.y) * k4.y + b4.y,
+                      (v.z - m4.z) * k4.z + b4.z, (v.w - m4.w) * k4.w + b4.w};
         if (residual) {
             const float4 e = __ldg(reinterpret_cast<const float4*>(residual + r * C + c));
             o[0] += e.x; o[1] += e.y; o[2] += e.z; o[3] += e.w;
@@ -193,10 +241,10 @@ extern "C" int wgs_bn_stats(const float* y, long long R, int C, float* sum, floa
     return 0;
 }
 
-extern "C" int wgs_bn_finalize(const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
-                               float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
+extern "C" int wgs_bn_finalize(const float* sum, const float* sumsq, const float* shift, long long R, int C, float eps,
+                               float momentum, float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
     WGS_REQUIRE(C > 0 && R > 0, "bn_finalize: bad sizes");
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, R, C, eps, momentum, mean, rstd,
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, shift, R, C, eps, momentum, mean, rstd,
                                                                          running_mean, running_var);
     count_launch();
     WGS_LAUNCH_CHECK();
@@ -205,9 +253,23 @@ extern "C" int wgs_bn_finalize(const float* sum, const float* sumsq, long long R
 
 extern "C" int wgs_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                               const float* residual, int relu, float* z, void* zs, long long R, int C, void* stream) {
-    WGS_REQUIRE(C % 4 == 0 && R > 0, "bn_act_fwd: C must be a multiple of 4");
-    bn_act_fwd_kernel<<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
-        y, mean, rstd, gamma, beta, residual, relu, z, (__nv_bfloat16*)zs, R, C);
+    WGS_REQUIRE(bn_ok(C) && R > 0, "bn_act_fwd: C must be a multiple of 4 with C/4 dividing 256");
+    bn_act_fwd_kernel<false><<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        y, mean, rstd, gamma, beta, residual, relu, z, (__nv_bfloat16*)zs, R, C, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr,
+        nullptr, nullptr);
+    count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_bn_fwd_fused(const float* y, const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
+                                const float* gamma, const float* beta, const float* residual, int relu, float* z, void* zs,
+                                float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
+    WGS_REQUIRE(bn_ok(C) && R > 0, "bn_fwd_fused: C must be a multiple of 4 with C/4 dividing 256");
+    WGS_REQUIRE(sum && sumsq && mean && rstd, "bn_fwd_fused: sums in, mean / rstd out are required");
+    bn_act_fwd_kernel<true><<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        y, nullptr, nullptr, gamma, beta, residual, relu, z, (__nv_bfloat16*)zs, R, C, sum, sumsq, eps, momentum, mean, rstd,
+        running_mean, running_var);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

@@ -69,6 +69,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 1) return v > 0.f ? v : 0.f;
     if (act == 2) return v > 0.f ? v : 0.2f * v;
     if (act == 3) return 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);      // FusedLeakyReLU
+    if (act == 4) return tanhf(v);                                              // BigGAN / SNGAN output layer
     return v;
 }
 
@@ -224,6 +225,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
             } else if (p.act == 3) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 1.41421356237309515f * (v[i] > 0.f ? v[i] : 0.2f * v[i]);
+            } else if (p.act == 4) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
             }
         } else if (!g_uniform) {
             // phase-packed output whose groups are narrower than a 16-channel block (e.g. the 6-channel stem data

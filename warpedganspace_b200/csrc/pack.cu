@@ -181,3 +181,89 @@ extern "C" int wgs_im2col_split32(const float* x, int N, int H, int W, int C, in
     WGS_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Grouped weight pack: every conv weight of a network (forward taps, transposed taps for the data-gradient, the stem's
+// im2col matrix, phase-merged strided data-gradient blocks) in ONE launch, gathered straight from the torch [Co, Ci, kh, kw]
+// layout.  The Reconstructor's 20 convolutions needed 40 permute-copy + 40 pack launches per training step (its weights
+// change every step); with the problem table passed by value this is one launch per 24 weights.
+namespace wgs {
+
+struct PackGroup {
+    wgs_pack_problem p[WGS_PACK_GROUP_MAX];
+    int count;
+};
+
+__device__ __forceinline__ float pack_fetch(const wgs_pack_problem& q, int t, int row, int k, int K) {
+    if (k >= K) return 0.f;
+    const int T = q.kh * q.kw;
+    switch (q.mode) {
+        case 0: return __ldg(q.src + ((size_t)row * q.ci + k) * T + t);
+        case 1: return __ldg(q.src + ((size_t)k * q.ci + row) * T + t);
+        case 2: return __ldg(q.src + ((size_t)row * q.ci + k % q.ci) * T + k / q.ci);
+        default: {
+            const int g = row / q.ci, c = row - g * q.ci, tap = q.idx[t * q.G + g];
+            return tap < 0 ? 0.f : __ldg(q.src + ((size_t)k * q.ci + c) * T + tap);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pack_weights_group_kernel(const __grid_constant__ PackGroup grp) {
+    const wgs_pack_problem& q = grp.p[blockIdx.y];
+    int T, rows, K;
+    if (q.mode == 0) { T = q.kh * q.kw; rows = q.co; K = q.ci; }
+    else if (q.mode == 1) { T = q.kh * q.kw; rows = q.ci; K = q.co; }
+    else if (q.mode == 2) { T = 1; rows = q.co; K = q.kh * q.kw * q.ci; }
+    else { T = q.S; rows = q.G * q.ci; K = q.co; }
+    const int chunks = (K + 31) >> 5;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(q.dst);
+    const long long total = (long long)T * rows * chunks * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g4 = (int)(i & 7);
+        long long rc = i >> 3;
+        const int ch = (int)(rc % chunks); rc /= chunks;
+        const int row = (int)(rc % rows);
+        const int t = (int)(rc / rows);
+        const int k0 = ch * 32 + g4 * 4;
+        __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16(pack_fetch(q, t, row, k0 + j, K), hi[j], lo[j]);
+        __nv_bfloat16* d;
+        size_t lo_off;
+        if (q.layout == 1) {            // stacked [T][chunks][hi | lo][rows][32]
+            d = dst + ((((size_t)t * chunks + ch) * 2) * rows + row) * 32 + g4 * 4;
+            lo_off = (size_t)rows * 32;
+        } else {                        // rows [T][rows][chunks][hi32 | lo32]
+            d = dst + (((size_t)t * rows + row) * chunks + ch) * 64 + g4 * 4;
+            lo_off = 32;
+        }
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(d + lo_off) = *reinterpret_cast<const uint2*>(lo);
+    }
+}
+
+}  // namespace wgs
+
+extern "C" int wgs_pack_problem_size(void) { return (int)sizeof(wgs_pack_problem); }
+
+extern "C" int wgs_pack_weights_group(const wgs_pack_problem* h_problems, int count, void* stream) {
+    WGS_REQUIRE(h_problems != nullptr && count >= 1, "pack_weights_group: empty problem list");
+    for (int lo = 0; lo < count; lo += WGS_PACK_GROUP_MAX) {
+        wgs::PackGroup grp;
+        grp.count = std::min(WGS_PACK_GROUP_MAX, count - lo);
+        for (int i = 0; i < grp.count; ++i) {
+            const wgs_pack_problem& q = h_problems[lo + i];
+            WGS_REQUIRE(q.src && q.dst && q.co >= 1 && q.ci >= 1 && q.kh >= 1 && q.kw >= 1, "pack_weights_group: bad problem");
+            WGS_REQUIRE(q.mode >= 0 && q.mode <= 3 && (q.layout == 0 || q.layout == 1), "pack_weights_group: bad mode / layout");
+            WGS_REQUIRE(q.mode != 3 || (q.S >= 1 && q.G >= 1 && q.S * q.G <= 64), "pack_weights_group: phase table too large");
+            const int rows = q.mode == 0 || q.mode == 2 ? q.co : (q.mode == 1 ? q.ci : q.G * q.ci);
+            WGS_REQUIRE(q.layout == 0 || rows <= 64, "pack_weights_group: the stacked layout is for <= 64 rows");
+            grp.p[i] = q;
+        }
+        wgs::pack_weights_group_kernel<<<dim3(48, grp.count), 256, 0, (cudaStream_t)stream>>>(grp);
+        wgs::count_launch();
+        WGS_LAUNCH_CHECK();
+    }
+    return 0;
+}

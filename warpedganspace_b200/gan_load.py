@@ -82,8 +82,8 @@ class BigGANWrapper(nn.Module):
         self.dim_z = self.G.dim_z
 
     def mixed_classes(self, batch_size):
-        if len(self.target_classes.data.shape) == 0:
-            return self.target_classes.repeat(batch_size).cuda()
+        if self.target_classes.numel() == 1:         # one class: nothing to draw (stays on the device, CUDA-graph safe)
+            return self.target_classes.reshape(1).repeat(batch_size).cuda()
         return torch.from_numpy(np.random.choice(self.target_classes.cpu(), [batch_size])).cuda()
 
     def forward(self, z, shift=None):
@@ -115,6 +115,10 @@ class ProgGANWrapper(nn.Module):
     def forward(self, z, shift=None):
         x = z if shift is None else z + shift
         return self.G(x.reshape(x.size(0), x.size(1), 1, 1))
+
+    def forward_pair(self, z, shift):
+        """(G(z), G(z, shift)) in one batched pass (fast path of lib/trainer.py:200,239)."""
+        return self.G.synthesize_pair(z, z + shift)
 
 
 def build_proggan(pretrained_gan_weights):

@@ -4,9 +4,12 @@ State-dict keys equal the reference modules' (models/ProgGAN/model.py:65-95, mod
 models/BigGAN/BigGAN.py:54-243), so released checkpoints load with ``load_state_dict``.  The generators are
 frozen during WarpedGANSpace training: weights are folded once per ``plan()`` (ProgGAN WScale into the conv
 weights; BigGAN spectral norm W/sigma — the reference redoes a non-updating power iteration on every forward,
-models/BigGAN/layers.py:84-96; eval-mode BatchNorm into a per-channel affine) and only the data gradient is
-propagated.  Round-1 state: the convolutions (forward + data-gradient) are ours; the light glue between them
-(pixel norm, nearest upsample, ReLU/tanh, attention softmax/bmm) is still ATen and is the next fusion target.
+models/BigGAN/layers.py:84-96; eval-mode BatchNorm into an affine map) and only the data gradient is propagated.
+ProgGAN and BigGAN are hand-scheduled kernel chains: every convolution is a tensor-core launch with bias / activation in
+its epilogue, the glue between convolutions (pixel norm, class-conditional BatchNorm + ReLU, operand packing) is ONE
+element-wise pass per conv (csrc/proggan.cu, csrc/ccbn.cu), and nearest x2 + conv3x3 runs as four output-phase 2x2 convs
+over the low-resolution operand (2.25x fewer MACs).  Still library calls: BigGAN's attention matrix products / soft-max
+(2 % of its FLOPs) and the tiny linears; SNGAN (config 1, a plumbing config) keeps ATen glue around our convs.
 """
 import math
 
@@ -14,7 +17,9 @@ import torch
 from torch import nn
 import torch.nn.functional as F
 
+from . import _lib
 from . import _tree
+from . import conv as C
 from . import reconstructor as _rec
 from .reconstructor import conv2d
 
@@ -58,7 +63,18 @@ class _Frozen(nn.Module):
 
 
 class ProgGANGenerator(_Frozen):
-    """models/ProgGAN/model.py:65-95."""
+    """models/ProgGAN/model.py:65-95 as a hand-scheduled kernel chain (one autograd node, data-gradient only).
+
+    Per block (reference: pixel-norm (3 kernels) -> nearest x2 -> cuDNN conv -> x*scale + b -> leaky_relu, :42-62):
+      * `wgs_pixelnorm_pack`: previous activation -> pixel-norm -> split32 operand (one pass, csrc/proggan.cu);
+      * tensor-core conv whose epilogue adds the bias and applies LeakyReLU(0.2) (act = 2); WScale's scale is folded into
+        the frozen weights once;
+      * nearest x2 + 3x3 conv = four output-phase 2x2 convs over the LOW-resolution operand with pre-summed taps: output
+        row 2q+py reads up-sampled rows 2q+py-1 .. 2q+py+1 = source rows {q-1, q, q} (py = 0) or {q, q, q+1} (py = 1), so
+        the three taps collapse to two per axis (w0 | w1+w2, resp. w0+w1 | w2) - 16 MACs per low-res pixel instead of 36.
+    Backward: `wgs_pixelnorm_bwd_pack` (pixel-norm backward + LeakyReLU backward of the block below + operand pack) and
+    one data-gradient conv per block; for up-sampling blocks the adjoint of the four phase convs is ONE 4x4 / stride-2
+    conv over the high-resolution gradient."""
 
     def __init__(self, plan=None):
         super().__init__()
@@ -74,23 +90,181 @@ class ProgGANGenerator(_Frozen):
         _tree.add(self, 'output.wscale.b', torch.randn(3))
 
     def plan(self):
-        if self._plan is None:
-            t = _tree.tensors(self)
-            with torch.no_grad():
-                self._plan = {n: (t[n + '.conv.weight'] * t[n + '.wscale.scale']).detach().contiguous()
-                              for n in ['features.%d' % i for i in range(len(self.blocks))] + ['output']}
+        if self._plan is not None:
+            return self._plan
+        t = _tree.tensors(self)
+        if t['output.conv.weight'].device.type != 'cuda':
+            raise RuntimeError('ProgGANGenerator runs on CUDA only (no CPU fallback); call .cuda() first')
+        P = []
+        with torch.no_grad():
+            for i, (ci, co, k, pad, up) in enumerate(self.blocks):
+                n = 'features.%d' % i
+                w = (t[n + '.conv.weight'] * t[n + '.wscale.scale']).detach().float()            # [co, ci, k, k]
+                e = dict(ci=ci, co=co, k=k, pad=pad, up=up, bias=t[n + '.wscale.b'].detach().float().contiguous())
+                if up:
+                    assert k == 3 and pad == 1
+                    e['w_fwd'], e['taps'], e['w_bwd'] = up_conv_weights(w)
+                else:
+                    e['w_fwd'] = C.pack_weights(w)
+                    e['w_bwd'] = C.pack_weights(torch.flip(w, [2, 3]).permute(1, 0, 2, 3).contiguous())
+                P.append(e)
+            wo = (t['output.conv.weight'] * t['output.wscale.scale']).detach().float()             # [3, c, 1, 1]
+            self._plan = dict(blocks=P, w_out=C.pack_weights(wo), w_out_bwd=C.pack_weights(wo.permute(1, 0, 2, 3).contiguous()),
+                              b_out=t['output.wscale.b'].detach().float().contiguous(), c_out=wo.shape[1])
         return self._plan
+
+    def synthesize_pair(self, x_plain, x_shifted):
+        """Both images of a training pair in one batched pass: rows [x_plain; x_shifted], only the shifted rows are taped."""
+        b = x_plain.shape[0]
+        x_all = torch.cat([x_plain.detach().float(), x_shifted.float()], dim=0).contiguous()
+        img = _ProgGANFn.apply(self, x_all, b).permute(0, 3, 1, 2)
+        return img[:b], img[b:]
 
     def forward(self, x):
         self._require_cuda(x)
-        t, w = _tree.tensors(self), self.plan()
-        for i, (_, _, k, pad, up) in enumerate(self.blocks):
-            x = _pixel_norm(x)
-            if up:
-                x = F.interpolate(x, scale_factor=2, mode='nearest')
-            n = 'features.%d' % i
-            x = F.leaky_relu(conv2d(_cl(x), w[n], t[n + '.wscale.b'].detach(), 1, pad), 0.2)
-        return conv2d(_cl(_pixel_norm(x)), w['output'], t['output.wscale.b'].detach(), 1, 0)
+        return _ProgGANFn.apply(self, x.reshape(x.shape[0], -1).float().contiguous(), 0).permute(0, 3, 1, 2)
+
+
+def _pixelnorm_pack(a):
+    """fp32 NHWC [N, H, W, C] -> split32 operand of pixel_norm(a) (models/ProgGAN/model.py:17-18)."""
+    n, h, w, c = a.shape
+    out = torch.empty(n, h, w, C.chunks_of(c), 64, device=a.device, dtype=torch.bfloat16)
+    _lib.call('wgs_pixelnorm_pack', _lib.ptr(a), n * h * w, c, 1e-8, _lib.ptr(out), None, _lib.stream())
+    return out
+
+
+def _pixelnorm_bwd(dxn, a, slope, split):
+    """Backward of pixel_norm at input `a` (+ LeakyReLU backward of the block that produced `a` when slope >= 0)."""
+    n, h, w, c = a.shape
+    if split:
+        out = torch.empty(n, h, w, C.chunks_of(c), 64, device=a.device, dtype=torch.bfloat16)
+        _lib.call('wgs_pixelnorm_bwd_pack', _lib.ptr(dxn), _lib.ptr(a), n * h * w, c, 1e-8, float(slope), _lib.ptr(out), None,
+                  _lib.stream())
+    else:
+        out = torch.empty_like(a)
+        _lib.call('wgs_pixelnorm_bwd_pack', _lib.ptr(dxn), _lib.ptr(a), n * h * w, c, 1e-8, float(slope), None, _lib.ptr(out),
+                  _lib.stream())
+    return out
+
+
+def _proggan_forward(G, x, tape, grad_from):
+    """x [N, 512] -> image NHWC [N, H, W, 3]; tape (rows >= grad_from): the input activation of every block."""
+    P = G.plan()
+    n = x.shape[0]
+    a = x.view(n, 1, 1, -1)
+    acts = []
+    for e in P['blocks']:
+        a = a.contiguous()
+        acts.append(a[grad_from:])
+        xs = _pixelnorm_pack(a)
+        h, w = a.shape[1], a.shape[2]
+        if e['up']:
+            a = up_conv_forward(xs, e['w_fwd'], e['taps'], e['co'], e['ci'], beta=e['bias'], act=2)
+        else:
+            a = C.conv2d(xs, e['w_fwd'], e['k'], e['k'], padding=e['pad'], beta=e['bias'], act=2, cin=e['ci'])
+    acts.append(a[grad_from:])
+    img = C.conv2d(_pixelnorm_pack(a), P['w_out'], 1, 1, beta=P['b_out'], cin=P['c_out'])
+    if tape is not None:
+        tape['acts'] = acts
+    return img
+
+
+def _proggan_backward(G, tape, dimg):
+    """dimg NHWC [n, H, W, 3] -> d(loss)/dx [n, 512]."""
+    P = G.plan()
+    acts = tape['acts']
+    dxn = C.conv2d(C.pack_split32(dimg.contiguous()), P['w_out_bwd'], 1, 1, cout=P['c_out'], cin=3)
+    for i in range(len(P['blocks']) - 1, -1, -1):
+        e = P['blocks'][i]
+        gs = _pixelnorm_bwd(dxn, acts[i + 1], 0.2, split=True)      # gradient w.r.t. block i's pre-activation, packed
+        if e['up']:
+            dxn = C.conv2d(gs, e['w_bwd'], 4, 4, stride=2, padding=1, cout=e['ci'], cin=e['co'])
+        else:
+            dxn = C.conv2d(gs, e['w_bwd'], e['k'], e['k'], padding=e['k'] - 1 - e['pad'], cout=e['ci'], cin=e['co'])
+    return _pixelnorm_bwd(dxn, acts[0], -1.0, split=False).reshape(dxn.shape[0], -1)
+
+
+class _ProgGANFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, G, x_all, n_plain):
+        need = ctx.needs_input_grad[1]
+        tape = {} if need else None
+        img = _proggan_forward(G, x_all.detach(), tape, n_plain)
+        ctx.G, ctx.tape, ctx.n_plain, ctx.rows = G, tape, n_plain, x_all.shape[0]
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        if ctx.tape is None:
+            return None, None, None
+        dx = _proggan_backward(ctx.G, ctx.tape, dimg[ctx.n_plain:])
+        ctx.tape = None
+        if ctx.n_plain == 0:
+            return None, dx, None
+        full = dx.new_zeros(ctx.rows, dx.shape[1])
+        full[ctx.n_plain:] = dx
+        return None, full, None
+
+
+# ------------------------------------------------------------------------------------------------
+# nearest x2 up-sample folded into the following 3x3 conv: output phase p along one axis reads source rows
+# {q-1, q, q} (p = 0) or {q, q, q+1} (p = 1), so the three taps collapse to two: (offset, kernel rows summed)
+_UP_PHASE = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}
+_UP_INV = ((1, 1), (0, 1), (1, 0), (0, 0))        # adjoint 4x4 / stride-2 kernel row ky <-> (phase, collapsed tap)
+
+
+def up_conv_weights(w):
+    """w [co, ci, 3, 3] (fp32) of a conv applied AFTER a nearest x2 up-sample -> (forward pack [16, co, ci] for four
+    output-phase 2x2 convs over the low-resolution input, {phase: taps}, adjoint pack [16, ci, co] = ONE 4x4 / stride-2 /
+    pad-1 conv over the high-resolution gradient)."""
+    fw, taps = [], {}
+    for py in range(2):
+        for px in range(2):
+            taps[(py, px)] = []
+            for dy, kys in _UP_PHASE[py]:
+                for dx, kxs in _UP_PHASE[px]:
+                    taps[(py, px)].append((dy, dx, len(fw)))
+                    fw.append(w[:, :, list(kys)][:, :, :, list(kxs)].sum(dim=(2, 3)))                  # [co, ci]
+    bw = []
+    for ky in range(4):
+        for kx in range(4):
+            (py, a), (px, b) = _UP_INV[ky], _UP_INV[kx]
+            bw.append(fw[((py * 2 + px) * 2 + a) * 2 + b].t())                                          # [ci, co]
+    return C.pack_weight_rows(torch.stack(fw).contiguous()), taps, C.pack_weight_rows(torch.stack(bw).contiguous())
+
+
+def up_conv_forward(xs, w_fwd, taps, co, ci, out=None, **epilogue):
+    """conv3x3(nearest_x2(x)) from the low-resolution split32 operand xs [N, h, w, chunks, 64] -> fp32 [N, 2h, 2w, co]."""
+    n, h, w = xs.shape[0], xs.shape[1], xs.shape[2]
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, co, device=xs.device, dtype=torch.float32)
+    for (py, px), tp in taps.items():
+        C.conv_taps(xs, w_fwd, tp, out, grid=(h, w), out_origin=(py, px), out_step=(2, 2), cout=co, cin=ci, **epilogue)
+    return out
+
+
+def affine_act_pack(x, A=None, B=None, relu=True, split=True):
+    """[relu](A[n, c] * x + B[n, c]) of an fp32 NHWC tensor as the split32 operand of the next conv (csrc/ccbn.cu)."""
+    n, h, w, c = x.shape
+    shape = (n, h, w, C.chunks_of(c), 64) if split else x.shape
+    out = torch.empty(shape, device=x.device, dtype=torch.bfloat16 if split else torch.float32)
+    groups = A.shape[0] if A is not None else 1
+    _lib.call('wgs_affine_act_pack', _lib.ptr(x), _lib.ptr(A), _lib.ptr(B), n * h * w, c, (n * h * w) // groups, int(relu),
+              _lib.ptr(out) if split else None, None if split else _lib.ptr(out), _lib.stream())
+    return out
+
+
+def affine_act_bwd(dz, x, A, B, relu=True, split=True, want_sums=True):
+    """-> (dx [split32 or fp32], dA, dB) for o = [relu](A x + B); A, B [groups, C] (groups = N, or 1 for a per-channel map)."""
+    n, h, w, c = x.shape
+    groups = A.shape[0]
+    shape = (n, h, w, C.chunks_of(c), 64) if split else x.shape
+    dx = torch.empty(shape, device=x.device, dtype=torch.bfloat16 if split else torch.float32)
+    sums = torch.zeros(2, groups, c, device=x.device, dtype=torch.float32) if want_sums else None
+    _lib.call('wgs_affine_act_bwd', _lib.ptr(dz), _lib.ptr(x), _lib.ptr(A), _lib.ptr(B), groups, (n * h * w) // groups, c,
+              int(relu), _lib.ptr(dx) if split else None, None if split else _lib.ptr(dx),
+              _lib.ptr(sums[0]) if want_sums else None, _lib.ptr(sums[1]) if want_sums else None, _lib.stream())
+    return (dx, sums[0], sums[1]) if want_sums else (dx, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,34 +405,61 @@ class BigGANGenerator(_Frozen):
         sn('output_layer.2', (3, c, 3, 3))
 
     def plan(self):
-        """W / sigma for every spectrally-normalised layer (one power iteration off the stored u0, as the
-        reference's eval forward does every call)."""
-        if self._plan is None:
-            t = {k: v.detach() for k, v in _tree.tensors(self).items()}
-            out = {}
-            with torch.no_grad():
-                for k in t:
-                    if k.endswith('.u0'):
-                        p = k[:-3]
-                        w = t[p + '.weight']
-                        wm = w.reshape(w.shape[0], -1)
-                        v = F.normalize(t[k] @ wm, eps=self.SN_eps)
-                        u2 = F.normalize(v @ wm.t(), eps=self.SN_eps)
-                        out[p] = (w / torch.squeeze((v @ wm.t()) @ u2.t())).contiguous()
-            self._plan = out
+        """Frozen, kernel-ready state: W / sigma for every spectrally-normalised layer (one power iteration off the stored
+        u0, exactly what the reference's eval forward redoes on every call, models/BigGAN/layers.py:84-96), packed conv
+        weights (up-sampling convs as collapsed phase taps) and the eval-BatchNorm constants."""
+        if self._plan is not None:
+            return self._plan
+        t = {k: v.detach() for k, v in _tree.tensors(self).items()}
+        if t['shared.weight'].device.type != 'cuda':
+            raise RuntimeError('BigGANGenerator runs on CUDA only (no CPU fallback); call .cuda() first')
+        sn = {}
+        with torch.no_grad():
+            for k in t:
+                if k.endswith('.u0'):
+                    p = k[:-3]
+                    w = t[p + '.weight']
+                    wm = w.reshape(w.shape[0], -1)
+                    v = F.normalize(t[k] @ wm, eps=self.SN_eps)
+                    u2 = F.normalize(v @ wm.t(), eps=self.SN_eps)
+                    sn[p] = (w / torch.squeeze((v @ wm.t()) @ u2.t())).float().contiguous()
+            blocks = []
+            for i in range(len(self.arch['out'])):
+                p = 'blocks.%d.0' % i
+                ci, co = self.arch['in'][i], self.arch['out'][i]
+                e = dict(ci=ci, co=co)
+                e['w1'], e['taps1'], e['w1_bwd'] = up_conv_weights(sn[p + '.conv1'])
+                e['w2'] = C.pack_weights(sn[p + '.conv2'])
+                e['w2_bwd'] = C.pack_weights(torch.flip(sn[p + '.conv2'], [2, 3]).permute(1, 0, 2, 3).contiguous())
+                e['wsc'] = C.pack_weights(sn[p + '.conv_sc'])
+                e['wsc_bwd'] = C.pack_weights(sn[p + '.conv_sc'].permute(1, 0, 2, 3).contiguous())
+                for name in ('conv1', 'conv2', 'conv_sc'):
+                    e['b_' + name] = t['%s.%s.bias' % (p, name)].float().contiguous()
+                for bn in ('bn1', 'bn2'):
+                    inv = torch.rsqrt(t['%s.%s.stored_var' % (p, bn)] + self.BN_eps)
+                    e[bn] = (inv.float().contiguous(), (t['%s.%s.stored_mean' % (p, bn)] * inv).float().contiguous())
+                blocks.append(e)
+            p = 'output_layer.0'
+            a = t[p + '.gain'] * torch.rsqrt(t[p + '.stored_var'] + self.BN_eps)
+            wo = sn['output_layer.2']
+            out = dict(A=a.float().reshape(1, -1).contiguous(), B=(t[p + '.bias'] - t[p + '.stored_mean'] * a).float().reshape(1, -1).contiguous(),
+                       w=C.pack_weights(wo), w_bwd=C.pack_weights(torch.flip(wo, [2, 3]).permute(1, 0, 2, 3).contiguous()),
+                       bias=t['output_layer.2.bias'].float().contiguous(), ci=wo.shape[1])
+        self._plan = dict(sn=sn, blocks=blocks, out=out)
         return self._plan
 
-    def _ccbn(self, t, w, p, x, y):
-        gain = 1.0 + F.linear(y, w[p + '.gain'])
-        bias = F.linear(y, w[p + '.bias'])
-        inv = torch.rsqrt(t[p + '.stored_var'] + self.BN_eps)
-        xn = (x - t[p + '.stored_mean'].view(1, -1, 1, 1)) * inv.view(1, -1, 1, 1)
-        return xn * gain.view(x.shape[0], -1, 1, 1) + bias.view(x.shape[0], -1, 1, 1)
+    def _ccbn_affine(self, sn, e, p, bn, y):
+        """ccbn in eval mode as a per-sample affine map (layers.py:303-322): A = gain / sqrt(var + eps), B = bias - mean * A."""
+        inv, mean_inv = e[bn]
+        gain = 1.0 + F.linear(y, sn['%s.%s.gain' % (p, bn)])
+        return (gain * inv).contiguous(), (F.linear(y, sn['%s.%s.bias' % (p, bn)]) - gain * mean_inv).contiguous()
 
     def forward(self, z, y):
+        """-> logical NCHW image (channels-last memory).  models/BigGAN/BigGAN.py:222-243."""
         self._require_cuda(z)
-        t = {k: v.detach() for k, v in _tree.tensors(self).items()}
-        w = self.plan()
+        P = self.plan()
+        sn = P['sn']
+        t = _tree.tensors(self)
         nb = len(self.arch['out'])
         if self.hier:
             zs = torch.split(z, self.z_chunk_size, 1)
@@ -266,26 +467,93 @@ class BigGANGenerator(_Frozen):
             ys = [torch.cat([y, item], 1) for item in zs[1:]]
         else:
             ys = [y] * nb
-        h = F.linear(z, w['linear'], t['linear.bias']).view(z.shape[0], -1, self.bottom_width, self.bottom_width)
-        for i in range(nb):
+        h = F.linear(z, sn['linear'], t['linear.bias'].detach()).view(z.shape[0], -1, self.bottom_width, self.bottom_width)
+        h = h.permute(0, 2, 3, 1).contiguous()                                  # NHWC from here on
+        for i, e in enumerate(P['blocks']):
             p = 'blocks.%d.0' % i
-            x = h
-            h = F.interpolate(F.relu(self._ccbn(t, w, p + '.bn1', x, ys[i])), scale_factor=2)
-            x = F.interpolate(x, scale_factor=2)
-            h = conv2d(_cl(h), w[p + '.conv1'], t[p + '.conv1.bias'], 1, 1)
-            h = conv2d(_cl(F.relu(self._ccbn(t, w, p + '.bn2', h, ys[i]))), w[p + '.conv2'], t[p + '.conv2.bias'], 1, 1)
-            h = h + conv2d(_cl(x), w[p + '.conv_sc'], t[p + '.conv_sc.bias'], 1, 0)
+            A1, B1 = self._ccbn_affine(sn, e, p, 'bn1', ys[i])
+            A2, B2 = self._ccbn_affine(sn, e, p, 'bn2', ys[i])
+            h = _GBlockFn.apply(h, A1, B1, A2, B2, e)
             if self.arch['attn'][i]:
-                q = 'blocks.%d.1' % i
-                b, c, hh, ww = h.shape
-                hc = _cl(h)
-                theta = conv2d(hc, w[q + '.theta'], None, 1, 0).reshape(b, c // 8, hh * ww)
-                phi = F.max_pool2d(conv2d(hc, w[q + '.phi'], None, 1, 0), [2, 2]).reshape(b, c // 8, hh * ww // 4)
-                g = F.max_pool2d(conv2d(hc, w[q + '.g'], None, 1, 0), [2, 2]).reshape(b, c // 2, hh * ww // 4)
-                beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)
-                o = torch.bmm(g, beta.transpose(1, 2)).view(b, c // 2, hh, ww)
-                h = t[q + '.gamma'] * conv2d(_cl(o), w[q + '.o'], None, 1, 0) + h
-        p = 'output_layer.0'
-        inv = t[p + '.gain'] * torch.rsqrt(t[p + '.stored_var'] + self.BN_eps)
-        h = F.relu((h - t[p + '.stored_mean'].view(1, -1, 1, 1)) * inv.view(1, -1, 1, 1) + t[p + '.bias'].view(1, -1, 1, 1))
-        return torch.tanh(conv2d(_cl(h), w['output_layer.2'], t['output_layer.2.bias'], 1, 1))
+                h = self._attention(sn, t, 'blocks.%d.1' % i, h)
+        return _OutputFn.apply(h, P['out']).permute(0, 3, 1, 2)
+
+    def _attention(self, sn, t, q, h):
+        """layers.py:153-166.  The four 1x1 convs run on the tensor-core kernel; the two batched matrix products
+        (4096 x 24 x 1024 and 96 x 1024 x 4096 per sample, ~1 GFLOP = 2 % of the generator), soft-max and 2x2 max-pool are
+        library calls (cuBLAS bmm / ATen) under autograd."""
+        x = h.permute(0, 3, 1, 2)                                               # logical NCHW view of NHWC memory
+        b, c, hh, ww = x.shape
+        theta = conv2d(x, sn[q + '.theta'], None, 1, 0).reshape(b, c // 8, hh * ww)
+        phi = F.max_pool2d(conv2d(x, sn[q + '.phi'], None, 1, 0), [2, 2]).reshape(b, c // 8, hh * ww // 4)
+        g = F.max_pool2d(conv2d(x, sn[q + '.g'], None, 1, 0), [2, 2]).reshape(b, c // 2, hh * ww // 4)
+        beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)
+        o = torch.bmm(g, beta.transpose(1, 2)).view(b, c // 2, hh, ww)
+        out = t[q + '.gamma'].detach() * conv2d(_cl(o), sn[q + '.o'], None, 1, 0) + x
+        return out.permute(0, 2, 3, 1).contiguous()
+
+
+class _GBlockFn(torch.autograd.Function):
+    """GBlock (models/BigGAN/layers.py:395-405) as one hand-scheduled node over NHWC fp32 activations:
+        r1 = relu(A1 x + B1) -> conv1(up(r1)) + b1 = h1 -> r2 = relu(A2 h1 + B2) -> conv2(r2) + b2 + up(conv_sc(x) + b_sc)
+    six tensor-core launch groups + three element-wise passes instead of ~14 full-tensor ATen passes around cuDNN convs:
+      * ccbn + ReLU + operand pack is ONE pass (wgs_affine_act_pack), the up-sample never materialises (phase convs);
+      * the 1x1 shortcut is computed at LOW resolution (1x1 conv commutes with nearest up-sampling) and written straight
+        into the four output phases; conv2 accumulates on top of it in its epilogue.
+    Backward carries the data gradient and the per-sample dA / dB (which autograd takes on to z through the ccbn linears)."""
+
+    @staticmethod
+    def forward(ctx, x, A1, B1, A2, B2, e):
+        x = x.contiguous()
+        n, h, w, ci = x.shape
+        co = e['co']
+        r1s = affine_act_pack(x, A1.detach(), B1.detach(), relu=True)
+        xs = affine_act_pack(x, relu=False)
+        out = up_conv_forward(xs, e['wsc'], {(py, px): [(0, 0, 0)] for py in range(2) for px in range(2)}, co, ci,
+                              beta=e['b_conv_sc'])
+        h1 = up_conv_forward(r1s, e['w1'], e['taps1'], co, ci, beta=e['b_conv1'])
+        r2s = affine_act_pack(h1, A2.detach(), B2.detach(), relu=True)
+        C.conv2d(r2s, e['w2'], 3, 3, padding=1, out=out, accumulate=True, beta=e['b_conv2'], cin=co)
+        if any(ctx.needs_input_grad[:5]):
+            ctx.save_for_backward(x, h1, A1, B1, A2, B2)
+        ctx.e = e
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, h1, A1, B1, A2, B2 = ctx.saved_tensors
+        e = ctx.e
+        n, h, w, ci = x.shape
+        co = e['co']
+        ds = C.pack_split32(d_out.contiguous())
+        dr2 = C.conv2d(ds, e['w2_bwd'], 3, 3, padding=1, cout=co, cin=co)
+        dh1s, dA2, dB2 = affine_act_bwd(dr2, h1, A2.detach(), B2.detach(), relu=True, split=True)
+        dr1 = C.conv2d(dh1s, e['w1_bwd'], 4, 4, stride=2, padding=1, cout=ci, cin=co)                # adjoint of up + conv1
+        dx, dA1, dB1 = affine_act_bwd(dr1, x, A1.detach(), B1.detach(), relu=True, split=False)
+        # shortcut: adjoint of up(conv_sc(x)) = conv_sc^T of the 2x2 sum-pooled gradient = four stride-2 taps of the 1x1 weight
+        C.conv_taps(ds, e['wsc_bwd'], [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)], dx, grid=(h, w), in_stride=2, cout=ci,
+                    cin=co, accumulate=True)
+        return dx, dA1, dB1, dA2, dB2, None
+
+
+class _OutputFn(torch.autograd.Function):
+    """output_layer: eval BatchNorm -> ReLU -> SNConv 3x3 -> tanh (models/BigGAN/BigGAN.py:200-203,242-243): one affine
+    pack pass + one conv with bias and tanh in its epilogue."""
+
+    @staticmethod
+    def forward(ctx, h, o):
+        h = h.contiguous()
+        img = C.conv2d(affine_act_pack(h, o['A'], o['B'], relu=True), o['w'], 3, 3, padding=1, beta=o['bias'], act=4, cin=o['ci'])
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(h, img)
+        ctx.o = o
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        h, img = ctx.saved_tensors
+        o = ctx.o
+        g = (dimg * (1.0 - img * img)).contiguous()                             # tanh'
+        dr = C.conv2d(C.pack_split32(g), o['w_bwd'], 3, 3, padding=1, cout=o['ci'], cin=3)
+        dh, _, _ = affine_act_bwd(dr, h, o['A'], o['B'], relu=True, split=False, want_sums=False)
+        return dh, None

@@ -10,6 +10,7 @@ Every convolution (forward and data-gradient) runs on the tcgen05 tap-list kerne
 """
 import math
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -30,12 +31,14 @@ def _packed(w, transposed):
         return C.pack_weights(w.detach().permute(1, 0, 2, 3).contiguous() if transposed else w.detach())
     key = (w.data_ptr(), tuple(w.shape), w._version, transposed)
     hit = _FROZEN_PACKS.get(key)
+    if hit is not None and hit[0]() is not w:      # the address was freed and reused by ANOTHER tensor: stale entry
+        hit = None
     if hit is None:
         if len(_FROZEN_PACKS) > 512:
             _FROZEN_PACKS.clear()
-        hit = C.pack_weights(w.detach().permute(1, 0, 2, 3).contiguous() if transposed else w.detach())
+        hit = (weakref.ref(w), C.pack_weights(w.detach().permute(1, 0, 2, 3).contiguous() if transposed else w.detach()))
         _FROZEN_PACKS[key] = hit
-    return hit
+    return hit[1]
 
 
 class _ConvFn(torch.autograd.Function):
@@ -112,16 +115,18 @@ class _StemConvFn(torch.autograd.Function):
         return dx, dw, None, None
 
 
-def conv_dgrad(dys, w, in_hw, stride, padding, out=None, accumulate=False):
+def conv_dgrad(dys, w, in_hw, stride, padding, out=None, accumulate=False, packed=None):
     """Data gradient of F.conv2d: dx[iy,ix,ci] = sum_{ky,kx,co} dy[(iy+p-ky)/s, (ix+p-kx)/s, co] * w[co,ci,ky,kx]
-    (terms with non-integer quotients vanish).  stride 1: one flipped-tap conv; stride s: s*s output phases."""
+    (terms with non-integer quotients vanish).  stride 1: one flipped-tap conv; stride s: s*s output phases.
+    packed: the weight already packed for this call (transposed taps for stride 1, phase-merged blocks for stride > 1;
+    conv.pack_weights_group) - otherwise it is packed here."""
     co, ci, kh, kw = w.shape
     h, wd = in_hw
     n, oh, ow = dys.shape[0], dys.shape[1], dys.shape[2]
     if stride > 1 and MERGE_PHASES and stride * stride * ci <= 1024:
         # all stride*stride output phases in one launch (phase-packed output, conv.py)
-        return C.conv_dgrad_merged(dys, w, in_hw, stride, padding, out=out, accumulate=accumulate)
-    wt = _packed(w, True)                                                   # [kh*kw, Ci, Co]
+        return C.conv_dgrad_merged(dys, w, in_hw, stride, padding, out=out, accumulate=accumulate, w_merged=packed)
+    wt = packed if packed is not None else _packed(w, True)                 # [kh*kw, Ci, Co]
     dx = out if out is not None else torch.empty(n, h, wd, ci, device=dys.device, dtype=torch.float32)
     for py in range(stride):
         for px in range(stride):
