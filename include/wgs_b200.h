@@ -113,6 +113,9 @@ int wgs_pack_weights_stacked(const float* src, int taps, int cout, int C, long l
  *   mode 2  im2col matrix         dst [1][Co][kh*kw*Ci], K = (ky, kx, c) (few-input-channel stem, wgs_im2col_split32)
  *   mode 3  phase-merged dgrad    dst [S][G*Ci][Co], block (s, g) = tap idx[s*G+g] transposed, idx < 0 = zero block
  *                                 (all stride^2 output phases of a strided data gradient stacked along N, wgs_conv_desc.group_size)
+ *   mode 4  space-to-depth taps   dst [S*S][Co][4*Ci]: a stride-2 kh x kw conv as a stride-1 S x S conv over the 2x2
+ *                                 space-to-depth input (wgs_s2d_pack_split32): k = (py*2+px)*Ci + c, tap (ty, tx) holds kernel
+ *                                 element (2*ty + py - G, 2*tx + px - G) or zero; S = taps per axis, G = kernel offset
  * layout 0 = rows [T][rows][chunks][hi32 | lo32], 1 = stacked [T][chunks][hi | lo][rows][32] (rows <= 64).
  * h_problems is a HOST array (copied into the launch parameters).                                                     */
 #define WGS_PACK_GROUP_MAX 24
@@ -125,6 +128,10 @@ typedef struct {
 } wgs_pack_problem;
 int wgs_pack_weights_group(const wgs_pack_problem* h_problems, int count, void* stream);
 int wgs_pack_problem_size(void);
+/* 2x2 space-to-depth + split32 pack: x fp32 NHWC [N,H,W,C] (H, W even) -> [N, H/2, W/2, ceil(4C/32), 64], channel
+ * (py*2+px)*C + c = x[2Y+py, 2X+px, c] - the operand of a few-input-channel stride-2 conv run as a stride-1 conv
+ * (ResNet stem 7x7/2 on 6 channels, lib/reconstructor.py:56-60 -> 4x4 taps on 24 channels).                        */
+int wgs_s2d_pack_split32(const float* x, int N, int H, int W, int C, void* out, void* stream);
 
 
 #define WGS_MAX_TAPS 64
@@ -170,6 +177,11 @@ typedef struct wgs_conv_desc {
      * w_cout <= 64 only: hi*hi and hi*lo then come out of ONE N = 2*BN MMA (the A operand is fetched twice per
      * K slice instead of three times; narrow-N MMAs are bound by that fetch).                                   */
     int w_layout;
+    /* 1 = this launch may split its contraction over a thread-block cluster (tiny-M, deep-K layers: the Reconstructor's
+     * layer 3 / 4 convs).  The split factor depends on the number of output tiles, i.e. on the batch size, so callers that
+     * need results independent of how images are batched (the generator: G(z) inside a pair batch == G(z) alone, bit for
+     * bit) leave it 0.  WGS_CONV_SPLITK=1 / 0 in the environment forces it on / off for every launch.                  */
+    int split_k;
 } wgs_conv_desc;
 
 /* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls

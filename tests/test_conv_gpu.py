@@ -274,10 +274,13 @@ def _unsplit(xs):
     return (f[..., :32] + f[..., 32:]).flatten(-2)
 
 
-@pytest.mark.parametrize('N,Ci,H,W,Co', [(2, 32, 48, 136, 32), (1, 24, 20, 200, 24), (3, 32, 16, 128, 16)])
+@pytest.mark.parametrize('N,Ci,H,W,Co', [(2, 32, 48, 136, 32), (1, 24, 20, 200, 24), (3, 32, 16, 128, 16),
+                                         (2, 64, 48, 136, 64), (1, 40, 20, 200, 24), (1, 64, 16, 128, 32),      # two chunks
+                                         (1, 32, 32, 1040, 32)])                                                # 16 tiles per CTA
 def test_multi_tile_halo_kernel_plain_and_fused(N, Ci, H, W, Co):
-    """Single-chunk layers wide enough for the multi-tile halo kernel (resident tap weights, patch ring, two TMEM
-    accumulators; ragged last tile group, ragged rows): plain epilogue with demod / bias / noise / activation, and the
+    """Layers with <= 64 input / output channels wide enough for the multi-tile halo kernel (resident tap weights of one or
+    two 32-channel chunks, patch ring, two TMEM accumulators; ragged last tile group, ragged rows; 8 and - at >= 512 pixels
+    of width, the variant the 1024^2 layers run - 16 tiles per CTA): plain epilogue with demod / bias / noise / activation, and the
     fused epilogue (next layer's split32 operand, ToRGB accumulation, fp32 only for the back-propagated images)."""
     from warpedganspace_b200 import conv
     g = torch.Generator().manual_seed(N + H + W)

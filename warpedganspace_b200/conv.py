@@ -51,7 +51,7 @@ class ConvDesc(ctypes.Structure):
         ('out_split', ctypes.c_void_p), ('split_scale', ctypes.c_void_p), ('split_scale_ld', ctypes.c_longlong),
         ('out_from_n', ctypes.c_int), ('rgb_w', ctypes.c_void_p), ('rgb_out', ctypes.c_void_p),
         ('group_size', ctypes.c_int), ('group_w', ctypes.c_int), ('out_h', ctypes.c_int), ('out_w', ctypes.c_int),
-        ('w_layout', ctypes.c_int),
+        ('w_layout', ctypes.c_int), ('split_k', ctypes.c_int),
     ]
 
 
@@ -115,13 +115,14 @@ class PackProblem(ctypes.Structure):
                 ('S', ctypes.c_int), ('G', ctypes.c_int), ('idx', ctypes.c_byte * 64)]
 
 
-PACK_FWD, PACK_TRANSPOSED, PACK_IM2COL, PACK_MERGED_DGRAD = 0, 1, 2, 3
+PACK_FWD, PACK_TRANSPOSED, PACK_IM2COL, PACK_MERGED_DGRAD, PACK_S2D = 0, 1, 2, 3, 4
 _pack_layout_checked = False
 
 
 def pack_weights_group(specs):
     """Every weight pack of a network in one launch (wgs_pack_weights_group).  specs: list of (w [Co, Ci, kh, kw] fp32
-    contiguous CUDA tensor, mode, extra) with extra = (stride, padding) for PACK_MERGED_DGRAD, None otherwise.
+    contiguous CUDA tensor, mode, extra) with extra = (stride, padding) for PACK_MERGED_DGRAD, the padding for PACK_S2D
+    (see s2d_geometry), None otherwise.
     Returns the packed tensors with nominal shape [T, rows, chunks, 64] (same as pack_weights / merged_phase_weights)."""
     global _pack_layout_checked
     lib = _lib.load()
@@ -142,6 +143,11 @@ def pack_weights_group(specs):
             T, rows, K = kh * kw, ci, co
         elif mode == PACK_IM2COL:
             T, rows, K = 1, co, kh * kw * ci
+        elif mode == PACK_S2D:
+            S, a_min, G = s2d_geometry(kh, extra)
+            assert kh == kw
+            T, rows, K = S * S, co, 4 * ci
+            q.S, q.G = S, G
         else:
             stride, padding = extra
             shifts, idx, G = _phase_plan('dgrad', kh, kw, stride, padding, w.device)
@@ -157,6 +163,27 @@ def pack_weights_group(specs):
     return outs
 
 
+def s2d_geometry(k, padding):
+    """A stride-2 k-tap (per axis) conv with `padding` as a stride-1 conv over the 2x2 space-to-depth input: input index
+    2*o + ky - padding = 2*(o + a) + p with a = floor((ky - padding) / 2) in [a_min, a_max].
+    -> (taps per axis S, a_min, kernel offset G) with ky = 2*(a - a_min) + p - G."""
+    a_min, a_max = (-padding) // 2, (k - 1 - padding) // 2
+    return a_max - a_min + 1, a_min, -(padding + 2 * a_min)
+
+
+def s2d_pack_split32(x_nhwc):
+    """fp32 NHWC [N, H, W, C] (H, W even) -> split32 [N, H/2, W/2, ceil(4C/32), 64], channel (py*2+px)*C + c."""
+    n, h, w, c = x_nhwc.shape
+    out = torch.empty(n, h // 2, w // 2, chunks_of(4 * c), 64, dtype=torch.bfloat16, device=x_nhwc.device)
+    _lib.call('wgs_s2d_pack_split32', _lib.ptr(x_nhwc), n, h, w, c, _lib.ptr(out), _lib.stream())
+    return out
+
+
+def s2d_taps(k, padding):
+    S, a_min, _ = s2d_geometry(k, padding)
+    return [(ty + a_min, tx + a_min, ty * S + tx) for ty in range(S) for tx in range(S)], S
+
+
 def pack_weights(w):
     """w: fp32 [Co, Ci, kh, kw] (torch conv layout) -> bf16 [kh*kw, Co, ceil(Ci/32), 64]; tap = ky*kw+kx."""
     co, ci, kh, kw = w.shape
@@ -166,7 +193,7 @@ def pack_weights(w):
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
               alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None,
               out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None, groups=None,
-              algo_macs_per_pixel=None):
+              algo_macs_per_pixel=None, split_k=False):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -194,6 +221,7 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
             assert split_scale.stride(1) == 1
             d.split_scale, d.split_scale_ld = split_scale.data_ptr(), split_scale.stride(0)
     d.out_from_n = out_from_n
+    d.split_k = int(bool(split_k))
     if rgb_out is not None:
         assert rgb_w.is_contiguous() and rgb_out.is_contiguous()
         d.rgb_w, d.rgb_out = rgb_w.data_ptr(), rgb_out.data_ptr()

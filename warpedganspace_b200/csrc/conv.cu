@@ -644,7 +644,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 //   * a ring of input patches filled ahead by the TMA warp,
 //   * two TMEM accumulators, so the MMAs of tile i+1 overlap the epilogue of tile i.
 // Stacked weight layout only (two MMAs per K slice).  2 CTAs / SM.
-constexpr int MT_STAGES = 2;
+// Also serves TWO-chunk layers (33..64 input channels: the 64 -> 64 convs at 512^2 / 256^2 and their data-gradients): the
+// taps of both chunks stay resident (147 KB for 9 taps x 64 channels), the patch ring then holds (tile, chunk) units and one
+// CTA owns the SM - the per-tap kernel moved 432 KB of operands through L2 per 128-pixel tile, this one 46 KB.
+constexpr int MT_STAGES = 2;                                       // patch ring depth, single-chunk layers (runtime: p.stages)
+constexpr int MT_MAX_STAGES = 4;
 constexpr int MT_STG_BYTES = 8192;                                 // 4 epilogue warps x 2 KB store staging
 
 template <bool FUSED>
@@ -655,13 +659,14 @@ conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_slice = p.BN * 128;
-    const int w_bytes = p.num_taps * b_slice;                              // multiple of 1024 (BN >= 16 -> 2 KB slices)
+    const int n_ch = p.c_chunks, n_stages = p.stages;
+    const int w_bytes = n_ch * p.num_taps * b_slice;                       // multiple of 1024 (BN >= 16 -> 2 KB slices)
     uint8_t* smem_w = smem;
     uint8_t* smem_p = smem + w_bytes;
-    uint8_t* stg = smem_p + (size_t)MT_STAGES * p.a_stage_bytes;
+    uint8_t* stg = smem_p + (size_t)n_stages * p.a_stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + MT_STG_BYTES);
-    uint64_t* empty_bar = full_bar + MT_STAGES;
-    uint64_t* tfull_bar = empty_bar + MT_STAGES;                           // [2] accumulator ready
+    uint64_t* empty_bar = full_bar + n_stages;
+    uint64_t* tfull_bar = empty_bar + n_stages;                            // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;                                  // [2] accumulator drained
     uint64_t* w_bar = tempty_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
@@ -682,7 +687,7 @@ conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
-        for (int s = 0; s < MT_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < n_stages; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar + a, 1); ptx::mbar_init(tempty_bar + a, 4); }
         ptx::mbar_init(w_bar, 1);
         ptx::fence_mbar_init();
@@ -700,17 +705,21 @@ conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             ptx::mbar_expect_tx(w_bar, (uint32_t)w_bytes);
-            for (int tap = 0; tap < p.num_taps; ++tap)
-                ptx::tma_load_5d(smem_w + (size_t)tap * b_slice, &tmap_b, w_bar, 0, co0, 0, 0, (int)p.tap_w[tap]);
+            for (int ch = 0; ch < n_ch; ++ch)
+                for (int tap = 0; tap < p.num_taps; ++tap)
+                    ptx::tma_load_5d(smem_w + (size_t)(ch * p.num_taps + tap) * b_slice, &tmap_b, w_bar, 0, co0, 0, ch,
+                                     (int)p.tap_w[tap]);
             const uint32_t bytes = (uint32_t)(p.halo_h * p.halo_w * 128);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < n_tiles; ++i) {
-                ptx::mbar_wait(empty_bar + stage, phase ^ 1);
-                ptx::mbar_expect_tx(full_bar + stage, bytes);
-                ptx::tma_load_5d(smem_p + (size_t)stage * p.a_stage_bytes, &tmap_a, full_bar + stage, 0, 0,
-                                 (tx0 + i) * p.bw + p.dx0, oy0 + p.dy0, n0);
-                if (++stage == MT_STAGES) { stage = 0; phase ^= 1; }
+                for (int ch = 0; ch < n_ch; ++ch) {
+                    ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+                    ptx::mbar_expect_tx(full_bar + stage, bytes);
+                    ptx::tma_load_5d(smem_p + (size_t)stage * p.a_stage_bytes, &tmap_a, full_bar + stage, 0, ch,
+                                     (tx0 + i) * p.bw + p.dx0, oy0 + p.dy0, n0);
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -729,29 +738,32 @@ conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int acc = i & 1;
             const uint32_t use = (uint32_t)(i >> 1) & 1u;
             ptx::mbar_wait(tempty_bar + acc, use ^ 1);                     // the epilogue has drained this accumulator
-            ptx::mbar_wait(full_bar + stage, phase);
-            ptx::tc_fence_after();
-            const uint32_t a_lo = p_lo0 + (uint32_t)stage * st_step;
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
             uint32_t accum = 0;
-            for (int tap = 0; tap < p.num_taps; ++tap) {
-                const uint32_t da = a_lo + tap_off[tap];
-                const uint32_t db = w_lo0 + (uint32_t)tap * b_step;
+            for (int ch = 0; ch < n_ch; ++ch) {
+                ptx::mbar_wait(full_bar + stage, phase);
+                ptx::tc_fence_after();
+                const uint32_t a_lo = p_lo0 + (uint32_t)stage * st_step;
+                const uint32_t w_ch = w_lo0 + (uint32_t)(ch * p.num_taps) * b_step;
+                for (int tap = 0; tap < p.num_taps; ++tap) {
+                    const uint32_t da = a_lo + tap_off[tap];
+                    const uint32_t db = w_ch + (uint32_t)tap * b_step;
+                    if (ptx::elect_one()) {
+                        ptx::mma_f16_lh(d_tmem, da + 0, a_hi, db + 0, b_hi, idesc2, accum);   // a_hi x [b_hi; b_lo]
+                        ptx::mma_f16_lh(d_tmem, da + 2, a_hi, db + 2, b_hi, idesc2, 1u);
+                        ptx::mma_f16_lh(d_tmem, da + 4, a_hi, db + 0, b_hi, idesc, 1u);       // a_lo x b_hi
+                        ptx::mma_f16_lh(d_tmem, da + 6, a_hi, db + 2, b_hi, idesc, 1u);
+                    }
+                    __syncwarp();
+                    accum = 1u;
+                }
                 if (ptx::elect_one()) {
-                    ptx::mma_f16_lh(d_tmem, da + 0, a_hi, db + 0, b_hi, idesc2, accum);   // a_hi x [b_hi; b_lo]
-                    ptx::mma_f16_lh(d_tmem, da + 2, a_hi, db + 2, b_hi, idesc2, 1u);
-                    ptx::mma_f16_lh(d_tmem, da + 4, a_hi, db + 0, b_hi, idesc, 1u);       // a_lo x b_hi
-                    ptx::mma_f16_lh(d_tmem, da + 6, a_hi, db + 2, b_hi, idesc, 1u);
+                    ptx::mma_commit(empty_bar + stage);                    // patch slot free once these MMAs retire
+                    if (ch == n_ch - 1) ptx::mma_commit(tfull_bar + acc);  // accumulator complete
                 }
                 __syncwarp();
-                accum = 1u;
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
-            if (ptx::elect_one()) {
-                ptx::mma_commit(empty_bar + stage);                        // patch slot free once these MMAs retire
-                ptx::mma_commit(tfull_bar + acc);                          // accumulator complete
-            }
-            __syncwarp();
-            if (++stage == MT_STAGES) { stage = 0; phase ^= 1; }
         }
     } else {
         for (int i = 0; i < n_tiles; ++i) {
@@ -917,17 +929,18 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.coalesce = coalesce_mode;
     static int splitk_mode = -1;
     if (splitk_mode < 0) {
-        // 1 = on.  Off by default: measured gain on the training step is within noise (219.8 vs 217.3-220.2 pairs/s), and the
-        // split factor depends on the batch size, so G(z) inside a batch of 8 and alone would differ by fp32 re-association
-        // (5.7e-6) instead of being bit-identical (tests/test_step_gpu.py::test_full_size_properties)
+        // -1 = per launch (wgs_conv_desc.split_k), 1 / 0 = forced on / off.  The split factor depends on the batch size, so
+        // G(z) inside a batch of 8 and alone would differ by fp32 re-association (5.7e-6) instead of being bit-identical
+        // (tests/test_step_gpu.py::test_full_size_properties): the generator never asks for it, the Reconstructor does
         const char* e = getenv("WGS_CONV_SPLITK");
-        splitk_mode = (e && e[0] == '1') ? 1 : 0;
+        splitk_mode = e ? ((e[0] == '1') ? 1 : 0) : -1;
     }
+    const bool splitk_on = splitk_mode < 0 ? (d->split_k != 0) : (splitk_mode == 1);
     const bool stack = d->w_layout == 1;
     // Cluster split-K for tiny-M, deep-K launches: widest N tile (math-bound MMAs, one patch load per tile), then as many
     // K splits as fill about two CTAs per SM (<= 8: portable cluster size)
     p.ksplit = 1;
-    if (splitk_mode && !stack && d->force_bn == 0 && d->group_size == 0 && k_blocks_total(d) >= 16 &&
+    if (splitk_on && !stack && d->force_bn == 0 && d->group_size == 0 && k_blocks_total(d) >= 16 &&
         (BN <= 64 || m_tiles * ceil_div(d->cout, BN) * 2 <= num_sms())) {   // narrow-N tiles or under half a wave
         const int wide = std::min(256, (d->cout + 15) / 16 * 16);
         const int tiles = m_tiles * ceil_div(d->cout, wide);
@@ -1015,11 +1028,27 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             halo_wide = (e && e[0] == '1') ? 1 : 0;
         }
         const int h_limit = ((d->num_taps >= 12 || halo_wide) ? 108 : 72) * 1024;
-        while (hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > h_limit) hBN /= 2;
+        // long tap lists on a single chunk (the 4x4-tap space-to-depth stem, 16 x 8 KB of weights): the multi-tile kernel
+        // with ALL taps resident and the full N tile, one CTA per SM (the two TMEM accumulators still overlap MMAs and
+        // epilogue) beats halving N, which re-loads every patch twice and the weights once per tile
+        const bool big_mt = stack && d->c_chunks == 1 && d->force_bn == 0 && d->num_taps >= 12 &&
+                            ceil_div(d->grid_w, 8) >= 32 &&
+                            d->num_taps * hBN * 128 + MT_STAGES * a_bytes + MT_STG_BYTES <= 200 * 1024;
+        // two-chunk layers (64 -> 64 3x3 and data-gradients; the 16-shift stem data-gradient): both chunks' taps resident,
+        // ring of three (tile, chunk) patches, one CTA per SM
+        static int mt_env = -1;
+        if (mt_env < 0) {
+            const char* e = getenv("WGS_HALO_MT");                // 0 = multi-tile kernels off (A/B switch)
+            mt_env = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        const bool mt2 = mt_env && halo_mode && stack && d->c_chunks == 2 && d->force_bn == 0 && d->in_stride == 1 &&
+                         d->num_taps >= 4 && wy <= 7 && wx <= 7 && d->grid_h >= 16 && ceil_div(d->grid_w, 8) >= 16 &&
+                         2 * d->num_taps * hBN * 128 + 3 * a_bytes + MT_STG_BYTES + 4096 <= 227 * 1024;
+        while (!big_mt && !mt2 && hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > h_limit) hBN /= 2;
         const int h_stage = a_bytes + d->num_taps * hBN * 128;
         const bool eligible = halo_mode && p.ksplit == 1 && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
-                              d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && h_stage <= h_limit &&
-                              (d->c_chunks == 1 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4) ||
+                              d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && (h_stage <= h_limit || big_mt || mt2) &&
+                              (d->c_chunks == 1 || mt2 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4) ||
                                (halo_wide && d->c_chunks == 2 && d->cout <= 64 && d->num_taps >= 4));
         // (64 -> 64 3x3, two chunks x two channel tiles, measured faster on the per-tap kernel: 0.73 vs 0.89 ms)
         if (eligible) {
@@ -1055,13 +1084,17 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
             // measured on 32 -> 32 @1024^2 x 8 images: 16 tiles per CTA 0.641 ms, 8: 0.665, one-tile kernel: 0.925
             const int mt_tiles = mt_mode == -2 ? (p.tiles_x >= 64 ? 16 : 8) : mt_mode;
             const int hgrid_tiles = p.tiles_y * p.tiles_n * p.n_tiles_co;
-            if (mt_tiles > 1 && stack && d->c_chunks == 1 && hBN <= 32 && p.tiles_x >= 2 * mt_tiles &&
-                d->num_taps * hBN * 128 + MT_STAGES * a_bytes + MT_STG_BYTES <= 108 * 1024) {
-                p.tiles_per_cta = mt_tiles;
-                p.x_groups = ceil_div(p.tiles_x, mt_tiles);
+            const int mt_use = mt2 ? std::min(mt_tiles > 1 ? mt_tiles : 8, std::max(2, p.tiles_x / 2)) : mt_tiles;
+            if (mt_use > 1 && stack && p.tiles_x >= 2 * mt_use &&
+                (mt2 || (d->c_chunks == 1 &&
+                         ((hBN <= 32 && d->num_taps * hBN * 128 + MT_STAGES * a_bytes + MT_STG_BYTES <= 108 * 1024) || big_mt)))) {
+                p.tiles_per_cta = mt_use;
+                p.x_groups = ceil_div(p.tiles_x, mt_use);
+                p.stages = mt2 ? 3 : MT_STAGES;
                 p.tmem_cols = std::max(32, next_pow2(4 * hBN));          // two stacked accumulators
-                const size_t msmem = (size_t)d->num_taps * hBN * 128 + (size_t)MT_STAGES * a_bytes + MT_STG_BYTES + (2 * MT_STAGES + 5) * 8 + 32 +
-                                     WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
+                const size_t msmem = (size_t)d->c_chunks * d->num_taps * hBN * 128 + (size_t)p.stages * a_bytes + MT_STG_BYTES +
+                                     (2 * MT_MAX_STAGES + 5) * 8 + 32 + WGS_MAX_TAPS * 4 + 6 * hBN * 4 + 1024;
+                WGS_REQUIRE(msmem <= 227 * 1024, "conv(halo, multi-tile): shared memory budget exceeded");
                 static bool mattr = false;
                 if (!mattr) {
                     WGS_CUDA(cudaFuncSetAttribute(conv_halo_mt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));

@@ -201,9 +201,16 @@ __device__ __forceinline__ float pack_fetch(const wgs_pack_problem& q, int t, in
         case 0: return __ldg(q.src + ((size_t)row * q.ci + k) * T + t);
         case 1: return __ldg(q.src + ((size_t)k * q.ci + row) * T + t);
         case 2: return __ldg(q.src + ((size_t)row * q.ci + k % q.ci) * T + k / q.ci);
-        default: {
+        case 3: {
             const int g = row / q.ci, c = row - g * q.ci, tap = q.idx[t * q.G + g];
             return tap < 0 ? 0.f : __ldg(q.src + ((size_t)k * q.ci + c) * T + tap);
+        }
+        default: {      // 4: stride-2 conv as a stride-1 conv over the 2x2 space-to-depth input: k = (py*2 + px)*ci + c,
+                        // tap t = ty*S + tx covers kernel row ky = 2*ty + py - G (G = kernel offset), zero outside the kernel
+            const int ph = k / q.ci, c = k - ph * q.ci;
+            const int ky = 2 * (t / q.S) + (ph >> 1) - q.G, kx = 2 * (t % q.S) + (ph & 1) - q.G;
+            if (ky < 0 || ky >= q.kh || kx < 0 || kx >= q.kw) return 0.f;
+            return __ldg(q.src + ((size_t)row * q.ci + c) * T + ky * q.kw + kx);
         }
     }
 }
@@ -215,7 +222,8 @@ pack_weights_group_kernel(const __grid_constant__ PackGroup grp) {
     if (q.mode == 0) { T = q.kh * q.kw; rows = q.co; K = q.ci; }
     else if (q.mode == 1) { T = q.kh * q.kw; rows = q.ci; K = q.co; }
     else if (q.mode == 2) { T = 1; rows = q.co; K = q.kh * q.kw * q.ci; }
-    else { T = q.S; rows = q.G * q.ci; K = q.co; }
+    else if (q.mode == 3) { T = q.S; rows = q.G * q.ci; K = q.co; }
+    else { T = q.S * q.S; rows = q.co; K = 4 * q.ci; }
     const int chunks = (K + 31) >> 5;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(q.dst);
     const long long total = (long long)T * rows * chunks * 8;
@@ -255,9 +263,10 @@ extern "C" int wgs_pack_weights_group(const wgs_pack_problem* h_problems, int co
         for (int i = 0; i < grp.count; ++i) {
             const wgs_pack_problem& q = h_problems[lo + i];
             WGS_REQUIRE(q.src && q.dst && q.co >= 1 && q.ci >= 1 && q.kh >= 1 && q.kw >= 1, "pack_weights_group: bad problem");
-            WGS_REQUIRE(q.mode >= 0 && q.mode <= 3 && (q.layout == 0 || q.layout == 1), "pack_weights_group: bad mode / layout");
+            WGS_REQUIRE(q.mode >= 0 && q.mode <= 4 && (q.layout == 0 || q.layout == 1), "pack_weights_group: bad mode / layout");
+            WGS_REQUIRE(q.mode != 4 || (q.S >= 1 && q.S * q.S <= 64), "pack_weights_group: bad space-to-depth tap grid");
             WGS_REQUIRE(q.mode != 3 || (q.S >= 1 && q.G >= 1 && q.S * q.G <= 64), "pack_weights_group: phase table too large");
-            const int rows = q.mode == 0 || q.mode == 2 ? q.co : (q.mode == 1 ? q.ci : q.G * q.ci);
+            const int rows = (q.mode == 0 || q.mode == 2 || q.mode == 4) ? q.co : (q.mode == 1 ? q.ci : q.G * q.ci);
             WGS_REQUIRE(q.layout == 0 || rows <= 64, "pack_weights_group: the stacked layout is for <= 64 rows");
             grp.p[i] = q;
         }
@@ -265,5 +274,54 @@ extern "C" int wgs_pack_weights_group(const wgs_pack_problem* h_problems, int co
         wgs::count_launch();
         WGS_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// 2x2 space-to-depth + split32 pack for stride-2 convolutions with very few input channels (the Reconstructor's 7x7/2
+// stem on 6 channels, lib/reconstructor.py:56-60): x fp32 NHWC [N, H, W, C] -> split32 [N, H/2, W/2, ceil(4C/32), 64] with
+// channel k = (py*2 + px)*C + c holding x[2Y+py, 2X+px, c].  The stride-2 KxK conv becomes a stride-1 ceil(K/2+.5)^2-tap
+// conv over this tensor (weights: wgs_pack_weights_group mode 4), which runs on the multi-tile halo kernel with its taps
+// resident in shared memory - instead of an im2col that wrote 1280 B per output pixel (0.48 ms + a 0.25 ms GEMM at 1024^2).
+namespace wgs {
+__global__ void __launch_bounds__(256)
+s2d_pack_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out, int chunks) {
+    const int OH = H >> 1, OW = W >> 1, K = 4 * C;
+    const long long total = (long long)N * OH * OW * chunks * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g4 = (int)(i & 7);
+        long long r = i >> 3;
+        const int ch = (int)(r % chunks); r /= chunks;
+        const int X = (int)(r % OW); r /= OW;
+        const int Y = (int)(r % OH);
+        const int n = (int)(r / OH);
+        const int k0 = ch * 32 + g4 * 4;
+        __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            float v = 0.f;
+            if (k < K) {
+                const int ph = k / C, c = k - ph * C;
+                v = __ldg(x + (((long long)n * H + 2 * Y + (ph >> 1)) * W + 2 * X + (ph & 1)) * C + c);
+            }
+            split_bf16(v, hi[j], lo[j]);
+        }
+        __nv_bfloat16* d = out + ((((long long)n * OH + Y) * OW + X) * chunks + ch) * 64 + g4 * 4;
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(d + 32) = *reinterpret_cast<const uint2*>(lo);
+    }
+}
+}  // namespace wgs
+
+extern "C" int wgs_s2d_pack_split32(const float* x, int N, int H, int W, int C, void* out, void* stream) {
+    WGS_REQUIRE(N >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C >= 1, "s2d_pack: even H and W required");
+    const int chunks = (4 * C + 31) / 32;
+    const long long total = (long long)N * (H / 2) * (W / 2) * chunks * 8;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)wgs::num_sms() * 32);
+    wgs::s2d_pack_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, (__nv_bfloat16*)out, chunks);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
     return 0;
 }

@@ -115,7 +115,7 @@ class _StemConvFn(torch.autograd.Function):
         return dx, dw, None, None
 
 
-def conv_dgrad(dys, w, in_hw, stride, padding, out=None, accumulate=False, packed=None):
+def conv_dgrad(dys, w, in_hw, stride, padding, out=None, accumulate=False, packed=None, split_k=False):
     """Data gradient of F.conv2d: dx[iy,ix,ci] = sum_{ky,kx,co} dy[(iy+p-ky)/s, (ix+p-kx)/s, co] * w[co,ci,ky,kx]
     (terms with non-integer quotients vanish).  stride 1: one flipped-tap conv; stride s: s*s output phases.
     packed: the weight already packed for this call (transposed taps for stride 1, phase-merged blocks for stride > 1;
@@ -143,7 +143,7 @@ def conv_dgrad(dys, w, in_hw, stride, padding, out=None, accumulate=False, packe
             taps = [((py + padding - ky) // stride, (px + padding - kx) // stride, ky * kw + kx)
                     for ky in kys for kx in kxs]
             C.conv_taps(dys, wt, taps, dx, grid=(gh, gw), out_origin=(py, px), out_step=(stride, stride), cout=ci, cin=co,
-                        accumulate=accumulate)
+                        accumulate=accumulate, split_k=split_k)
     return dx
 
 

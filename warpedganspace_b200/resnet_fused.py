@@ -98,7 +98,7 @@ def _pack_all(net):
 
     def add(w, stride, padding, stem=False):
         wd = w.detach()
-        specs.append((wd, C.PACK_IM2COL if stem else C.PACK_FWD, None))
+        specs.append((wd, C.PACK_S2D, padding) if stem else (wd, C.PACK_FWD, None))
         keys.append((id(w), 'fwd'))
         specs.append((wd, C.PACK_MERGED_DGRAD, (stride, padding)) if stride > 1 else (wd, C.PACK_TRANSPOSED, None))
         keys.append((id(w), 'bwd'))
@@ -111,6 +111,26 @@ def _pack_all(net):
             if hasattr(b, 'downsample'):
                 add(b.downsample[0].weight, b.stride, 0)
     return dict(zip(keys, C.pack_weights_group(specs)))
+
+
+_S2D_INDEX = {}
+
+
+def _s2d_weight_grad(dws, ci, k, S, G):
+    """dws [co, 4*ci, S, S] (channel (py*2+px)*ci + c, tap (ty, tx) = kernel element (2*ty+py-G, 2*tx+px-G)) -> [co, ci, k, k]."""
+    key = (ci, k, S, G, str(dws.device))
+    idx = _S2D_INDEX.get(key)
+    if idx is None:
+        flat = []
+        for c in range(ci):
+            for ky in range(k):
+                for kx in range(k):
+                    py, ty = (ky + G) % 2, (ky + G) // 2
+                    px, tx = (kx + G) % 2, (kx + G) // 2
+                    flat.append((((py * 2 + px) * ci + c) * S + ty) * S + tx)
+        idx = _S2D_INDEX[key] = torch.tensor(flat, device=dws.device)
+    co = dws.shape[0]
+    return dws.reshape(co, -1).index_select(1, idx).reshape(co, ci, k, k)
 
 
 class ResNetFeatures(torch.autograd.Function):
@@ -140,16 +160,18 @@ class ResNetFeatures(torch.autograd.Function):
 
         def conv(xs, wt, stride, padding):
             co, cin, kh, kw = wt.shape
-            return C.conv2d(xs, packs[(id(wt), 'fwd')], kh, kw, stride=stride, padding=padding, cin=cin)
+            return C.conv2d(xs, packs[(id(wt), 'fwd')], kh, kw, stride=stride, padding=padding, cin=cin, split_k=True)
 
-        # stem: im2col -> 1-tap GEMM
+        # stem 7x7 / 2 on 6 channels: 2x2 space-to-depth (24 channels, one split32 chunk) -> stride-1 4x4-tap conv on the
+        # multi-tile halo kernel (taps resident in shared memory); no im2col (it wrote 1280 B per output pixel)
         w1 = net.conv1.weight
         co, _, kh, kw = w1.shape
         oh, ow = (h + 6 - kh) // 2 + 1, (w + 6 - kw) // 2 + 1
-        chunks = (kh * kw * ci + 31) // 32
-        xcol = torch.empty(n, oh, ow, chunks, 64, device=x.device, dtype=torch.bfloat16)
-        _lib.call('wgs_im2col_split32', _lib.ptr(x_nhwc), n, h, w, ci, kh, kw, 2, 3, oh, ow, _lib.ptr(xcol), _lib.stream())
-        y0 = C.conv2d(xcol, packs[(id(w1), 'fwd')], 1, 1, cin=kh * kw * ci)
+        xs2d = C.s2d_pack_split32(x_nhwc)
+        taps, S = C.s2d_taps(kh, 3)
+        y0 = torch.empty(n, oh, ow, co, device=x.device, dtype=torch.float32)
+        C.conv_taps(xs2d, packs[(id(w1), 'fwd')], taps, y0, grid=(oh, ow), cin=kh * kw * ci,
+                    algo_macs_per_pixel=kh * kw * ci * co)
         z0, _, st0 = _bn_forward(y0, net.bn1, None, True, False, pool)
         ph, pw = (oh + 1) // 2, (ow + 1) // 2
         cur = torch.empty(n, ph, pw, co, device=x.device, dtype=torch.float32)             # NHWC fp32
@@ -157,7 +179,7 @@ class ResNetFeatures(torch.autograd.Function):
         cur_s = torch.empty(n, ph, pw, C.chunks_of(co), 64, device=x.device, dtype=torch.bfloat16)
         _lib.call('wgs_maxpool3s2_fwd', _lib.ptr(z0), n, oh, ow, co, _lib.ptr(cur), _lib.ptr(pool_idx), _lib.ptr(cur_s),
                   _lib.stream())
-        tape['stem'] = (xcol, y0, z0, st0, pool_idx, (n, ci, h, w))
+        tape['stem'] = (xs2d, y0, z0, st0, pool_idx, (n, ci, h, w))
         tape['blocks'] = []
         for li in range(1, 5):
             for b in getattr(net, 'layer%d' % li):
@@ -195,7 +217,8 @@ class ResNetFeatures(torch.autograd.Function):
             grads[wt] = WG.conv_wgrad(xs, dys, tuple(wt.shape), stride, padding, out=_flat(wt))
 
         def dgrad(dys, wt, in_hw, stride, padding, out=None, accumulate=False):
-            return conv_dgrad(dys, wt, in_hw, stride, padding, out=out, accumulate=accumulate, packed=packs[(id(wt), 'bwd')])
+            return conv_dgrad(dys, wt, in_hw, stride, padding, out=out, accumulate=accumulate, packed=packs[(id(wt), 'bwd')],
+                              split_k=True)
 
         for (b, xs, x_shape, y1, z1, z1s, st1, y2, out, st2, yd, std) in reversed(tape['blocks']):
             s = b.stride
@@ -213,7 +236,7 @@ class ResNetFeatures(torch.autograd.Function):
             else:
                 dx = dgrad(dy1s, b.conv1.weight, (xh, xw), s, 1, out=dres, accumulate=True)     # dx = dres + conv^T(dy1)
             dcur = dx
-        xcol, y0, z0, st0, pool_idx, (n, ci, h, w) = tape['stem']
+        xs2d, y0, z0, st0, pool_idx, (n, ci, h, w) = tape['stem']
         dz0 = torch.empty_like(z0)
         dcur = dcur.contiguous()           # (held in a name: _lib.ptr() of a temporary would free it before the launch)
         _lib.call('wgs_maxpool3s2_bwd', _lib.ptr(dcur), _lib.ptr(pool_idx), z0.shape[0], z0.shape[1], z0.shape[2],
@@ -221,8 +244,10 @@ class ResNetFeatures(torch.autograd.Function):
         dy0s, _ = _bn_backward(dz0, z0, y0, st0, net.bn1, True, False, pool, grads)
         w1 = net.conv1.weight
         co, _, kh, kw = w1.shape
-        dwm = WG.conv_wgrad(xcol, dy0s, (co, kh * kw * ci, 1, 1), 1, 0)
-        grads[w1] = dwm.reshape(co, kh, kw, ci).permute(0, 3, 1, 2).contiguous()
+        # weight gradient in the space-to-depth form [co, 4*ci, S, S], gathered back to [co, ci, kh, kw]
+        S, a_min, G = C.s2d_geometry(kh, 3)
+        dws = WG.conv_wgrad(xs2d, dy0s, (co, 4 * ci, S, S), 1, -a_min)
+        grads[w1] = _s2d_weight_grad(dws, ci, kh, S, G)
         dx = dgrad(dy0s, w1, (h, w), 2, 3).permute(0, 3, 1, 2) if ctx.need_dx else None
         ctx.tape = None
         plist = ResNetFeatures.param_list(net)
