@@ -518,7 +518,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // (ty * halo_w + tx) 128-byte rows and whose stride-byte-offset is the patch row pitch: the eight pixels of one output
 // row are eight consecutive rows (one swizzle group), successive output rows are halo_w rows apart.  TMA and UMMA both
 // apply the 128B swizzle as a function of the absolute shared-memory address, so shifted views stay consistent
-// (descriptor base_offset = 0; measured, csrc/experimental/README.md).  One tile per CTA, 3 CTAs per SM.
+// (descriptor base_offset = 0; measured in round 1, profiles/r01_conv_halo_ncu.md).  One tile per CTA, 3 CTAs per SM.
 template <bool FUSED, bool STACK>
 __global__ void __launch_bounds__(CONV_THREADS, 3)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
