@@ -92,6 +92,15 @@ int wgs_affine_act_pack(const float* x, const float* A, const float* B, long lon
 int wgs_affine_act_bwd(const float* dz, const float* x, const float* A, const float* B, int N, long long rows_per_group,
                        int C, int relu, void* dx_split, float* dx_f32, float* dA, float* dB, void* stream);
 
+/* ---- output stage: GPU JPEG encode (nvJPEG, resolved with dlopen at first use) ------------------------- *
+ * Replaces the host-side PIL encode of traverse_latent_space.py:466-483 / sample_gan.py:172-176 (quality 95, optimised
+ * Huffman tables, progressive): pixels = uint8 [N, H, W, C] on the DEVICE (C = 3 interleaved RGB or 1 gray, the output of
+ * wgs_image_to_u8); image i's bitstream is written to the HOST buffer h_out + i * h_capacity_per_image and its length to
+ * h_sizes[i].  Synchronises the stream (the bitstream is returned to the host).  wgs_jpeg_available() = 1 when nvJPEG loads. */
+int wgs_jpeg_available(void);
+int wgs_jpeg_encode(const unsigned char* pixels, int N, int H, int W, int C, int quality, int progressive,
+                    unsigned char* h_out, long long h_capacity_per_image, long long* h_sizes, void* stream);
+
 /* ---- tensor-core convolution -------------------------------------------------------------------- *
  * "split32" operand format: every 32 fp32 channels become one 128-byte row of 64 bf16 —
  * [hi(32) | lo(32)], x = hi + lo — so a tensor of C channels (padded to a multiple of 32) is

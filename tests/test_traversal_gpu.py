@@ -102,3 +102,42 @@ def test_traverse_and_save_writes_the_reference_tree(tmp_path):
         assert torch.allclose(codes[:, 3], z.expand(4, -1), atol=1e-6)            # centre frame = the pool's code
         im = Image.open(root / 'paths_images' / 'path_000' / '000003.jpg')
         assert im.size == (32, 32) and im.mode == 'L'
+
+
+@pytest.mark.parametrize('shape', [(3, 256, 320, 3), (2, 64, 64, 1), (1, 1024, 1024, 3)])
+def test_nvjpeg_encode_decodes_to_the_frames(shape, tmp_path):
+    """Output stage on the GPU (traverse_latent_space.py:466-483 writes PIL JPEGs: quality 95, optimised, progressive): the
+    nvJPEG bitstreams must be valid JPEG files of the right size / mode, progressive, and decode to the source pixels as
+    closely as the reference's own PIL encode of the same pixels does."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from warpedganspace_b200.image_out import encode_jpegs, save_jpegs, nvjpeg_available
+    if not nvjpeg_available():
+        pytest.skip('nvJPEG is not installed on this box')
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(h + w)
+    # smooth synthetic frames (JPEG is built for those): low-frequency pattern + mild noise
+    yy, xx = torch.meshgrid(torch.linspace(0, 6.28, h), torch.linspace(0, 6.28, w), indexing='ij')
+    base = torch.stack([torch.sin(yy * (i + 1)) * torch.cos(xx * (c - i)) for i in range(c)], -1)
+    pix = ((base[None] * 0.4 + 0.5 + 0.02 * torch.randn(n, h, w, c, generator=g)).clamp(0, 1) * 255).to(torch.uint8)
+    streams = encode_jpegs(pix.cuda(), quality=95, progressive=True)
+    assert len(streams) == n
+    for i, data in enumerate(streams):
+        assert data[:2] == b'\xff\xd8' and data[-2:] == b'\xff\xd9'                 # SOI ... EOI
+        assert b'\xff\xc2' in data                                                      # SOF2: progressive DCT
+        im = Image.open(io.BytesIO(data))
+        assert im.size == (w, h) and im.mode == ('L' if c == 1 else 'RGB')
+        dec = np.asarray(im).reshape(h, w, c).astype(np.float64)
+        src = pix[i].numpy().astype(np.float64)
+        err_nv = np.sqrt(((dec - src) ** 2).mean())
+        ref = io.BytesIO()
+        Image.fromarray(pix[i].numpy()[:, :, 0] if c == 1 else pix[i].numpy()).save(ref, 'JPEG', quality=95, optimize=True,
+                                                                                    progressive=True)
+        dec_ref = np.asarray(Image.open(io.BytesIO(ref.getvalue()))).reshape(h, w, c).astype(np.float64)
+        err_pil = np.sqrt(((dec_ref - src) ** 2).mean())
+        print('image %d: rmse nvJPEG %.3f, PIL %.3f (of 255); bytes %d vs %d' % (i, err_nv, err_pil, len(data), len(ref.getvalue())))
+        assert err_nv < max(1.5 * err_pil, 1.0)
+    paths = [str(tmp_path / ('%d.jpg' % i)) for i in range(n)]
+    save_jpegs(pix.cuda(), paths, quality=95)
+    assert all(Image.open(p).size == (w, h) for p in paths)

@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
         log = os.path.join(HERE, 'build', os.path.basename(src)[:-3] + '.ptxas.log')
         with open(log, 'w') as f:
             f.write(out)
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart', '-ldl']
     subprocess.run(cmd, check=True)
     return LIB
 

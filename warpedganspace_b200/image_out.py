@@ -3,9 +3,12 @@
 
 The reference pulls every fp32 image to the host, normalises it there and lets ToPILImage transpose CHW -> HWC.  Here
 the per-image min/max and the uint8 conversion run in two launches over the NHWC image the generator produced
-(csrc/imgio.cu, bit-identical pixels), one byte per value crosses PCIe, and the JPEG files are written by a small
-thread pool (libjpeg releases the GIL) with the reference's encoder settings.
+(csrc/imgio.cu, bit-identical pixels) and the frames are JPEG-encoded ON THE GPU by nvJPEG with the reference's encoder
+settings (quality 95, optimised Huffman tables, progressive; csrc/jpeg.cu), so only the compressed bitstream crosses PCIe
+and the host just writes files.  When a resize is requested (``img_size``, done by PIL in the reference) the PIL path of
+the reference is used: one byte per value crosses PCIe and a small thread pool encodes.
 """
+import ctypes
 from concurrent.futures import ThreadPoolExecutor
 
 import torch
@@ -45,8 +48,43 @@ def save_jpeg(pixels_hwc, path, quality=95, img_size=None):
     im.save(path, 'JPEG', quality=quality, optimize=True, progressive=True)
 
 
-def save_jpegs(pixels_nhwc, paths, quality=95, img_size=None, workers=8):
-    """One D2H copy of the uint8 batch, then parallel encodes."""
+def nvjpeg_available():
+    return bool(_lib.load().wgs_jpeg_available())
+
+
+_HOST_BUF = {}
+
+
+def encode_jpegs(pixels_nhwc, quality=95, progressive=True):
+    """uint8 [N, H, W, C] CUDA tensor (C = 3 or 1) -> list of N JPEG bitstreams (bytes), encoded by nvJPEG on the device."""
+    if not pixels_nhwc.is_cuda or pixels_nhwc.dtype != torch.uint8:
+        raise RuntimeError('encode_jpegs needs a uint8 CUDA tensor (no CPU fallback)')
+    x = pixels_nhwc.contiguous()
+    n, h, w, c = x.shape
+    cap = h * w * c + 65536
+    key = (n, cap)
+    if key not in _HOST_BUF:
+        _HOST_BUF.clear()
+        _HOST_BUF[key] = (torch.empty(n * cap, dtype=torch.uint8).pin_memory(), (ctypes.c_longlong * n)())
+    buf, sizes = _HOST_BUF[key]
+    _lib.call('wgs_jpeg_encode', _lib.ptr(x), n, h, w, c, int(quality), int(bool(progressive)),
+              ctypes.c_void_p(buf.data_ptr()), cap, sizes, _lib.stream())
+    arr = buf.numpy()
+    return [arr[i * cap: i * cap + int(sizes[i])].tobytes() for i in range(n)]
+
+
+def save_jpegs(pixels_nhwc, paths, quality=95, img_size=None, workers=8, backend=None):
+    """Writes one JPEG per image.  backend 'nvjpeg' (default when available and no resize is requested): GPU encode, the host
+    only writes the bitstreams; 'pil': one D2H copy of the uint8 batch, then parallel PIL encodes (the reference's encoder)."""
+    if backend is None:
+        backend = 'nvjpeg' if (img_size is None and pixels_nhwc.is_cuda and nvjpeg_available()) else 'pil'
+    if backend == 'nvjpeg':
+        if img_size is not None:
+            raise ValueError('the nvJPEG path does not resize; use backend="pil" with img_size')
+        for data, path in zip(encode_jpegs(pixels_nhwc, quality, True), paths):
+            with open(path, 'wb') as f:
+                f.write(data)
+        return
     host = pixels_nhwc.cpu()
     with ThreadPoolExecutor(max_workers=workers) as pool:
         list(pool.map(lambda a: save_jpeg(a[0], a[1], quality, img_size), zip(host, paths)))
