@@ -190,7 +190,10 @@ def test_stem_im2col_path(case):
                                                 (1, 6, 10, 8, 2, 7, 11), (2, 5, 7, 4, 1, 4, 6),
                                                 # wide maps (interior fast path, ragged strips, both paddings)
                                                 (2, 33, 65, 32, 1, 32, 64), (1, 16, 40, 64, 2, 17, 41), (1, 19, 50, 32, 1, 18, 49),
-                                                (2, 64, 64, 32, 2, 65, 65)])
+                                                (2, 64, 64, 32, 2, 65, 65),
+                                                # >= 128 pixels wide with C % 32 == 0: the TMA-fed shared-memory variant
+                                                (2, 129, 129, 32, 1, 128, 128), (1, 65, 257, 64, 1, 64, 256),
+                                                (1, 128, 144, 32, 2, 129, 145), (2, 70, 200, 96, 1, 69, 199)])
 def test_fir4_act_matches_torch(N, H, W, C, pad0, Ho, Wo):
     """Separable 4-tap FIR + per-sample scale + noise + bias + sqrt2*lrelu against upfirdn2d-style torch code."""
     import ctypes
@@ -211,6 +214,39 @@ def test_fir4_act_matches_torch(N, H, W, C, pad0, Ho, Wo):
     want = f * alpha[:, :, None, None] + 0.3 * noise[None, None] + beta[None, :, None, None]
     want = 2 ** 0.5 * F.leaky_relu(want, 0.2)
     assert rel(out, want.permute(0, 2, 3, 1)) < 1e-6
+
+
+@pytest.mark.parametrize('N,H,W,C,pad0', [(3, 129, 161, 32, 1), (2, 64, 130, 64, 2), (2, 33, 40, 32, 1)])
+def test_fir4_act_split_output_and_selective_fp32(N, H, W, C, pad0):
+    """The fused outputs of fir4_act (both kernel variants): split32(out * split_scale[n, c]) for every image, fp32 only for
+    images n >= out_from_n (the back-propagated half of a pair batch), and the transposed-blur mode of the backward pass
+    (pad0 = 2, no bias / noise / activation, split32 output only)."""
+    import ctypes
+    from warpedganspace_b200 import _lib
+    g = torch.Generator().manual_seed(N + H + W + C)
+    Ho, Wo = (H - 1, W - 1) if pad0 == 1 else (H + 1, W + 1)
+    y = torch.randn(N, H, W, C, generator=g).cuda()
+    alpha = (torch.rand(N, C, generator=g) + 0.5).cuda()
+    beta = torch.randn(C, generator=g).cuda()
+    noise = torch.randn(Ho, Wo, generator=g).cuda()
+    sc = (torch.rand(N, C + 8, generator=g) + 0.5).cuda()[:, 4: 4 + C]            # a strided view, as the style slices are
+    taps = (ctypes.c_float * 4)(0.25, 0.75, 0.75, 0.25)
+    out = torch.full((N, Ho, Wo, C), 7.0, device='cuda')
+    xs = torch.empty(N, Ho, Wo, C // 32, 64, dtype=torch.bfloat16, device='cuda')
+    k1 = torch.tensor([0.25, 0.75, 0.75, 0.25], device='cuda')
+    yp = F.pad(y.permute(0, 3, 1, 2), [pad0, Wo + 3 - W - pad0, pad0, Ho + 3 - H - pad0])
+    f = F.conv2d(yp, torch.flip(torch.outer(k1, k1), [0, 1]).view(1, 1, 4, 4).expand(C, 1, 4, 4), groups=C).permute(0, 2, 3, 1)
+    if pad0 == 1:
+        _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(out), N, H, W, Ho, Wo, C, pad0, taps, _lib.ptr(alpha), _lib.ptr(beta),
+                  _lib.ptr(noise), 0.3, 3, _lib.ptr(xs), ctypes.c_void_p(sc.data_ptr()), sc.stride(0), 1, _lib.stream())
+        want = 2 ** 0.5 * F.leaky_relu(f * alpha[:, None, None, :] + 0.3 * noise[None, :, :, None] + beta, 0.2)
+        assert float((out[0] - 7.0).abs().max()) == 0.0                            # image 0 is not back-propagated
+        assert rel(out[1:], want[1:]) < 1e-6
+        assert rel(_unsplit(xs), want * sc[:, None, None, :]) < 2e-5
+    else:
+        _lib.call('wgs_fir4_act', _lib.ptr(y), None, N, H, W, Ho, Wo, C, pad0, taps, _lib.ptr(alpha), None, None, 0.0, 0,
+                  _lib.ptr(xs), None, 0, 0, _lib.stream())
+        assert rel(_unsplit(xs), f * alpha[:, None, None, :]) < 2e-5
 
 
 @pytest.mark.parametrize('N,Ci,H,W,Co,k,pad', [(2, 6, 32, 32, 64, 7, 3), (1, 6, 33, 35, 64, 7, 3), (2, 64, 32, 32, 128, 3, 1),

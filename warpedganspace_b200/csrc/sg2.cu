@@ -8,6 +8,10 @@
 
 namespace wgs {
 
+int fir4_act_tma_launch(const float* y, float* out, int N, int Hin, int Win, int Hout, int Wout, int C, int pad0,
+                        const float* taps4, const float* alpha, const float* beta, const float* noise, float noise_w, int act,
+                        void* out_split, const float* split_scale, long long split_scale_ld, int out_from_n, void* stream);
+
 // ------------------------------------------------------------------------------------------------
 // out[b, o] (+)= mul[b, o] * epi( wscale * sum_i f(x[b, i], x2[b, i]) * W[o, i]  (+ bscale * bias[o]) )     B small, I % 4 == 0
 //   f (in_mode): 0 x;  1 x^2;  2 x * dlrelu(x2) with dlrelu = sqrt2 (x2 > 0) or 0.2 sqrt2 (backward of 'fused_lrelu',
@@ -405,6 +409,11 @@ extern "C" int wgs_fir4_act(const float* y, float* out, int N, int Hin, int Win,
                             int out_from_n, void* stream) {
     WGS_REQUIRE(N > 0 && C > 0 && C % 4 == 0, "fir4_act: channels must be a multiple of 4");
     WGS_REQUIRE(taps4 != nullptr, "fir4_act: taps4 is a HOST pointer to 4 floats");
+    {   // large layers: TMA-fed shared-memory variant (fir_tma.cu); returns 0 when the shape is not its business
+        const int took = wgs::fir4_act_tma_launch(y, out, N, Hin, Win, Hout, Wout, C, pad0, taps4, alpha, beta, noise, noise_w, act,
+                                                  out_split, split_scale, split_scale_ld, out_from_n, stream);
+        if (took != 0) return took > 0 ? 0 : took;
+    }
     static int rows = 0;
     if (!rows) {
         const char* e = getenv("WGS_FIR_ROWS");
