@@ -235,6 +235,17 @@ typedef struct {
 } wgs_linear_problem;
 int wgs_linear_group(const wgs_linear_problem* problems, int count, int B, void* stream);
 int wgs_linear_problem_size(void);
+/* A chain of L equal-width linears (d -> d) in one launch on a cluster of 8 CTAs (csrc/mlp.cu): the mapping network
+ * (8 x EqualLinear + fused leaky-ReLU, model.py:110-131,291-295) forward, and its backward pass.
+ *   out_l[b,o] = epi( wscale * sum_i f(in[b,i], aux_l[b,i]) W_l[o,i] + bscale * bias_l[o] ),  in = out_{l-1}, in_0 = x
+ * in_mode 0: f = in; 2: f = in * lrelu'(aux) (aux = that layer's FORWARD output, [B, d] contiguous).  epi 0 linear, 1 sqrt(2)*lrelu_0.2.
+ * W_l [d, d] row-major (row = output feature), bias_l [d] or NULL, out_l [B, d] contiguous or NULL (intermediate not kept).
+ * h_layers is a HOST array.  d % 128 == 0, 2 * B * d * 4 bytes of shared memory (B <= 48 at d = 512).               */
+#define WGS_MLP_MAX_LAYERS 16
+typedef struct { const float* W; const float* bias; const float* aux; float* out; } wgs_mlp_layer;
+int wgs_mlp_chain(const float* x, long long x_ld, const wgs_mlp_layer* h_layers, int L, int B, int d, float wscale,
+                  float bscale, int in_mode, int epi, void* stream);
+int wgs_mlp_layer_size(void);
 /* PixelNorm over latent rows (model.py:9-15). */
 int wgs_pixelnorm_rows(const float* x, float* out, int B, int d, void* stream);
 /* Separable 4-tap FIR (upfirdn2d up=down=1: Blur, model.py:66-81; op/upfirdn2d_kernel.cu:52-137) fused with

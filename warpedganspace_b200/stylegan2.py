@@ -272,6 +272,40 @@ def _linear_group(problems, B):
         _lib.check(lib.wgs_linear_group(arr, len(chunk), int(B), _lib.stream()))
 
 
+class MlpLayer(ctypes.Structure):
+    """Mirror of wgs_mlp_layer (include/wgs_b200.h)."""
+    _fields_ = [('W', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('aux', ctypes.c_void_p), ('out', ctypes.c_void_p)]
+
+
+MLP_CHAIN = os.environ.get('WGS_MLP_CHAIN', '1') != '0'      # 0 = one launch per mapping layer (A/B switch)
+_mlp_checked = False
+
+
+def _mlp_chain(x, layers, B, d, wscale, bscale, in_mode, epi):
+    """layers: list of (W, bias or None, aux or None, out or None) -> one cluster launch (csrc/mlp.cu)."""
+    global _mlp_checked
+    lib = _lib.load()
+    if not _mlp_checked:
+        if lib.wgs_mlp_layer_size() != ctypes.sizeof(MlpLayer):
+            raise RuntimeError('wgs_mlp_layer layout mismatch between header and ctypes mirror')
+        _mlp_checked = True
+    arr = (MlpLayer * len(layers))()
+    for q, (W, bias, aux, out) in zip(arr, layers):
+        for t in (W, bias, aux, out):
+            if t is not None and not (t.is_cuda and t.is_contiguous()):
+                raise RuntimeError('mapping network needs contiguous CUDA tensors (no CPU fallback)')
+        q.W = W.data_ptr()
+        q.bias = bias.data_ptr() if bias is not None else None
+        q.aux = aux.data_ptr() if aux is not None else None
+        q.out = out.data_ptr() if out is not None else None
+    _lib.check(lib.wgs_mlp_chain(ctypes.c_void_p(x.data_ptr()), x.stride(0), arr, len(layers), B, d, float(wscale),
+                                 float(bscale), int(in_mode), int(epi), _lib.stream()))
+
+
+def _chain_ok(G, B):
+    return MLP_CHAIN and G.style_dim % 128 == 0 and 2 * B * G.style_dim * 4 <= 200 * 1024 and 1 <= G.n_mlp <= 16
+
+
 def _mapping_forward(G, z):
     """Returns the list [pixelnorm(z), h1, ..., h8 = w] (all kept for the backward pass)."""
     P = G.plan()
@@ -279,6 +313,10 @@ def _mapping_forward(G, z):
     acts = [torch.empty_like(z)]
     _lib.call('wgs_pixelnorm_rows', _lib.ptr(z), _lib.ptr(acts[0]), B, d, _lib.stream())
     wscale = (1.0 / math.sqrt(d)) * G.lr_mlp
+    if _chain_ok(G, B) and d == G.style_dim:
+        outs = torch.empty(G.n_mlp, B, G.style_dim, device=z.device, dtype=torch.float32)
+        _mlp_chain(acts[0], [(P['map_w'][i], P['map_b'][i], None, outs[i]) for i in range(G.n_mlp)], B, d, wscale, G.lr_mlp, 0, 1)
+        return acts + [outs[i] for i in range(G.n_mlp)]
     for i in range(G.n_mlp):
         out = torch.empty(B, G.style_dim, device=z.device, dtype=torch.float32)
         _linear(acts[-1], P['map_w'][i], P['map_b'][i], out, wscale=wscale, bscale=G.lr_mlp, epi=1)
@@ -449,6 +487,14 @@ def _mapping_backward(G, acts, dw):
     P = G.plan()
     wscale = (1.0 / math.sqrt(G.style_dim)) * G.lr_mlp
     g = dw
+    B = g.shape[0]
+    if _chain_ok(G, B) and all(a.is_contiguous() for a in acts):
+        out = torch.empty_like(acts[0])
+        n = G.n_mlp
+        # the fused-lrelu derivative (taken from each layer's forward output) is applied to g inside the chain
+        layers = [(P['map_w_t'][i], None, acts[i + 1], out if i == 0 else None) for i in range(n - 1, -1, -1)]
+        _mlp_chain(g.contiguous(), layers, B, G.style_dim, wscale, 0.0, 2, 0)
+        return out
     for i in range(G.n_mlp - 1, -1, -1):
         out = torch.empty_like(acts[i])
         # the fused-lrelu derivative (taken from the layer's forward output) is applied to g while it is loaded
