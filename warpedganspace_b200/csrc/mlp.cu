@@ -17,7 +17,7 @@
 namespace wgs {
 
 constexpr int MLP_CLUSTER = 8;
-constexpr int MLP_THREADS = 256;
+constexpr int MLP_THREADS = 1024;                 // 32 warps: two output features per warp per layer at d = 512, all loads in flight
 constexpr int MLP_BT = 8;
 
 struct MlpChain {
@@ -57,13 +57,24 @@ mlp_chain_kernel(const __grid_constant__ MlpChain g) {
                 float acc[MLP_BT];
 #pragma unroll
                 for (int t = 0; t < MLP_BT; ++t) acc[t] = 0.f;
-                for (int i = lane * 4; i < d; i += 128) {
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + i));
+                for (int i0 = lane * 4; i0 < d; i0 += 512) {
+                    float4 w4[4];                                   // the whole 512-wide slice of the row in flight at once
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * 128;
+                        w4[j] = i < d ? __ldg(reinterpret_cast<const float4*>(wrow + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
                     for (int t = 0; t < MLP_BT; ++t) {
                         if (b0 + t < B) {
-                            const float4 x4 = *reinterpret_cast<const float4*>(cur + (size_t)(b0 + t) * d + i);
-                            acc[t] += w4.x * x4.x + w4.y * x4.y + w4.z * x4.z + w4.w * x4.w;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int i = i0 + j * 128;
+                                if (i < d) {
+                                    const float4 x4 = *reinterpret_cast<const float4*>(cur + (size_t)(b0 + t) * d + i);
+                                    acc[t] += w4[j].x * x4.x + w4[j].y * x4.y + w4[j].z * x4.z + w4[j].w * x4.w;
+                                }
+                            }
                         }
                     }
                 }

@@ -267,7 +267,10 @@ extern "C" int wgs_conv_wgrad_split32(const void* xs, int n, int h, int w, int c
         row_env = (e && e[0] == '1') ? 1 : 0;                     // measured: no gain (the kernel is bound by its atomics)
     }
     // row mode keeps kw accumulators of 64*NB columns in the 512 TMEM columns
-    p.row_mode = (row_env && stride == 1 && kw >= 2 && kw * 64 <= 512 && p.bw == 8 && p.bh == 8) ? 1 : 0;
+    // on by default for long tap lists (the 4x4-tap space-to-depth stem: one CTA per tap re-read x and dy 16 times and was
+    // L2-bound, 0.45 ms; one CTA per kernel ROW loads dy once for its 4 taps: -0.29 ms on the training step); measured
+    // neutral for 3x3 layers, where it stays opt-in
+    p.row_mode = ((row_env || kh * kw >= 12) && stride == 1 && kw >= 2 && kw * 64 <= 512 && p.bw == 8 && p.bh == 8) ? 1 : 0;
     p.NB = std::min(p.row_mode ? std::max(1, 512 / (64 * kw)) : 4, std::min(4, ci_chunks));
     p.n_blocks = ceil_div(ci_chunks, p.NB);
     p.m_blocks = ceil_div(co_chunks, 2);
