@@ -1,15 +1,20 @@
 """Turns an ncu metrics capture of the tensor-core conv launches of one training step into
-profiles/r01_conv_traffic.json (bench.py reads it for `roofline.traffic`).
+profiles/rNN_conv_traffic.json (bench.py reads the newest one for `roofline.traffic`).  The file is stamped with the sha1 of
+the CUDA sources it measured (bench.source_stamp): bench.py reports `traffic_stale` instead of a number when the kernels
+have changed since the capture.
 
   ncu --profile-from-start off --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
       --csv --log-file gpurun_out/conv_traffic.csv python tools/ncu_step.py 400 "" wgs_conv_split32
-  python tools/ncu_traffic.py gpurun_out/conv_traffic.csv profiles/r01_conv_traffic.json
+  python tools/ncu_traffic.py gpurun_out/conv_traffic.csv profiles/r02_conv_traffic.json
 """
 import collections
 import csv
 import json
+import os
 import re
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 rows = collections.defaultdict(dict)
 names = {}
@@ -38,6 +43,7 @@ for k, v in conv.items():
 out = {
     'dram_bytes_per_launch': (rd + wr) / max(1, n), 'launches': n, 'dram_read_bytes': rd, 'dram_write_bytes': wr,
     'summed_ms': ms,
+    'source_stamp': __import__('bench').source_stamp(),
     'per_kernel': {k: {'launches': c, 'dram_bytes': b, 'ms': t} for k, (c, b, t) in per_kernel.items()},
     'source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum over every tensor-core conv launch of one eager training step '
               '(tools/ncu_step.py, B = 4 per GPU), averaged per launch',
