@@ -154,9 +154,15 @@ def test_reference_shaped_loop_over_the_repo_modules_matches_paired_trainer():
         eng_losses.append(float(out['loss']))
     print('reference-shaped loop losses', ref_losses, 'engine losses', eng_losses)
     assert abs(ref_losses[0] - eng_losses[0]) < 1e-4 * abs(ref_losses[0])      # (magnitude multiplied inside vs outside the RBF kernel)
-    # same forward inputs, same kernels underneath: only the accumulation order of atomically-reduced sums differs
+    # same forward inputs (the fused magnitude is applied after the normalisation, like `mag * S(mask, z)`), same kernels
+    # underneath: only the accumulation order of atomically-reduced sums (BatchNorm statistics, ToRGB, weight gradients)
+    # differs.  Train-mode BatchNorm over 4 samples x 1 pixel (layer 4 of a 32-px input) amplifies that last-bit noise
+    # by 1e3 .. 1e5 into the gradients (profiles/r02_gradient_conditioning.md: the reference's own fp32 graph moves by
+    # 1e-2 under a 1e-5 perturbation), so the train-mode bound is the conditioning-aware one of
+    # tests/test_gradients_gpu.py; the 1e-3 pin of the same graph lives there (kink-free draws, R.eval()).
     for a, b in zip(ref_grad, eng_grad):
-        assert rel(a, b) < 1e-3
+        cos = float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+        assert rel(a, b) < 5e-2 and cos > 0.999, (rel(a, b), cos)
     # later steps: the first Adam updates are ~lr * sign(g), so near-zero gradient entries whose sign depends on the
     # accumulation order move parameters by a full +-lr either way and the trajectories separate at the 1e-2 level
     # (two runs of the SAME loop do as well, tests/test_step_gpu.py::test_cuda_graph_replay_matches_eager)

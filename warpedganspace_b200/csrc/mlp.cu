@@ -41,7 +41,9 @@ mlp_chain_kernel(const __grid_constant__ MlpChain g) {
     float* cur = act;
     float* nxt = act + (size_t)B * d;
     for (int i = threadIdx.x; i < B * d; i += MLP_THREADS) cur[i] = __ldg(g.x + (size_t)(i / d) * g.x_ld + i % d);
-    __syncthreads();
+    // cluster-wide, not CTA-wide: a peer's shared memory may only be written once that CTA is known to have started
+    // (compute-sanitizer racecheck: "block that might not have entered yet")
+    ptx::cluster_sync();
     const int per = d / MLP_CLUSTER;
     for (int l = 0; l < g.L; ++l) {
         const wgs_mlp_layer& q = g.layer[l];

@@ -122,8 +122,11 @@ rbf_forward_kernel(const float* __restrict__ support_sets, const float* __restri
     rbf_accumulate<NV>(support_sets + (size_t)k * n_vec * d, alphas + (size_t)k * n_vec, gamma, zv, n_vec, d,
                        warp, lane, acc);
     const float n2 = rbf_reduce<NV>(acc, sm, red, d, warp, lane);
-    const float scale = (mag ? __ldg(mag + b) : 1.f) / sqrtf(n2);          // no epsilon, as the reference
-    for (int e = threadIdx.x; e < d; e += RBF_THREADS) out[(size_t)b * d + e] = sm[e] * scale;
+    // unit vector first, magnitude second: bit-identical to `mag * S(mask, z)` formed outside the kernel
+    // (lib/trainer.py:236), so a module-level loop and the fused engine see the same shift.  No epsilon, as the reference.
+    const float inv_n = 1.f / sqrtf(n2);
+    const float m = mag ? __ldg(mag + b) : 1.f;
+    for (int e = threadIdx.x; e < d; e += RBF_THREADS) out[(size_t)b * d + e] = (sm[e] * inv_n) * m;
 }
 
 // Backward of out = m * g/||g||,  g = -2 sum_j w_j D_j,  D_j = z - s_j,  w_j = a_j*gamma*exp(-gamma |D_j|^2).
