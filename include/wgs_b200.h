@@ -134,6 +134,7 @@ typedef struct {
     int co, ci, kh, kw;
     int mode, layout, S, G;
     signed char idx[64];
+    int ci_src, ci_off;   /* mode 3 only: pack input channels [ci_off, ci_off + ci) of a [Co, ci_src, kh, kw] weight (0 = all of ci) */
 } wgs_pack_problem;
 int wgs_pack_weights_group(const wgs_pack_problem* h_problems, int count, void* stream);
 int wgs_pack_problem_size(void);
@@ -141,6 +142,9 @@ int wgs_pack_problem_size(void);
  * (py*2+px)*C + c = x[2Y+py, 2X+px, c] - the operand of a few-input-channel stride-2 conv run as a stride-1 conv
  * (ResNet stem 7x7/2 on 6 channels, lib/reconstructor.py:56-60 -> 4x4 taps on 24 channels).                        */
 int wgs_s2d_pack_split32(const float* x, int N, int H, int W, int C, void* out, void* stream);
+/* The same over the channel concatenation [x1 (C1 channels) ; x2 (C2 channels)] without materialising it: the Reconstructor's
+ * torch.cat([x1, x2], dim=1) (lib/reconstructor.py:72) folded into the operand pack of its stem.                     */
+int wgs_s2d_pack_split32_pair(const float* x1, const float* x2, int N, int H, int W, int C1, int C2, void* out, void* stream);
 
 
 #define WGS_MAX_TAPS 64
@@ -189,7 +193,8 @@ typedef struct wgs_conv_desc {
     /* 1 = this launch may split its contraction over a thread-block cluster (tiny-M, deep-K layers: the Reconstructor's
      * layer 3 / 4 convs).  The split factor depends on the number of output tiles, i.e. on the batch size, so callers that
      * need results independent of how images are batched (the generator: G(z) inside a pair batch == G(z) alone, bit for
-     * bit) leave it 0.  WGS_CONV_SPLITK=1 / 0 in the environment forces it on / off for every launch.                  */
+     * bit) leave it 0 or pass 2 = split by GEOMETRY only (feature maps up to 16 x 16; the factor is a function of the map
+     * size, channel and tap counts, never of the batch).  WGS_CONV_SPLITK=1 / 0 in the environment forces splitting on / off. */
     int split_k;
 } wgs_conv_desc;
 
@@ -231,7 +236,7 @@ typedef struct {
     float* out;       long long out_ld;
     int I, O;
     float wscale, bscale, eps;
-    int in_mode, epi, accumulate;
+    int in_mode, epi, accumulate;   /* accumulate: 0 overwrite, 1 add to the output, 2 atomic add (problems of one launch sharing an output) */
 } wgs_linear_problem;
 int wgs_linear_group(const wgs_linear_problem* problems, int count, int B, void* stream);
 int wgs_linear_problem_size(void);
@@ -333,6 +338,19 @@ int wgs_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const 
  * fwd: out fp32 [N,OH,OW,C], idx uint8 argmax tap, optional split32 pack; bwd: gather, dz [N,H,W,C] fully written.   */
 int wgs_maxpool3s2_fwd(const float* z, int N, int H, int W, int C, float* out, void* idx, void* outs, void* stream);
 int wgs_maxpool3s2_bwd(const float* dout, const void* idx, int N, int H, int W, int C, float* dz, void* stream);
+/* The stem's train-mode BatchNorm + ReLU + max-pool fused (torchvision resnet18 bn1 / relu / maxpool, lib/reconstructor.py:54):
+ * the normalised activation is never stored.  fwd: y [N,H,W,C] + the shifted sums of wgs_bn_stats -> pooled out fp32, arg-max
+ * table, optional split32 pack, mean / rstd (+ running statistics).  bwd: the pooled gradient is gathered through the arg-max
+ * table, the ReLU mask re-derived from y; reduce accumulates sum dzr / sum dzr*xhat, apply writes split32(dy).            */
+int wgs_bn_pool_fwd(const float* y, const float* sum, const float* sumsq, int N, int H, int W, int C, float eps,
+                    float momentum, const float* gamma, const float* beta, float* out, void* idx, void* outs,
+                    float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+int wgs_bn_pool_bwd_reduce(const float* dout, const void* idx, const float* y, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, int N, int H, int W, int C, float* sum_dz,
+                           float* sum_dzx, void* stream);
+int wgs_bn_pool_bwd_apply(const float* dout, const void* idx, const float* y, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, const float* sum_dz, const float* sum_dzx, int N,
+                          int H, int W, int C, void* dys, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,3 +55,103 @@ def test_reconstructor_fixture(golden, name):
         assert rel(sd_after[k], v) < 1e-4, k
     if name == 'resnet':
         assert params['features_extractor.fc.weight'].grad is None             # the dead fc stays untouched
+
+
+def test_pair_inputs_skip_the_cat_and_form_only_the_shifted_images_gradient(golden):
+    """Reconstructor.forward(x1, x2) with x1 detached (the paired step, lib/trainer.py:200,242): the channel concatenation is
+    folded into the stem's operand pack and the stem's data gradient is formed for x2's three channels only - same logits
+    and the same d x2 as the path that materialises cat([x1, x2]) and back-propagates into both."""
+    from warpedganspace_b200.reconstructor import Reconstructor
+    fx = golden('reconstructor_resnet.pt')
+    sd = o_rec.init_state(fx['type'], fx['dim'], fx['channels'], generator=gen(fx['seed']))
+    outs = []
+    for both in (True, False):
+        R = Reconstructor(fx['type'], fx['dim'], fx['channels'])
+        R.load_state_dict(sd, strict=True)
+        R.cuda().train()
+        x1 = fx['x1'].cuda().requires_grad_(both)
+        x2 = fx['x2'].cuda().requires_grad_(True)
+        logits, mag = R(x1, x2)
+        loss = F.cross_entropy(logits, fx['idx'].cuda()) + 0.25 * (mag - fx['tgt'].cuda()).abs().mean()
+        loss.backward()
+        assert (x1.grad is not None) == both
+        outs.append((logits.detach(), x2.grad.clone(), R.features_extractor.conv1.weight.grad.clone()))
+    # (BatchNorm statistics and weight gradients are atomically accumulated: the order, hence the last bits, vary run to run,
+    # and train-mode BatchNorm at batch 4 amplifies them into the gradients - same bound as the fixture test above)
+    assert rel(outs[1][0], outs[0][0]) < 1e-4
+    assert rel(outs[1][1], outs[0][1]) < 2e-2 and rel(outs[1][2], outs[0][2]) < 2e-2
+    assert rel(outs[1][1], fx['dx2']) < 2e-2
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 20, 64), (1, 9, 7, 32), (3, 34, 34, 64)])
+def test_fused_stem_batchnorm_relu_maxpool_matches_torch(shape):
+    """wgs_bn_pool_fwd / _bwd_reduce / _bwd_apply (the normalised activation is never stored) against
+    max_pool2d(relu(batch_norm(y, training=True)), 3, 2, 1) and its autograd backward."""
+    import ctypes
+    from warpedganspace_b200 import _lib
+    n, h, w, c = shape
+    g = gen(77)
+    y = (torch.randn(n, h, w, c, generator=g) * 1.5 + 0.7).cuda()
+    gamma = (1.0 + 0.3 * torch.randn(c, generator=g)).cuda()        # some negative-slope channels: relu(bn) is not monotone in y
+    gamma[::5] *= -1
+    beta = (0.2 * torch.randn(c, generator=g)).cuda()
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    dout = torch.randn(n, oh, ow, c, generator=g).cuda()
+    rm, rv = torch.zeros(c).cuda(), torch.ones(c).cuda()
+    # torch reference
+    yt = y.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gt, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_t, rv_t = rm.clone(), rv.clone()
+    zt = F.max_pool2d(F.relu(F.batch_norm(yt, rm_t, rv_t, gt, bt, True, 0.1, 1e-5)), 3, 2, 1)
+    zt.backward(dout.permute(0, 3, 1, 2))
+    # kernels
+    s0, s1 = torch.zeros(c).cuda(), torch.zeros(c).cuda()
+    st = _lib.stream()
+    _lib.call('wgs_bn_stats', _lib.ptr(y), n * h * w, c, _lib.ptr(s0), _lib.ptr(s1), st)
+    out = torch.empty(n, oh, ow, c).cuda()
+    idx = torch.empty(n, oh, ow, c, dtype=torch.uint8).cuda()
+    outs = torch.empty(n, oh, ow, (c + 31) // 32, 64, dtype=torch.bfloat16).cuda()
+    mean, rstd = torch.empty(c).cuda(), torch.empty(c).cuda()
+    _lib.call('wgs_bn_pool_fwd', _lib.ptr(y), _lib.ptr(s0), _lib.ptr(s1), n, h, w, c, 1e-5, 0.1, _lib.ptr(gamma), _lib.ptr(beta),
+              _lib.ptr(out), _lib.ptr(idx), _lib.ptr(outs), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(rm), _lib.ptr(rv), st)
+    assert rel(out, zt.permute(0, 2, 3, 1)) < 2e-6
+    unsplit = outs.float().view(n, oh, ow, -1, 2, 32).sum(dim=4).reshape(n, oh, ow, -1)[..., :c]
+    assert rel(unsplit, out) < 1e-5
+    assert rel(rm, rm_t) < 1e-6 and rel(rv, rv_t) < 1e-6
+    d_beta, d_gamma = torch.zeros(c).cuda(), torch.zeros(c).cuda()
+    _lib.call('wgs_bn_pool_bwd_reduce', _lib.ptr(dout), _lib.ptr(idx), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd),
+              _lib.ptr(gamma), _lib.ptr(beta), n, h, w, c, _lib.ptr(d_beta), _lib.ptr(d_gamma), st)
+    dys = torch.empty(n, h, w, (c + 31) // 32, 64, dtype=torch.bfloat16).cuda()
+    _lib.call('wgs_bn_pool_bwd_apply', _lib.ptr(dout), _lib.ptr(idx), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd),
+              _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(d_beta), _lib.ptr(d_gamma), n, h, w, c, _lib.ptr(dys), st)
+    dy = dys.float().view(n, h, w, -1, 2, 32).sum(dim=4).reshape(n, h, w, -1)[..., :c]
+    assert rel(d_beta, bt.grad) < 1e-5 and rel(d_gamma, gt.grad) < 1e-5
+    assert rel(dy, yt.grad.permute(0, 2, 3, 1)) < 3e-5
+
+
+@pytest.mark.parametrize('hw', [(32, 32), (64, 48)])
+def test_stem_data_gradient_for_a_channel_slice(hw):
+    """The 7x7/2 stem's data gradient for input channels [3, 6) only (phase-packed output with 3-channel groups on a dense
+    [N, H, W, 3] tensor: the small-group epilogue) against torch autograd, and against the slice of the 6-channel launch;
+    the grouped weight pack with a channel slice against the host-side pack."""
+    from warpedganspace_b200 import conv as C
+    h, w = hw
+    g = gen(91)
+    x = torch.randn(2, 6, h, w, generator=g).cuda().requires_grad_(True)
+    wt = (torch.randn(64, 6, 7, 7, generator=g) * 0.1).cuda()
+    dy = torch.randn(2, 64, h // 2, w // 2, generator=g).cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    F.conv2d(x, wt, None, 2, 3).backward(dy)
+    dys = C.pack_split32(dy.permute(0, 2, 3, 1).contiguous())
+    full = C.conv_dgrad_merged(dys, wt, (h, w), 2, 3)
+    sub = C.conv_dgrad_merged(dys, wt, (h, w), 2, 3, ci_sub=(3, 3))
+    assert sub.shape == (2, h, w, 3)
+    assert rel(full, x.grad.permute(0, 2, 3, 1)) < 3e-5
+    assert rel(sub, x.grad.permute(0, 2, 3, 1)[..., 3:]) < 3e-5
+    assert rel(sub, full[..., 3:]) < 1e-6
+    packed = C.pack_weights_group([(wt, C.PACK_MERGED_DGRAD, (2, 3, 3, 3))])[0]
+    shifts, idx, G = C._phase_plan('dgrad', 7, 7, 2, 3, wt.device)
+    host = C.merged_phase_weights(wt[:, 3:6].permute(1, 0, 2, 3).reshape(3, 64, 49), idx, len(shifts), G)
+    assert torch.equal(packed, host)
+    sub2 = C.conv_dgrad_merged(dys, wt, (h, w), 2, 3, w_merged=packed, ci_sub=(3, 3))
+    assert torch.equal(sub2, sub)

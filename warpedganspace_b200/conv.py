@@ -112,7 +112,8 @@ class PackProblem(ctypes.Structure):
     """Mirror of wgs_pack_problem (include/wgs_b200.h)."""
     _fields_ = [('src', ctypes.c_void_p), ('dst', ctypes.c_void_p), ('co', ctypes.c_int), ('ci', ctypes.c_int),
                 ('kh', ctypes.c_int), ('kw', ctypes.c_int), ('mode', ctypes.c_int), ('layout', ctypes.c_int),
-                ('S', ctypes.c_int), ('G', ctypes.c_int), ('idx', ctypes.c_byte * 64)]
+                ('S', ctypes.c_int), ('G', ctypes.c_int), ('idx', ctypes.c_byte * 64),
+                ('ci_src', ctypes.c_int), ('ci_off', ctypes.c_int)]
 
 
 PACK_FWD, PACK_TRANSPOSED, PACK_IM2COL, PACK_MERGED_DGRAD, PACK_S2D = 0, 1, 2, 3, 4
@@ -149,8 +150,11 @@ def pack_weights_group(specs):
             T, rows, K = S * S, co, 4 * ci
             q.S, q.G = S, G
         else:
-            stride, padding = extra
+            stride, padding = extra[:2]
             shifts, idx, G = _phase_plan('dgrad', kh, kw, stride, padding, w.device)
+            if len(extra) == 4:                  # data gradient w.r.t. input channels [ci_off, ci_off + ci_n) only
+                q.ci_src, q.ci_off, q.ci = ci, extra[2], extra[3]
+                ci = extra[3]
             T, rows, K = len(shifts), G * ci, co
             q.S, q.G = T, G
             for i, t in enumerate(_phase_idx_host('dgrad', kh, kw, stride, padding)):
@@ -171,11 +175,18 @@ def s2d_geometry(k, padding):
     return a_max - a_min + 1, a_min, -(padding + 2 * a_min)
 
 
-def s2d_pack_split32(x_nhwc):
-    """fp32 NHWC [N, H, W, C] (H, W even) -> split32 [N, H/2, W/2, ceil(4C/32), 64], channel (py*2+px)*C + c."""
+def s2d_pack_split32(x_nhwc, x2_nhwc=None):
+    """fp32 NHWC [N, H, W, C] (H, W even) -> split32 [N, H/2, W/2, ceil(4C/32), 64], channel (py*2+px)*C + c.
+    With x2_nhwc: the same over the channel concatenation [x_nhwc ; x2_nhwc] without materialising it."""
     n, h, w, c = x_nhwc.shape
-    out = torch.empty(n, h // 2, w // 2, chunks_of(4 * c), 64, dtype=torch.bfloat16, device=x_nhwc.device)
-    _lib.call('wgs_s2d_pack_split32', _lib.ptr(x_nhwc), n, h, w, c, _lib.ptr(out), _lib.stream())
+    if x2_nhwc is None:
+        out = torch.empty(n, h // 2, w // 2, chunks_of(4 * c), 64, dtype=torch.bfloat16, device=x_nhwc.device)
+        _lib.call('wgs_s2d_pack_split32', _lib.ptr(x_nhwc), n, h, w, c, _lib.ptr(out), _lib.stream())
+        return out
+    assert x2_nhwc.shape[:3] == x_nhwc.shape[:3] and x_nhwc.is_contiguous() and x2_nhwc.is_contiguous()
+    c2 = x2_nhwc.shape[3]
+    out = torch.empty(n, h // 2, w // 2, chunks_of(4 * (c + c2)), 64, dtype=torch.bfloat16, device=x_nhwc.device)
+    _lib.call('wgs_s2d_pack_split32_pair', _lib.ptr(x_nhwc), _lib.ptr(x2_nhwc), n, h, w, c, c2, _lib.ptr(out), _lib.stream())
     return out
 
 
@@ -221,7 +232,7 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
             assert split_scale.stride(1) == 1
             d.split_scale, d.split_scale_ld = split_scale.data_ptr(), split_scale.stride(0)
     d.out_from_n = out_from_n
-    d.split_k = int(bool(split_k))
+    d.split_k = int(split_k)                     # 0 off, 1 batch-dependent (Reconstructor), 2 geometry-only (frozen generators)
     if rgb_out is not None:
         assert rgb_w.is_contiguous() and rgb_out.is_contiguous()
         d.rgb_w, d.rgb_out = rgb_w.data_ptr(), rgb_out.data_ptr()
@@ -377,12 +388,16 @@ def merged_phase_weights(w_src, idx, S, G):
     return pack_weight_rows(sel.permute(2, 0, 1).reshape(S, G * rows, K).contiguous())
 
 
-def conv_dgrad_merged(dys, w, in_hw, stride, padding, out=None, accumulate=False, w_merged=None):
-    """Data gradient of F.conv2d(x, w, stride, padding) for stride > 1 in ONE launch -> dx fp32 [N, H, W, Ci]."""
+def conv_dgrad_merged(dys, w, in_hw, stride, padding, out=None, accumulate=False, w_merged=None, ci_sub=None):
+    """Data gradient of F.conv2d(x, w, stride, padding) for stride > 1 in ONE launch -> dx fp32 [N, H, W, Ci].
+    ci_sub = (offset, count): the gradient w.r.t. that slice of the input channels only (w_merged packed to match)."""
     co, ci, kh, kw = w.shape
     h, wd = in_hw
     n = dys.shape[0]
     shifts, idx, G = _phase_plan('dgrad', kh, kw, stride, padding, dys.device)
+    if ci_sub is not None:
+        w = w[:, ci_sub[0]: ci_sub[0] + ci_sub[1]]
+        ci = ci_sub[1]
     if w_merged is None:
         w_merged = merged_phase_weights(w.detach().permute(1, 0, 2, 3).reshape(ci, co, kh * kw), idx, len(shifts), G)
     dx = out if out is not None else torch.empty(n, h, wd, ci, device=dys.device, dtype=torch.float32)

@@ -232,7 +232,12 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ 
 }
 
 static bool bn_ok(int C) { return C >= 4 && C % 4 == 0 && (C / 4) <= BN_THREADS && BN_THREADS % (C / 4) == 0; }
-static int bn_red_blocks(long long R) { return (int)std::max<long long>(1, std::min<long long>((long long)num_sms() * 8, (R + 63) / 64)); }
+// reduction grids: ~8 float4 loads per thread (the deep layers have few rows but wide channels: 64 rows per block left
+// layer 4 at 64 blocks of 32 dependent iterations each - 19 us for 17 MB)
+static int bn_red_blocks(long long R, int C) {
+    const long long quads = R * (C / 4);
+    return (int)std::max<long long>(1, std::min<long long>((long long)num_sms() * 8, (quads + 2047) / 2048));
+}
 static int bn_ew_blocks(long long total) { return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)num_sms() * 32)); }
 
 }  // namespace wgs
@@ -242,7 +247,7 @@ using namespace wgs;
 extern "C" int wgs_bn_stats(const float* y, long long R, int C, float* sum, float* sumsq, void* stream) {
     WGS_REQUIRE(bn_ok(C) && R > 0, "bn_stats: C must be a multiple of 4 with C/4 dividing 256");
     const size_t smem = 2 * (size_t)(BN_THREADS / (C / 4)) * C * sizeof(float);
-    bn_stats_kernel<<<bn_red_blocks(R), BN_THREADS, smem, (cudaStream_t)stream>>>(y, R, C, sum, sumsq);
+    bn_stats_kernel<<<bn_red_blocks(R, C), BN_THREADS, smem, (cudaStream_t)stream>>>(y, R, C, sum, sumsq);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
@@ -286,7 +291,7 @@ extern "C" int wgs_bn_act_bwd_reduce(const float* dz, const float* z, const floa
                                      int relu, long long R, int C, float* sum_dz, float* sum_dzx, void* stream) {
     WGS_REQUIRE(bn_ok(C) && R > 0, "bn_act_bwd_reduce: C must be a multiple of 4 with C/4 dividing 256");
     const size_t smem = 2 * (size_t)(BN_THREADS / (C / 4)) * C * sizeof(float);
-    bn_act_bwd_reduce_kernel<<<bn_red_blocks(R), BN_THREADS, smem, (cudaStream_t)stream>>>(dz, z, y, mean, rstd, relu, R, C,
+    bn_act_bwd_reduce_kernel<<<bn_red_blocks(R, C), BN_THREADS, smem, (cudaStream_t)stream>>>(dz, z, y, mean, rstd, relu, R, C,
                                                                                          sum_dz, sum_dzx);
     count_launch();
     WGS_LAUNCH_CHECK();
@@ -390,6 +395,258 @@ maxpool3s2_bwd_kernel(const float* __restrict__ dout, const unsigned char* __res
 }
 
 }  // namespace wgs
+
+// ---------------------------------------------------------------------------------------------------
+// The ResNet stem's BatchNorm + ReLU + 3x3/2 max-pool as ONE forward kernel and two backward kernels (torchvision resnet18
+// bn1 / relu / maxpool, lib/reconstructor.py:54-69).  The normalised activation z = relu(bn(y)) (268 MB at 4 x 512^2 x 64) is
+// never stored: the forward pools it on the fly out of the conv output y, the backward re-derives the ReLU mask from y and
+// gathers the pooled gradient through the arg-max table - instead of bn_act_fwd (write z) -> maxpool fwd (read z) and
+// maxpool bwd (write dz) -> bn reduce (read dz, z, y) -> bn apply (read dz, z, y).
+namespace wgs {
+
+__device__ __forceinline__ float bn_affine(float v, float m, float k, float b) { return (v - m) * k + b; }
+
+__global__ void __launch_bounds__(256)
+bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ sum, const float* __restrict__ sumsq,
+                        int N, int H, int W, int C, float eps, float momentum, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float* __restrict__ out, unsigned char* __restrict__ idx,
+                        __nv_bfloat16* __restrict__ outs, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                        float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int OH = (H + 1) / 2, OW = (W + 1) / 2, C4 = C >> 2;
+    const long long R = (long long)N * H * W;
+    const long long total = (long long)N * OH * OW * C4;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c = (int)(i0 % C4) * 4;                                 // fixed per thread (host: stride % C4 == 0)
+    const float4 su = __ldg(reinterpret_cast<const float4*>(sum + c)), sq = __ldg(reinterpret_cast<const float4*>(sumsq + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(y + c));
+    float4 m4, s4;
+    if (blockIdx.x == 0 && threadIdx.x < C4) {
+        double v0, v1, v2, v3;
+        bn_moments(su.x, sq.x, sh.x, R, eps, m4.x, s4.x, v0);
+        bn_moments(su.y, sq.y, sh.y, R, eps, m4.y, s4.y, v1);
+        bn_moments(su.z, sq.z, sh.z, R, eps, m4.z, s4.z, v2);
+        bn_moments(su.w, sq.w, sh.w, R, eps, m4.w, s4.w, v3);
+        *reinterpret_cast<float4*>(mean_out + c) = m4;
+        *reinterpret_cast<float4*>(rstd_out + c) = s4;
+        if (running_mean) {
+            const double ub = R > 1 ? (double)R / (double)(R - 1) : 1.0;
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            const double vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                running_mean[c + k] = (1.f - momentum) * running_mean[c + k] + momentum * mm[k];
+                running_var[c + k] = (1.f - momentum) * running_var[c + k] + momentum * (float)(vv[k] * ub);
+            }
+        }
+    }
+    // every thread uses the SAME fp32 moments the backward kernels read back (mean_out / rstd_out are the double-rounded
+    // values of block 0): recompute them identically here
+    {
+        double v;
+        bn_moments(su.x, sq.x, sh.x, R, eps, m4.x, s4.x, v);
+        bn_moments(su.y, sq.y, sh.y, R, eps, m4.y, s4.y, v);
+        bn_moments(su.z, sq.z, sh.z, R, eps, m4.z, s4.z, v);
+        bn_moments(su.w, sq.w, sh.w, R, eps, m4.w, s4.w, v);
+    }
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 k4 = make_float4(s4.x * g4.x, s4.y * g4.y, s4.z * g4.z, s4.w * g4.w);
+    for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / C4;
+        const int ox = (int)(r % OW); r /= OW;
+        const int oy = (int)(r % OH);
+        const int n = (int)(r / OH);
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        unsigned char arg[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = 2 * oy - 1 + t / 3, xx = 2 * ox - 1 + t % 3;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(y + (((size_t)n * H + yy) * W + xx) * C + c));
+            const float vv[4] = {fmaxf(bn_affine(v.x, m4.x, k4.x, b4.x), 0.f), fmaxf(bn_affine(v.y, m4.y, k4.y, b4.y), 0.f),
+                                 fmaxf(bn_affine(v.z, m4.z, k4.z, b4.z), 0.f), fmaxf(bn_affine(v.w, m4.w, k4.w, b4.w), 0.f)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (vv[k] > best[k]) { best[k] = vv[k]; arg[k] = (unsigned char)t; }
+        }
+        const size_t pix = ((size_t)n * OH + oy) * OW + ox;
+        *reinterpret_cast<float4*>(out + pix * C + c) = make_float4(best[0], best[1], best[2], best[3]);
+        *reinterpret_cast<uchar4*>(idx + pix * C + c) = make_uchar4(arg[0], arg[1], arg[2], arg[3]);
+        if (outs) {
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_bf16(best[k], hi[k], lo[k]);
+            __nv_bfloat16* sp = outs + pix * (size_t)(((C + 31) >> 5) * 64) + (size_t)(c >> 5) * 64 + (c & 31);
+            *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+}
+
+// Backward, reduction pass, from the POOLED side: every pooled element routes its gradient to exactly one input position
+// (its arg-max tap), so  sum_dz[c] = sum_pooled dout * [z(argmax) > 0]  and  sum_dzx[c] = sum_pooled dout * [..] * xhat(argmax)
+// - a quarter of the elements of the input-side formulation, one gathered y value each.
+__global__ void __launch_bounds__(BN_THREADS)
+bn_pool_bwd_reduce_kernel(const float* __restrict__ dout, const unsigned char* __restrict__ idx, const float* __restrict__ y,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, int N, int H, int W, int C, float* __restrict__ sum_dz,
+                          float* __restrict__ sum_dzx) {
+    extern __shared__ float sm[];
+    const int C4 = C >> 2, PL = BN_THREADS / C4, OH = (H + 1) / 2, OW = (W + 1) / 2;
+    const int q = threadIdx.x % C4, pl = threadIdx.x / C4, c = q * 4;
+    const int RP = N * OH * OW;                                        // pooled rows
+    const int per = (RP + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * per, r1 = min(RP, r0 + per);
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c)), s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float kk[4] = {s4.x * g4.x, s4.y * g4.y, s4.z * g4.z, s4.w * g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = r0 + pl; r < r1; r += PL) {
+        const int ox = r % OW, t1 = r / OW, oy = t1 % OH, n = t1 / OH;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dout + (size_t)r * C + c));
+        const uchar4 id = *reinterpret_cast<const uchar4*>(idx + (size_t)r * C + c);
+        const float gg[4] = {g.x, g.y, g.z, g.w};
+        const unsigned char tt[4] = {id.x, id.y, id.z, id.w};
+        const long long yb = (((long long)n * H + (2 * oy - 1)) * W + (2 * ox - 1)) * C + c;  // tap (0, 0) of the window (may lie outside)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ty = tt[k] / 3, tx = tt[k] - ty * 3;
+            const float v = __ldg(y + (yb + ((long long)ty * W + tx) * C + k));       // the arg-max tap itself is always inside
+            if (bn_affine(v, mm[k], kk[k], bb[k]) > 0.f) {
+                a[k] += gg[k];
+                b[k] += gg[k] * (v - mm[k]) * ss[k];
+            }
+        }
+    }
+    bn_reduce2_to_global(a, b, sm, C, C4, PL, sum_dz, sum_dzx);
+}
+
+// Backward, apply pass: dy = gamma * rstd * (dzr - sum_dz/R - xhat * sum_dzx/R) -> split32 (operand of the stem's dgrad /
+// wgrad).  One thread per 2x2 block of input pixels and channel quad: the block's pixels look at the four pooling windows
+// (Y, X), (Y, X+1), (Y+1, X), (Y+1, X+1) only, whose gradient / arg-max entries are loaded once for all four pixels
+// (pixel (2Y+dy, 2X+dx) is tap (1+dy-2a, 1+dx-2b) of window (Y+a, X+b)).
+__global__ void __launch_bounds__(BN_THREADS)
+bn_pool_bwd_apply_kernel(const float* __restrict__ dout, const unsigned char* __restrict__ idx, const float* __restrict__ y,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx,
+                         int N, int H, int W, int C, __nv_bfloat16* __restrict__ dys) {
+    const int C4 = C >> 2, OH = (H + 1) / 2, OW = (W + 1) / 2;
+    const long long total = (long long)N * OH * OW * C4;
+    const float inv_r = 1.f / (float)((long long)N * H * W);
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c = (int)(i0 % C4) * 4;                                 // fixed per thread (host: stride % C4 == 0)
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c)), s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 k4 = make_float4(s4.x * g4.x, s4.y * g4.y, s4.z * g4.z, s4.w * g4.w);
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(sum_dz + c)), q4 = __ldg(reinterpret_cast<const float4*>(sum_dzx + c));
+    const int chunks64 = ((C + 31) >> 5) * 64;
+    for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / C4);
+        const int X = r % OW, t1 = r / OW, Y = t1 % OH, n = t1 / OH;
+        float4 wg[2][2];
+        uchar4 wi[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                wg[a][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                wi[a][b] = make_uchar4(255, 255, 255, 255);
+                if (Y + a < OH && X + b < OW) {
+                    const size_t pix = ((size_t)n * OH + Y + a) * OW + X + b;
+                    wg[a][b] = __ldg(reinterpret_cast<const float4*>(dout + pix * C + c));
+                    wi[a][b] = *reinterpret_cast<const uchar4*>(idx + pix * C + c);
+                }
+            }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int yy = 2 * Y + dy;
+            if (yy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int xx = 2 * X + dx;
+                if (xx >= W) continue;
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int a = 0; a <= dy; ++a)
+#pragma unroll
+                    for (int b = 0; b <= dx; ++b) {
+                        const unsigned char t = (unsigned char)((1 + dy - 2 * a) * 3 + (1 + dx - 2 * b));
+                        if (wi[a][b].x == t) g.x += wg[a][b].x;
+                        if (wi[a][b].y == t) g.y += wg[a][b].y;
+                        if (wi[a][b].z == t) g.z += wg[a][b].z;
+                        if (wi[a][b].w == t) g.w += wg[a][b].w;
+                    }
+                const size_t row = ((size_t)n * H + yy) * W + xx;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(y + row * C + c));
+                g.x = bn_affine(v.x, m4.x, k4.x, b4.x) > 0.f ? g.x : 0.f;
+                g.y = bn_affine(v.y, m4.y, k4.y, b4.y) > 0.f ? g.y : 0.f;
+                g.z = bn_affine(v.z, m4.z, k4.z, b4.z) > 0.f ? g.z : 0.f;
+                g.w = bn_affine(v.w, m4.w, k4.w, b4.w) > 0.f ? g.w : 0.f;
+                float o[4];
+                o[0] = g4.x * s4.x * (g.x - a4.x * inv_r - (v.x - m4.x) * s4.x * q4.x * inv_r);
+                o[1] = g4.y * s4.y * (g.y - a4.y * inv_r - (v.y - m4.y) * s4.y * q4.y * inv_r);
+                o[2] = g4.z * s4.z * (g.z - a4.z * inv_r - (v.z - m4.z) * s4.z * q4.z * inv_r);
+                o[3] = g4.w * s4.w * (g.w - a4.w * inv_r - (v.w - m4.w) * s4.w * q4.w * inv_r);
+                __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) split_bf16(o[k], hi[k], lo[k]);
+                __nv_bfloat16* sp = dys + row * chunks64 + (c >> 5) * 64 + (c & 31);
+                *reinterpret_cast<uint2*>(sp) = *reinterpret_cast<const uint2*>(hi);
+                *reinterpret_cast<uint2*>(sp + 32) = *reinterpret_cast<const uint2*>(lo);
+            }
+        }
+    }
+}
+
+// grid of element-wise kernels whose threads keep one channel quad: a multiple of C/4 threads in total
+static int bn_quad_blocks(long long total, int C4, int threads) {
+    long long b = std::max<long long>(1, std::min<long long>((total + threads - 1) / threads, (long long)num_sms() * 32));
+    while ((b * threads) % C4 != 0) ++b;
+    return (int)b;
+}
+
+}  // namespace wgs
+
+extern "C" int wgs_bn_pool_fwd(const float* y, const float* sum, const float* sumsq, int N, int H, int W, int C, float eps,
+                               float momentum, const float* gamma, const float* beta, float* out, void* idx, void* outs,
+                               float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
+    WGS_REQUIRE(wgs::bn_ok(C) && N > 0 && H > 0 && W > 0, "bn_pool_fwd: C must be a multiple of 4 with C/4 dividing 256");
+    WGS_REQUIRE(y && sum && sumsq && gamma && beta && out && idx && mean && rstd, "bn_pool_fwd: missing tensor");
+    const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+    wgs::bn_relu_pool_fwd_kernel<<<wgs::bn_quad_blocks(total, C / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+        y, sum, sumsq, N, H, W, C, eps, momentum, gamma, beta, out, (unsigned char*)idx, (__nv_bfloat16*)outs, mean, rstd,
+        running_mean, running_var);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_bn_pool_bwd_reduce(const float* dout, const void* idx, const float* y, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, int N, int H, int W, int C, float* sum_dz,
+                                      float* sum_dzx, void* stream) {
+    WGS_REQUIRE(wgs::bn_ok(C) && N > 0 && H > 0 && W > 0, "bn_pool_bwd_reduce: C must be a multiple of 4 with C/4 dividing 256");
+    const size_t smem = 2 * (size_t)(wgs::BN_THREADS / (C / 4)) * C * sizeof(float);
+    WGS_REQUIRE((long long)N * H * W < (1ll << 31), "bn_pool_bwd_reduce: too many rows");
+    wgs::bn_pool_bwd_reduce_kernel<<<wgs::bn_red_blocks((long long)N * ((H + 1) / 2) * ((W + 1) / 2), C), wgs::BN_THREADS, smem, (cudaStream_t)stream>>>(
+        dout, (const unsigned char*)idx, y, mean, rstd, gamma, beta, N, H, W, C, sum_dz, sum_dzx);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wgs_bn_pool_bwd_apply(const float* dout, const void* idx, const float* y, const float* mean, const float* rstd,
+                                     const float* gamma, const float* beta, const float* sum_dz, const float* sum_dzx, int N,
+                                     int H, int W, int C, void* dys, void* stream) {
+    WGS_REQUIRE(wgs::bn_ok(C) && N > 0 && H > 0 && W > 0 && dys, "bn_pool_bwd_apply: C must be a multiple of 4 with C/4 dividing 256");
+    WGS_REQUIRE((long long)N * H * W < (1ll << 31), "bn_pool_bwd_apply: too many rows");
+    const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+    wgs::bn_pool_bwd_apply_kernel<<<wgs::bn_quad_blocks(total, C / 4, wgs::BN_THREADS), wgs::BN_THREADS, 0, (cudaStream_t)stream>>>(
+        dout, (const unsigned char*)idx, y, mean, rstd, gamma, beta, sum_dz, sum_dzx, N, H, W, C, (__nv_bfloat16*)dys);
+    wgs::count_launch();
+    WGS_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int wgs_maxpool3s2_fwd(const float* z, int N, int H, int W, int C, float* out, void* idx, void* outs,
                                   void* stream) {

@@ -102,6 +102,28 @@ __device__ __forceinline__ void warp_store_rows64(uint32_t stg_s, int lane, cons
     __syncwarp();
 }
 
+
+// Phase-packed output whose groups are narrower than a 16-channel block on a DENSE few-channel NHWC tensor (out_sx == GSZ,
+// two phases per row): the stem's data gradient, [N, H, W, 3] or [N, H, W, 6].  Column cc of the accumulator row belongs
+// to output row gy = cc / (2*GSZ) at float offset cc % (2*GSZ) from the row's first pixel - constant divisors, staged
+// constants, no per-element 64-bit address arithmetic (the generic element-wise path below made this launch
+// epilogue-bound: 0.46 ms with the tensor pipe 24 % active).
+template <int GSZ>
+__device__ __forceinline__ void small_group_store(const float (&v)[16], int c, int co, int cout, float* dst, long long out_sy,
+                                                  bool lane_ok, int py0, int out_h, uint32_t ep_s, int BN, float nz, int act) {
+    constexpr int RUN = 2 * GSZ;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int cc = co + i;
+        if (cc < cout) {
+            const int gy = cc / RUN, rem = cc - gy * RUN;
+            float r = fmaf(v[i], ptx::lds32(ep_s + (uint32_t)(c + i) * 4u), nz) + ptx::lds32(ep_s + (uint32_t)(BN + c + i) * 4u);
+            r = apply_act(r, act);
+            if (lane_ok && py0 + gy < out_h) dst[(long long)gy * out_sy + rem] = r;
+        }
+    }
+}
+
 // Epilogue shared by the tensor-core conv kernels (executed by warps 2..5, threads 64..191).
 template <bool FUSED, bool STACK>
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep, uint64_t* acc_bar,
@@ -229,6 +251,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
             }
+        } else if (!g_uniform && cs && !p.accumulate && p.group_w == 2 && p.out_sx == gsz && (gsz == 3 || gsz == 6) &&
+                   px0 + 2 <= p.out_w) {
+            if (gsz == 3) small_group_store<3>(v, c, co, p.cout, dst, p.out_sy, lane_ok, py0, p.out_h, ep_s, BN, nz, p.act);
+            else small_group_store<6>(v, c, co, p.cout, dst, p.out_sy, lane_ok, py0, p.out_h, ep_s, BN, nz, p.act);
+            continue;
         } else if (!g_uniform) {
             // phase-packed output whose groups are narrower than a 16-channel block (e.g. the 6-channel stem data
             // gradient): element-wise destination, written here
@@ -940,7 +967,20 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     // Cluster split-K for tiny-M, deep-K launches: widest N tile (math-bound MMAs, one patch load per tile), then as many
     // K splits as fill about two CTAs per SM (<= 8: portable cluster size)
     p.ksplit = 1;
-    if (splitk_on && !stack && d->force_bn == 0 && d->group_size == 0 && k_blocks_total(d) >= 16 &&
+    if (splitk_on && d->split_k == 2) {
+        // geometry-only decision (frozen generators): the split depends on the feature-map size, channel and tap counts
+        // alone, never on the batch, so an image computed alone or inside any batch goes through the same sums in the same
+        // order.  Maps up to 16 x 16 (StyleGAN2 / ProgGAN / BigGAN layers at 4^2 .. 16^2: 8 - 64 CTAs of 144 dependent
+        // stages each, ~60 us per launch whatever the batch)
+        if (!stack && d->force_bn == 0 && d->group_size == 0 && k_blocks_total(d) >= 16 && d->grid_h * d->grid_w <= 256) {
+            const int wide = std::min(256, (d->cout + 15) / 16 * 16);
+            const int tiles1 = p.tiles_x * p.tiles_y * ceil_div(d->cout, wide);
+            int ks = 1;
+            while (ks < 8 && tiles1 * ks * 2 <= 64 && k_blocks_total(d) / (ks * 2) >= 4) ks *= 2;
+            while (ks > 1 && (wide % (16 * ks)) != 0) ks /= 2;
+            if (ks > 1) { BN = wide; p.ksplit = ks; }
+        }
+    } else if (splitk_on && !stack && d->force_bn == 0 && d->group_size == 0 && k_blocks_total(d) >= 16 &&
         (BN <= 64 || m_tiles * ceil_div(d->cout, BN) * 2 <= num_sms())) {   // narrow-N tiles or under half a wave
         const int wide = std::min(256, (d->cout + 15) / 16 * 16);
         const int tiles = m_tiles * ceil_div(d->cout, wide);

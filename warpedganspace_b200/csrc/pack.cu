@@ -202,8 +202,11 @@ __device__ __forceinline__ float pack_fetch(const wgs_pack_problem& q, int t, in
         case 1: return __ldg(q.src + ((size_t)k * q.ci + row) * T + t);
         case 2: return __ldg(q.src + ((size_t)row * q.ci + k % q.ci) * T + k / q.ci);
         case 3: {
+            // (ci_src > 0: only input channels [ci_off, ci_off + ci) of a [Co, ci_src, kh, kw] weight - the stem's data
+            // gradient is needed for the shifted image's 3 of 6 channels only)
             const int g = row / q.ci, c = row - g * q.ci, tap = q.idx[t * q.G + g];
-            return tap < 0 ? 0.f : __ldg(q.src + ((size_t)k * q.ci + c) * T + tap);
+            const int cs = q.ci_src > 0 ? q.ci_src : q.ci;
+            return tap < 0 ? 0.f : __ldg(q.src + ((size_t)k * cs + c + q.ci_off) * T + tap);
         }
         default: {      // 4: stride-2 conv as a stride-1 conv over the 2x2 space-to-depth input: k = (py*2 + px)*ci + c,
                         // tap t = ty*S + tx covers kernel row ky = 2*ty + py - G (G = kernel offset), zero outside the kernel
@@ -286,8 +289,11 @@ extern "C" int wgs_pack_weights_group(const wgs_pack_problem* h_problems, int co
 // resident in shared memory - instead of an im2col that wrote 1280 B per output pixel (0.48 ms + a 0.25 ms GEMM at 1024^2).
 namespace wgs {
 __global__ void __launch_bounds__(256)
-s2d_pack_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out, int chunks) {
-    const int OH = H >> 1, OW = W >> 1, K = 4 * C;
+s2d_pack_split32_kernel(const float* __restrict__ x, const float* __restrict__ x2, int C1, int N, int H, int W, int C,
+                        __nv_bfloat16* __restrict__ out, int chunks) {
+    // channels [0, C1) come from x (row pitch C1), channels [C1, C) from x2 (row pitch C - C1): the Reconstructor's
+    // torch.cat([x1, x2], dim=1) (lib/reconstructor.py:72) folded into the pack
+    const int OH = H >> 1, OW = W >> 1, K = 4 * C, C2 = C - C1;
     const long long total = (long long)N * OH * OW * chunks * 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int g4 = (int)(i & 7);
@@ -304,7 +310,8 @@ s2d_pack_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C,
             float v = 0.f;
             if (k < K) {
                 const int ph = k / C, c = k - ph * C;
-                v = __ldg(x + (((long long)n * H + 2 * Y + (ph >> 1)) * W + 2 * X + (ph & 1)) * C + c);
+                const long long pix = ((long long)n * H + 2 * Y + (ph >> 1)) * W + 2 * X + (ph & 1);
+                v = c < C1 ? __ldg(x + pix * C1 + c) : __ldg(x2 + pix * C2 + (c - C1));
             }
             split_bf16(v, hi[j], lo[j]);
         }
@@ -315,13 +322,24 @@ s2d_pack_split32_kernel(const float* __restrict__ x, int N, int H, int W, int C,
 }
 }  // namespace wgs
 
-extern "C" int wgs_s2d_pack_split32(const float* x, int N, int H, int W, int C, void* out, void* stream) {
-    WGS_REQUIRE(N >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C >= 1, "s2d_pack: even H and W required");
+static int s2d_launch(const float* x, const float* x2, int C1, int N, int H, int W, int C, void* out, void* stream) {
     const int chunks = (4 * C + 31) / 32;
     const long long total = (long long)N * (H / 2) * (W / 2) * chunks * 8;
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)wgs::num_sms() * 32);
-    wgs::s2d_pack_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, (__nv_bfloat16*)out, chunks);
+    wgs::s2d_pack_split32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x2, C1, N, H, W, C, (__nv_bfloat16*)out, chunks);
     wgs::count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int wgs_s2d_pack_split32(const float* x, int N, int H, int W, int C, void* out, void* stream) {
+    WGS_REQUIRE(N >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C >= 1, "s2d_pack: even H and W required");
+    return s2d_launch(x, nullptr, C, N, H, W, C, out, stream);
+}
+
+extern "C" int wgs_s2d_pack_split32_pair(const float* x1, const float* x2, int N, int H, int W, int C1, int C2, void* out,
+                                         void* stream) {
+    WGS_REQUIRE(N >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C1 >= 1 && C2 >= 1, "s2d_pack_pair: even H and W required");
+    WGS_REQUIRE(x1 && x2, "s2d_pack_pair: two inputs required");
+    return s2d_launch(x1, x2, C1, N, H, W, C1 + C2, out, stream);
 }

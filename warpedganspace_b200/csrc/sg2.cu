@@ -94,7 +94,8 @@ linear_group_kernel(const __grid_constant__ LinearGroup g) {
             }
             if (q.mul) v *= __ldg(q.mul + (size_t)(b0 + lane) * q.mul_ld + o);
             float* dst = q.out + (size_t)(b0 + lane) * q.out_ld + o;
-            *dst = q.accumulate ? (*dst + v) : v;
+            if (q.accumulate == 2) atomicAdd(dst, v);          // several problems of one launch share this output (split-I)
+            else *dst = q.accumulate ? (*dst + v) : v;
         }
     }
 }
@@ -224,40 +225,55 @@ fir4_act_kernel(const float* __restrict__ y, float* __restrict__ out, int N, int
 // (A shared-memory tiled variant - window loaded once per block, horizontal pass out of shared memory - was measured
 // and dropped: the LDS + STS + barrier instructions it adds outweigh the L1 hits it removes, 202 vs 210 pairs/s.)
 
-// rgb[n,y,x,:] = bias + up2(prev)[n,y,x,:]  — initialises the ToRGB accumulator that the conv epilogue adds into
+// rgb[n,y,x,:] = bias + up2(prev)[n,y,x,:]  — initialises the ToRGB accumulator that the conv epilogue adds into.
+// One thread per FOUR consecutive output pixels of a row (W % 4 == 0): the 2 x 4 window of the half-resolution skip image
+// is read once (24 loads instead of 48) and the 12 outputs leave as three 128-bit stores.
 __global__ void rgb_init_kernel(const float* __restrict__ bias, const float* __restrict__ prev, float* __restrict__ rgb,
                                 int N, int H, int W, float k0, float k1, float k2, float k3) {
-    const long long total = (long long)N * H * W;
+    const int W4 = W >> 2;
+    const long long total = (long long)N * H * W4;
     const int h2 = H >> 1, w2 = W >> 1;
+    const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int xx = (int)(i % W);
-        const int yy = (int)((i / W) % H);
-        const int n = (int)(i / ((long long)W * H));
-        float o3[3] = {__ldg(bias), __ldg(bias + 1), __ldg(bias + 2)};
+        const int x0 = (int)(i % W4) * 4;
+        const int yy = (int)((i / W4) % H);
+        const int n = (int)(i / ((long long)W4 * H));
+        float o[12] = {b0, b1, b2, b0, b1, b2, b0, b1, b2, b0, b1, b2};
         if (prev) {
-            int ya, yb, xa, xb;
-            float wya, wyb, wxa, wxb;
+            int ya, yb;
+            float wya, wyb;
             if (yy & 1) { ya = (yy - 1) >> 1; yb = (yy + 1) >> 1; wya = k2; wyb = k0; }
             else        { ya = (yy >> 1) - 1; yb = yy >> 1;       wya = k3; wyb = k1; }
-            if (xx & 1) { xa = (xx - 1) >> 1; xb = (xx + 1) >> 1; wxa = k2; wxb = k0; }
-            else        { xa = (xx >> 1) - 1; xb = xx >> 1;       wxa = k3; wxb = k1; }
-            const int ys[2] = {ya, yb}, xs[2] = {xa, xb};
-            const float wy[2] = {wya, wyb}, wx[2] = {wxa, wxb};
+            const int ys[2] = {ya, yb};
+            const float wy[2] = {wya, wyb};
+            const int xb = (x0 >> 1) - 1;                       // window columns xb .. xb + 3
+            float col[4][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // vertically filtered
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 if (ys[a] < 0 || ys[a] >= h2) continue;
+                const float* row = prev + ((size_t)n * h2 + ys[a]) * w2 * 3;
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    if (xs[b] < 0 || xs[b] >= w2) continue;
-                    const float* pp = prev + (((size_t)n * h2 + ys[a]) * w2 + xs[b]) * 3;
-                    const float wgt = wy[a] * wx[b];
-                    o3[0] += wgt * __ldg(pp); o3[1] += wgt * __ldg(pp + 1); o3[2] += wgt * __ldg(pp + 2);
+                for (int j = 0; j < 4; ++j) {
+                    const int xc = xb + j;
+                    if (xc < 0 || xc >= w2) continue;
+                    col[j][0] += wy[a] * __ldg(row + xc * 3); col[j][1] += wy[a] * __ldg(row + xc * 3 + 1);
+                    col[j][2] += wy[a] * __ldg(row + xc * 3 + 2);
                 }
             }
+            // output x0 + p: even p -> columns (p/2, p/2 + 1) of the window with (k3, k1); odd p -> ((p+1)/2, (p+1)/2 + 1) with (k2, k0)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int ja = (p & 1) ? (p + 1) / 2 : p / 2;
+                const float wa = (p & 1) ? k2 : k3, wb = (p & 1) ? k0 : k1;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o[p * 3 + c] += wa * col[ja][c] + wb * col[ja + 1][c];
+            }
         }
-        float* d = rgb + i * 3;
-        d[0] = o3[0]; d[1] = o3[1]; d[2] = o3[2];
+        float4* d = reinterpret_cast<float4*>(rgb + (((size_t)n * H + yy) * W + x0) * 3);
+        d[0] = make_float4(o[0], o[1], o[2], o[3]);
+        d[1] = make_float4(o[4], o[5], o[6], o[7]);
+        d[2] = make_float4(o[8], o[9], o[10], o[11]);
     }
 }
 
@@ -460,7 +476,8 @@ extern "C" int wgs_sg2_rgb_init(const float* bias, const float* prev, float* rgb
     WGS_REQUIRE(!prev || (H % 2 == 0 && W % 2 == 0), "rgb_init: skip needs even output size");
     const float k0 = h_taps4 ? h_taps4[0] : 0.25f, k1 = h_taps4 ? h_taps4[1] : 0.75f, k2 = h_taps4 ? h_taps4[2] : 0.75f,
                 k3 = h_taps4 ? h_taps4[3] : 0.25f;
-    const long long total = (long long)N * H * W;
+    WGS_REQUIRE(W % 4 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0, "rgb_init: width must be a multiple of 4, output 16-byte aligned");
+    const long long total = (long long)N * H * (W / 4);
     rgb_init_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16), 256, 0, (cudaStream_t)stream>>>(
         bias, prev, rgb, N, H, W, k0, k1, k2, k3);
     count_launch();

@@ -233,7 +233,7 @@ class Reconstructor(nn.Module):
         r = self.features_extractor
         if self.fused and self.training:
             from .resnet_fused import ResNetFeatures
-            return ResNetFeatures.apply(x, r, *ResNetFeatures.param_list(r))
+            return ResNetFeatures.apply(x, None, r, *ResNetFeatures.param_list(r))
         x = F.relu(r.bn1(conv2d(x, r.conv1.weight, None, 2, 3)))
         x = F.max_pool2d(x, 3, 2, 1)
         for li in range(1, 5):
@@ -247,6 +247,12 @@ class Reconstructor(nn.Module):
         return x.mean(dim=[2, 3])
 
     def forward(self, x1, x2):
+        if self.reconstructor_type == 'ResNet' and self.fused and self.training and x1.shape == x2.shape:
+            # torch.cat([x1, x2], dim=1) (lib/reconstructor.py:72) folded into the stem's operand pack
+            from .resnet_fused import ResNetFeatures
+            r = self.features_extractor
+            f = ResNetFeatures.apply(x1, x2, r, *ResNetFeatures.param_list(r))
+            return self.path_indices(f), self.shift_magnitudes(f).squeeze()
         x = torch.cat([x1, x2], dim=1).contiguous(memory_format=torch.channels_last)
         f = self.features(x)
         return self.path_indices(f), self.shift_magnitudes(f).squeeze()

@@ -92,15 +92,17 @@ def _bn_backward(dz, z, y, stats, bn, relu, want_res, pool, grads):
     return dys, dres
 
 
-def _pack_all(net):
-    """One grouped launch: {(weight, 'fwd' | 'bwd'): packed}."""
+def _pack_all(net, stem_sub=None):
+    """One grouped launch: {(weight, 'fwd' | 'bwd'): packed}.  stem_sub = (offset, count): the stem's data-gradient pack
+    covers that slice of its input channels only (the shifted image of a pair)."""
     specs, keys = [], []
 
     def add(w, stride, padding, stem=False):
         wd = w.detach()
         specs.append((wd, C.PACK_S2D, padding) if stem else (wd, C.PACK_FWD, None))
         keys.append((id(w), 'fwd'))
-        specs.append((wd, C.PACK_MERGED_DGRAD, (stride, padding)) if stride > 1 else (wd, C.PACK_TRANSPOSED, None))
+        extra = (stride, padding) + (tuple(stem_sub) if (stem and stem_sub) else ())
+        specs.append((wd, C.PACK_MERGED_DGRAD, extra) if stride > 1 else (wd, C.PACK_TRANSPOSED, None))
         keys.append((id(w), 'bwd'))
 
     add(net.conv1.weight, 2, 3, stem=True)
@@ -111,6 +113,20 @@ def _pack_all(net):
             if hasattr(b, 'downsample'):
                 add(b.downsample[0].weight, b.stride, 0)
     return dict(zip(keys, C.pack_weights_group(specs)))
+
+
+def prepack(net, stem_sub, stream):
+    """Form every weight operand of the coming step on `stream` (a side stream forked from the current one) so that the
+    grouped pack - 0.17 ms that depends on nothing but the weights - runs underneath the RBF kernel / mapping network /
+    low-resolution generator layers, which leave most of the GPU idle.  ResNetFeatures.forward picks the result up (and
+    waits for it) when the slice matches."""
+    cur = torch.cuda.current_stream()
+    stream.wait_stream(cur)                      # the previous step's Adam update and last readers of the old packs are done
+    with torch.cuda.stream(stream):
+        packs = _pack_all(net, stem_sub)
+        done = torch.cuda.Event()
+        done.record(stream)
+    net._wgs_prepacked = (stem_sub, packs, done)
 
 
 _S2D_INDEX = {}
@@ -134,8 +150,11 @@ def _s2d_weight_grad(dws, ci, k, S, G):
 
 
 class ResNetFeatures(torch.autograd.Function):
-    """features = avgpool(resnet18_trunk(x));  inputs: x (logical NCHW, channels-last), net (the _ResNet18 module),
-    then every trainable tensor in `param_list(net)` order (so that autograd routes their gradients)."""
+    """features = avgpool(resnet18_trunk(cat(x, x2)));  inputs: x, x2 (logical NCHW, channels-last; x2 may be None), net
+    (the _ResNet18 module), then every trainable tensor in `param_list(net)` order (so that autograd routes their
+    gradients).  With two inputs the channel concatenation of lib/reconstructor.py:72 is folded into the stem's operand
+    pack, and when only x2 needs a gradient (the paired step: x1 = G(z) is detached) the stem's data gradient is formed
+    for x2's channels alone and returned as is - no cat, no slice copies."""
 
     @staticmethod
     def param_list(net):
@@ -148,13 +167,25 @@ class ResNetFeatures(torch.autograd.Function):
         return ps
 
     @staticmethod
-    def forward(ctx, x, net, *params):
-        if not x.is_cuda:
+    def forward(ctx, x, x2, net, *params):
+        if not x.is_cuda or (x2 is not None and not x2.is_cuda):
             raise RuntimeError('Reconstructor runs on CUDA tensors only (no CPU fallback); got %s' % x.device)
         tape = {}
-        n, ci, h, w = x.shape
+        n, c1, h, w = x.shape
+        c2 = x2.shape[1] if x2 is not None else 0
+        ci = c1 + c2
         x_nhwc = x.permute(0, 2, 3, 1).contiguous()
-        packs = _pack_all(net)
+        x2_nhwc = x2.permute(0, 2, 3, 1).contiguous() if x2 is not None else None
+        ctx.need_dx = (ctx.needs_input_grad[0], x2 is not None and ctx.needs_input_grad[1])
+        ctx.split = (c1, c2)
+        stem_sub = (c1, c2) if ctx.need_dx == (False, True) else None
+        pre = getattr(net, '_wgs_prepacked', None)
+        net._wgs_prepacked = None
+        if pre is not None and pre[0] == stem_sub:
+            packs = pre[1]
+            torch.cuda.current_stream().wait_event(pre[2])
+        else:
+            packs = _pack_all(net, stem_sub)
         bns = _bn_list(net)
         pool = _Pool(sum(2 * ((b.num_features + 3) // 4 * 4) for b in bns), x.device)
 
@@ -167,19 +198,25 @@ class ResNetFeatures(torch.autograd.Function):
         w1 = net.conv1.weight
         co, _, kh, kw = w1.shape
         oh, ow = (h + 6 - kh) // 2 + 1, (w + 6 - kw) // 2 + 1
-        xs2d = C.s2d_pack_split32(x_nhwc)
+        xs2d = C.s2d_pack_split32(x_nhwc, x2_nhwc)
         taps, S = C.s2d_taps(kh, 3)
         y0 = torch.empty(n, oh, ow, co, device=x.device, dtype=torch.float32)
         C.conv_taps(xs2d, packs[(id(w1), 'fwd')], taps, y0, grid=(oh, ow), cin=kh * kw * ci,
                     algo_macs_per_pixel=kh * kw * ci * co)
-        z0, _, st0 = _bn_forward(y0, net.bn1, None, True, False, pool)
+        # bn1 + relu + maxpool in one pass over y0: the normalised 512^2 activation is never stored
+        bn1 = net.bn1
+        s0, s1 = pool.take(co), pool.take(co)
+        _lib.call('wgs_bn_stats', _lib.ptr(y0), n * oh * ow, co, _lib.ptr(s0), _lib.ptr(s1), _lib.stream())
+        st0 = torch.empty(2, co, device=x.device, dtype=torch.float32)
         ph, pw = (oh + 1) // 2, (ow + 1) // 2
         cur = torch.empty(n, ph, pw, co, device=x.device, dtype=torch.float32)             # NHWC fp32
         pool_idx = torch.empty(n, ph, pw, co, device=x.device, dtype=torch.uint8)
         cur_s = torch.empty(n, ph, pw, C.chunks_of(co), 64, device=x.device, dtype=torch.bfloat16)
-        _lib.call('wgs_maxpool3s2_fwd', _lib.ptr(z0), n, oh, ow, co, _lib.ptr(cur), _lib.ptr(pool_idx), _lib.ptr(cur_s),
-                  _lib.stream())
-        tape['stem'] = (xs2d, y0, z0, st0, pool_idx, (n, ci, h, w))
+        _lib.call('wgs_bn_pool_fwd', _lib.ptr(y0), _lib.ptr(s0), _lib.ptr(s1), n, oh, ow, co, float(bn1.eps),
+                  float(bn1.momentum), _lib.ptr(bn1.weight.detach()), _lib.ptr(bn1.bias.detach()), _lib.ptr(cur),
+                  _lib.ptr(pool_idx), _lib.ptr(cur_s), _lib.ptr(st0[0]), _lib.ptr(st0[1]), _lib.ptr(bn1.running_mean),
+                  _lib.ptr(bn1.running_var), _lib.stream())
+        tape['stem'] = (xs2d, y0, st0, pool_idx, (n, ci, h, w))
         tape['blocks'] = []
         for li in range(1, 5):
             for b in getattr(net, 'layer%d' % li):
@@ -200,7 +237,6 @@ class ResNetFeatures(torch.autograd.Function):
         tape['final_shape'] = cur.shape
         tape['packs'] = packs
         ctx.tape, ctx.net = tape, net
-        ctx.need_dx = ctx.needs_input_grad[0]
         return feat
 
     @staticmethod
@@ -213,8 +249,26 @@ class ResNetFeatures(torch.autograd.Function):
         n, fh, fw, fc = tape['final_shape']
         dcur = (dfeat.contiguous().view(n, 1, 1, fc) / float(fh * fw)).expand(n, fh, fw, fc).contiguous()
 
+        # Weight gradients hang off the data-gradient chain: nothing on the way back to the generator waits for them.
+        # With a side stream from the trainer (net._wgs_wgrad_stream, low priority) they are launched there as soon as
+        # their operands exist and fill whatever the main chain leaves idle; operands are kept alive in net._wgs_keep until
+        # the trainer joins the stream (the caching allocator knows nothing about this second reader).
+        side = getattr(net, '_wgs_wgrad_stream', None)
+        keep = []
+        if side is not None:
+            net._wgs_keep = keep
+
         def wgrad(xs, dys, wt, stride, padding):
-            grads[wt] = WG.conv_wgrad(xs, dys, tuple(wt.shape), stride, padding, out=_flat(wt))
+            out = _flat(wt)
+            if side is None or out is None:
+                grads[wt] = WG.conv_wgrad(xs, dys, tuple(wt.shape), stride, padding, out=out)
+                return
+            ready = torch.cuda.Event()
+            ready.record()
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                WG.conv_wgrad(xs, dys, tuple(wt.shape), stride, padding, out=out)
+            keep.append((xs, dys))
 
         def dgrad(dys, wt, in_hw, stride, padding, out=None, accumulate=False):
             return conv_dgrad(dys, wt, in_hw, stride, padding, out=out, accumulate=accumulate, packed=packs[(id(wt), 'bwd')],
@@ -236,19 +290,44 @@ class ResNetFeatures(torch.autograd.Function):
             else:
                 dx = dgrad(dy1s, b.conv1.weight, (xh, xw), s, 1, out=dres, accumulate=True)     # dx = dres + conv^T(dy1)
             dcur = dx
-        xs2d, y0, z0, st0, pool_idx, (n, ci, h, w) = tape['stem']
-        dz0 = torch.empty_like(z0)
+        xs2d, y0, st0, pool_idx, (n, ci, h, w) = tape['stem']
         dcur = dcur.contiguous()           # (held in a name: _lib.ptr() of a temporary would free it before the launch)
-        _lib.call('wgs_maxpool3s2_bwd', _lib.ptr(dcur), _lib.ptr(pool_idx), z0.shape[0], z0.shape[1], z0.shape[2],
-                  z0.shape[3], _lib.ptr(dz0), _lib.stream())
-        dy0s, _ = _bn_backward(dz0, z0, y0, st0, net.bn1, True, False, pool, grads)
+        bn1 = net.bn1
+        _, oh, ow, c0 = y0.shape
+        d_beta, d_gamma = _flat(bn1.bias), _flat(bn1.weight)
+        if d_beta is None or d_gamma is None:
+            d_beta, d_gamma = pool.take(c0), pool.take(c0)
+            grads[bn1.weight], grads[bn1.bias] = d_gamma, d_beta
+        g1, b1 = bn1.weight.detach(), bn1.bias.detach()
+        _lib.call('wgs_bn_pool_bwd_reduce', _lib.ptr(dcur), _lib.ptr(pool_idx), _lib.ptr(y0), _lib.ptr(st0[0]), _lib.ptr(st0[1]),
+                  _lib.ptr(g1), _lib.ptr(b1), n, oh, ow, c0, _lib.ptr(d_beta), _lib.ptr(d_gamma), _lib.stream())
+        dy0s = torch.empty(n, oh, ow, C.chunks_of(c0), 64, device=y0.device, dtype=torch.bfloat16)
+        _lib.call('wgs_bn_pool_bwd_apply', _lib.ptr(dcur), _lib.ptr(pool_idx), _lib.ptr(y0), _lib.ptr(st0[0]), _lib.ptr(st0[1]),
+                  _lib.ptr(g1), _lib.ptr(b1), _lib.ptr(d_beta), _lib.ptr(d_gamma), n, oh, ow, c0, _lib.ptr(dy0s), _lib.stream())
         w1 = net.conv1.weight
         co, _, kh, kw = w1.shape
         # weight gradient in the space-to-depth form [co, 4*ci, S, S], gathered back to [co, ci, kh, kw]
         S, a_min, G = C.s2d_geometry(kh, 3)
-        dws = WG.conv_wgrad(xs2d, dy0s, (co, 4 * ci, S, S), 1, -a_min)
-        grads[w1] = _s2d_weight_grad(dws, ci, kh, S, G)
-        dx = dgrad(dy0s, w1, (h, w), 2, 3).permute(0, 3, 1, 2) if ctx.need_dx else None
+        flat1 = _flat(w1)
+        if side is not None and flat1 is not None:
+            ready = torch.cuda.Event()
+            ready.record()
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                dws = WG.conv_wgrad(xs2d, dy0s, (co, 4 * ci, S, S), 1, -a_min)
+                flat1.add_(_s2d_weight_grad(dws, ci, kh, S, G))
+            keep.append((xs2d, dy0s))
+        else:
+            dws = WG.conv_wgrad(xs2d, dy0s, (co, 4 * ci, S, S), 1, -a_min)
+            grads[w1] = _s2d_weight_grad(dws, ci, kh, S, G)
+        dx1 = dx2 = None
+        c1, c2 = ctx.split
+        if ctx.need_dx == (False, True):
+            dx2 = C.conv_dgrad_merged(dy0s, w1, (h, w), 2, 3, w_merged=packs[(id(w1), 'bwd')], ci_sub=(c1, c2)).permute(0, 3, 1, 2)
+        elif ctx.need_dx[0] or ctx.need_dx[1]:
+            dx = dgrad(dy0s, w1, (h, w), 2, 3).permute(0, 3, 1, 2)
+            dx1 = dx[:, :c1] if ctx.need_dx[0] else None
+            dx2 = dx[:, c1:] if ctx.need_dx[1] else None
         ctx.tape = None
         plist = ResNetFeatures.param_list(net)
-        return (dx, None) + tuple(grads.get(p) for p in plist)
+        return (dx1, dx2, None) + tuple(grads.get(p) for p in plist)

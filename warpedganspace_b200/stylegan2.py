@@ -198,8 +198,8 @@ class Generator(nn.Module):
         rows are taped / back-propagated.  Returns (img_plain, img_shifted) as logical NCHW."""
         b = w_plain.shape[0]
         w_all = torch.cat([w_plain.detach().float(), w_shifted.float()], dim=0).contiguous()
-        img = _PairFn.apply(self, w_all, b).permute(0, 3, 1, 2)
-        return img[:b], img[b:]
+        img_plain, img_shifted = _PairFn.apply(self, w_all, b)                 # NHWC halves of one buffer
+        return img_plain.permute(0, 3, 1, 2), img_shifted.permute(0, 3, 1, 2)
 
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 input_is_latent=False, noise=None, randomize_noise=False):
@@ -380,7 +380,7 @@ def synthesis(G, w, tape=None, grad_from=0):
             if 'w_up' in e:
                 y = C.conv_transpose2d_s2_merged(xs, e['w_up'], 3, e['co'])    # [B, 2h+1, 2w+1, Co] raw
             else:
-                y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3)
+                y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3, split_k=2)
             _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(a), n, 2 * h + 1, 2 * wd + 1, oh, ow, e['co'], 1,
                       _TAPS, _lib.ptr(demod[li]), _lib.ptr(e['bias']), _lib.ptr(noise), e['noise_w'], 3,
                       _lib.ptr(xs_next), ctypes.c_void_p(s_next.data_ptr()), s_next.stride(0), g0, st())
@@ -394,7 +394,7 @@ def synthesis(G, w, tape=None, grad_from=0):
                       _lib.ptr(wm), n, e['co'], r['scale'], st())
             C.conv2d(xs, e['w_fwd'], 3, 3, padding=1, out=a, no_f32=a is None, alpha=demod[li], beta=e['bias'],
                      noise=noise, noise_w=e['noise_w'], act=3, out_split=xs_next, split_scale=s_next, out_from_n=g0,
-                     rgb_w=wm, rgb_out=rgb)
+                     rgb_w=wm, rgb_out=rgb, split_k=2)
             skip = rgb
         if tape is not None:
             tape['acts'].append(a[g0:])
@@ -462,10 +462,10 @@ def synthesis_backward(G, tape, dimg):
             gs = torch.empty(n, h + 1, wd + 1, co // 32, 64, device=dev, dtype=torch.bfloat16)
             _lib.call('wgs_fir4_act', _lib.ptr(dpre), None, n, h, wd, h + 1, wd + 1, co, 2, _TAPS,
                       _lib.ptr(demod[li]), None, None, 0.0, 0, _lib.ptr(gs), None, 0, 0, st())
-            dx = C.conv2d(gs, e['w_bwd'], 3, 3, stride=2, padding=0, cout=e['ci'])       # [n, hi, wi, ci]
+            dx = C.conv2d(gs, e['w_bwd'], 3, 3, stride=2, padding=0, cout=e['ci'], split_k=2)       # [n, hi, wi, ci]
             assert dx.shape[1] == hi and dx.shape[2] == wi
         else:
-            dx = C.conv2d(gs, e['w_bwd'], 3, 3, padding=1, cout=e['ci'])
+            dx = C.conv2d(gs, e['w_bwd'], 3, 3, padding=1, cout=e['ci'], split_k=2)
         # demodulation: d = rsqrt(scale^2 sum_i s_i^2 Wsq[o,i] + eps)  ->  ds_i += s_i * sum_o (-dd_o d_o^3 scale^2) Wsq[o,i]
         # (deferred: all layers in one grouped launch after the loop; every writer of ds_all accumulates)
         s_e, ds_e = sl(s_all, e), sl(ds_all, e)
@@ -477,8 +477,13 @@ def synthesis_backward(G, tape, dimg):
                       vp(ds_e), ds_e.stride(0), n, pin, e['ci'], st())
         dx_up, up_e = dx, e
     _linear_group(demod_bwd, B)
-    dw = torch.empty(B, G.style_dim, device=dev, dtype=torch.float32)
-    _linear(ds_all, P['mod_w_t'], None, dw, wscale=1.0 / math.sqrt(G.style_dim))
+    # dw = ds_all @ mod_w (512 outputs over ~9000 style channels): split along the contraction into chunks that atomically
+    # share the output - one warp per output streaming a 35 KB weight row left this launch at 128 CTAs / 122 us
+    dw = torch.zeros(B, G.style_dim, device=dev, dtype=torch.float32)
+    sum_c, step = P['sum_c'], 1024
+    parts = [_problem(ds_all[:, lo: min(sum_c, lo + step)], P['mod_w_t'][:, lo: min(sum_c, lo + step)], dw,
+                      wscale=1.0 / math.sqrt(G.style_dim), accumulate=2) for lo in range(0, sum_c, step)]
+    _linear_group(parts, B)
     return dw
 
 
@@ -541,19 +546,24 @@ class _SynthesisFn(torch.autograd.Function):
 
 
 class _PairFn(torch.autograd.Function):
+    """Both halves of the batched pass as separate outputs: the gradient of the shifted half arrives as it is (no
+    zero-padded full-batch gradient, no slice copies)."""
+
     @staticmethod
     def forward(ctx, G, w_all, n_plain):
         need = ctx.needs_input_grad[1]
         tape = {} if need else None
         img = synthesis(G, w_all.detach(), tape, grad_from=n_plain)
         ctx.G, ctx.tape, ctx.n_plain, ctx.rows = G, tape, n_plain, w_all.shape[0]
-        return img
+        plain, shifted = img[:n_plain], img[n_plain:]
+        ctx.mark_non_differentiable(plain)
+        return plain, shifted
 
     @staticmethod
-    def backward(ctx, dimg):
-        if ctx.tape is None:
+    def backward(ctx, _dplain, dimg):
+        if ctx.tape is None or dimg is None:
             return None, None, None
-        dw = synthesis_backward(ctx.G, ctx.tape, dimg[ctx.n_plain:])
+        dw = synthesis_backward(ctx.G, ctx.tape, dimg)
         ctx.tape = None
         full = dw.new_zeros(ctx.rows, dw.shape[1])
         full[ctx.n_plain:] = dw

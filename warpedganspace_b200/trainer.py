@@ -13,6 +13,7 @@ Differences from the reference loop, none of which change the numbers it produce
 Train-mode BatchNorm in R uses per-rank batch statistics, as the reference's DataParallel replicas do.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -105,10 +106,40 @@ class PairedTrainer:
             with torch.no_grad():
                 wdist.broadcast_([self.flat_s.flat, self.flat_r.flat] + [b for b in self.R.buffers()], src=0, group=self.pg)
 
+    # Side streams (forked from / joined to the current stream with events, so the same code is captured into the CUDA graph):
+    #   _side : R's weight-gradient kernels, then R's gradient all-reduce, then (inside step()) R's Adam update - all of it
+    #           underneath the generator's data-gradient pass; joined before forward_backward returns.  Default (= lowest)
+    #           priority; the graph is captured on a high-priority stream so that this work only fills what the main chain
+    #           leaves idle;
+    #   _pack : the grouped weight pack of R at the start of the step, underneath the RBF / mapping / low-resolution layers.
+    # WGS_SIDE_STREAMS=0 keeps everything on one stream (A/B switch).
+    _side = None
+    _pack = None
+    _side_busy = False          # work is in flight on _side
+    _r_reduced = False          # R's gradient all-reduce of this step has been issued
+    _r_stepped = False          # R's Adam update of this step has been issued
+    _early_adam = False         # step(): R's Adam update may run as soon as R's gradients are final
+
+    def _fused_resnet(self):
+        return (os.environ.get('WGS_SIDE_STREAMS', '1') != '0' and getattr(self.R, 'reconstructor_type', None) == 'ResNet'
+                and getattr(self.R, 'fused', False))
+
+    def _streams(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+            self._pack = torch.cuda.Stream()
+        return self._side, self._pack
+
     def forward_backward(self, z, indices, magnitudes):
         """One forward + backward; gradients land in the flat buffers.  Returns a dict of device tensors."""
         self.flat_s.zero_grad()
         self.flat_r.zero_grad()
+        if self._fused_resnet():
+            from . import resnet_fused
+            side, pack = self._streams()
+            net = self.R.features_extractor
+            net._wgs_wgrad_stream = side
+            resnet_fused.prepack(net, (self.R.channels, self.R.channels), pack)
         where = self.G.get_w(z).detach() if self.shift_in_w_space else z            # lib/trainer.py:236
         shift = self.S.warp(indices, where, magnitudes)                              # :235
         if hasattr(self.G, 'forward_pair'):
@@ -128,43 +159,64 @@ class PairedTrainer:
         loss.backward()                                                              # R's leg of :250
         self._start_r_reduce()
         img_shifted.backward(x2.grad)                                                # G data-gradient + RBF leg
+        self._join_side()
         acc = (logits.argmax(dim=1) == indices).float().mean()
         return dict(loss=loss.detach(), cls=cls.detach(), reg=reg.detach(), accuracy=acc, logits=logits.detach(),
                     pred=pred.detach(), shift=shift.detach(), img=img.detach(), img_shifted=img_shifted.detach())
 
-    _side = None
-    _r_reduce_pending = False
-
     def _start_r_reduce(self):
-        """Sum R's flat gradient over ranks on a side stream (forked from / joined to the current stream with events, so
-        the same code is captured into the CUDA graph)."""
-        if self.world <= 1:
+        """After R's leg of the backward pass: on the side stream (behind R's weight-gradient kernels, which already run
+        there) sum R's flat gradient over ranks and, inside step(), apply R's Adam update, while the main stream goes on
+        with the generator's data-gradient pass."""
+        fused = self._fused_resnet()
+        if self.world <= 1 and not fused:
             return
-        if self._side is None:
-            self._side = torch.cuda.Stream()
-        self._side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._side):
-            wdist.all_reduce_sum_([self.flat_r.grad], group=self.pg)
-        self._r_reduce_pending = True
+        side, _ = self._streams()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            if self.world > 1:
+                wdist.all_reduce_sum_([self.flat_r.grad], group=self.pg)
+                self._r_reduced = True
+            if self._early_adam:
+                self.flat_r.adam_step(self.lr_r, grad_scale=1.0 / self.world)          # lib/trainer.py:254
+                self._r_stepped = True
+        self._side_busy = True
+
+    def _join_side(self):
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_busy = False
+        net = getattr(self.R, 'features_extractor', None)
+        if net is not None:
+            net._wgs_keep = None                               # the side stream's readers are ordered before us now
+            net._wgs_wgrad_stream = None                       # a backward pass outside this engine stays on one stream
 
     def all_reduce_gradients(self):
         """Two NCCL all-reduces per step: R's (started inside forward_backward, overlapped) and S's (here)."""
         if self.world > 1:
-            if not self._r_reduce_pending:                     # gradients produced outside forward_backward
-                self._start_r_reduce()
+            if not self._r_reduced:                            # gradients produced outside forward_backward
+                wdist.all_reduce_sum_([self.flat_r.grad], group=self.pg)
             wdist.all_reduce_sum_([self.flat_s.grad], group=self.pg)
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._r_reduce_pending = False
+        self._r_reduced = False
 
     def optimizer_step(self):
         scale = 1.0 / self.world
         self.flat_s.adam_step(self.lr_s, grad_scale=scale)                            # :253
-        self.flat_r.adam_step(self.lr_r, grad_scale=scale)                            # :254
+        if not self._r_stepped:
+            self.flat_r.adam_step(self.lr_r, grad_scale=scale)                        # :254
+        self._r_stepped = False
 
     def step(self, z, indices, magnitudes, eager=False):
         if self._graph is not None and not eager:
             return self._replay(z, indices, magnitudes)
-        out = self.forward_backward(z, indices, magnitudes)
+        return self._full_step(z, indices, magnitudes)
+
+    def _full_step(self, z, indices, magnitudes):
+        self._early_adam = True
+        try:
+            out = self.forward_backward(z, indices, magnitudes)
+        finally:
+            self._early_adam = False
         self.all_reduce_gradients()
         self.optimizer_step()
         return out
@@ -201,22 +253,18 @@ class PairedTrainer:
 
     def _capture(self, z, indices, magnitudes, warmup):
         self._static_in = (z.clone(), indices.clone(), magnitudes.clone())
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
+        main = torch.cuda.Stream(priority=-1)         # above the side streams' (default = lowest) priority
+        main.wait_stream(torch.cuda.current_stream())
         try:
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(main):
                 for _ in range(warmup):
-                    self.forward_backward(*self._static_in)
-                    self.all_reduce_gradients()
-                    self.optimizer_step()
-            torch.cuda.current_stream().wait_stream(side)
+                    self._full_step(*self._static_in)
+            torch.cuda.current_stream().wait_stream(main)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
-            with torch.cuda.graph(graph):
-                out = self.forward_backward(*self._static_in)
-                self.all_reduce_gradients()
-                self.optimizer_step()
+            with torch.cuda.graph(graph, stream=main):
+                out = self._full_step(*self._static_in)
             self.launches_per_step = _lib.launch_count() - before
             self._static_out = out
             self._graph = graph
