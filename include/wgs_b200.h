@@ -196,6 +196,13 @@ typedef struct wgs_conv_desc {
      * bit) leave it 0 or pass 2 = split by GEOMETRY only (feature maps up to 16 x 16; the factor is a function of the map
      * size, channel and tap counts, never of the batch).  WGS_CONV_SPLITK=1 / 0 in the environment forces splitting on / off. */
     int split_k;
+    /* Train-mode BatchNorm statistics of the OUTPUT formed in the epilogue (the Reconstructor's convs, lib/reconstructor.py:54
+     * -> torchvision BasicBlock): stat_sum[c] += sum_pixels (out - shift[c]), stat_sumsq[c] += sum_pixels (out - shift[c])^2
+     * (atomics; zero them first; stat_shift may be NULL = 0).  Replaces a separate pass over the output (wgs_bn_stats).  Plain
+     * fp32 output only (no fused / phase-packed / accumulate epilogue), cout % 16 == 0, output maps of >= 128 pixels.      */
+    float* stat_sum;
+    float* stat_sumsq;
+    const float* stat_shift;
 } wgs_conv_desc;
 
 /* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls
@@ -321,10 +328,11 @@ int wgs_im2col_split32(const float* x, int N, int H, int W, int C, int kh, int k
 int wgs_bn_stats(const float* y, long long R, int C, float* sum, float* sumsq, void* stream);   /* accumulates sums of (y - y[0,c]) and (y - y[0,c])^2: shifted statistics, shift = first row */
 int wgs_bn_finalize(const float* sum, const float* sumsq, const float* shift, long long R, int C, float eps,
                     float momentum, float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
-/* bn_finalize folded into bn_act_fwd: mean / rstd are derived inside the apply kernel from the sums of wgs_bn_stats over the
- * same y (block 0 writes them out for the backward pass and updates the running statistics).                         */
-int wgs_bn_fwd_fused(const float* y, const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
-                     const float* gamma, const float* beta, const float* residual, int relu, float* z, void* zs,
+/* bn_finalize folded into bn_act_fwd: mean / rstd are derived inside the apply kernel from the shifted sums over the same y
+ * (block 0 writes them out for the backward pass and updates the running statistics).  shift = the [C] vector the sums were
+ * formed with (wgs_conv_desc.stat_shift, statistics from the conv epilogue) or NULL = row 0 of y (wgs_bn_stats).        */
+int wgs_bn_fwd_fused(const float* y, const float* sum, const float* sumsq, const float* shift, long long R, int C, float eps,
+                     float momentum, const float* gamma, const float* beta, const float* residual, int relu, float* z, void* zs,
                      float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
 int wgs_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                    const float* residual, int relu, float* z, void* zs, long long R, int C, void* stream);
@@ -342,8 +350,8 @@ int wgs_maxpool3s2_bwd(const float* dout, const void* idx, int N, int H, int W, 
  * the normalised activation is never stored.  fwd: y [N,H,W,C] + the shifted sums of wgs_bn_stats -> pooled out fp32, arg-max
  * table, optional split32 pack, mean / rstd (+ running statistics).  bwd: the pooled gradient is gathered through the arg-max
  * table, the ReLU mask re-derived from y; reduce accumulates sum dzr / sum dzr*xhat, apply writes split32(dy).            */
-int wgs_bn_pool_fwd(const float* y, const float* sum, const float* sumsq, int N, int H, int W, int C, float eps,
-                    float momentum, const float* gamma, const float* beta, float* out, void* idx, void* outs,
+int wgs_bn_pool_fwd(const float* y, const float* sum, const float* sumsq, const float* shift, int N, int H, int W, int C,
+                    float eps, float momentum, const float* gamma, const float* beta, float* out, void* idx, void* outs,
                     float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
 int wgs_bn_pool_bwd_reduce(const float* dout, const void* idx, const float* y, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, int N, int H, int W, int C, float* sum_dz,

@@ -426,3 +426,39 @@ print('ok')
                          capture_output=True, text=True, timeout=600,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0 and 'ok' in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
+STAT_CASES = [
+    # N, Ci, H, W, Co, k, stride, pad, split_k       kernel this lands on
+    (2, 128, 32, 32, 128, 3, 1, 1, 0),             # conv_tc, one tile per CTA
+    (2, 64, 64, 256, 64, 3, 1, 1, 0),              # multi-tile halo kernel, two chunks (statistics flushed after the last tile)
+    (1, 32, 128, 128, 32, 3, 1, 1, 0),             # multi-tile halo kernel, one chunk
+    (2, 64, 36, 40, 128, 3, 2, 1, 0),              # strided, ragged tiles (out-of-grid lanes must not count)
+    (2, 512, 16, 16, 512, 3, 1, 1, 1),             # cluster split-K: every rank reduces its own columns
+    (3, 64, 32, 32, 128, 1, 2, 0, 0),              # 1x1 / 2 shortcut conv
+]
+
+
+@pytest.mark.parametrize('case', STAT_CASES)
+def test_batchnorm_statistics_in_the_conv_epilogue(case):
+    """wgs_conv_desc.stat_sum / stat_sumsq / stat_shift: shifted first and second moments of the conv output per channel,
+    accumulated in the epilogue (train-mode BatchNorm of the Reconstructor without a separate pass over the output)."""
+    from warpedganspace_b200 import conv
+    N, Ci, H, W, Co, k, stride, pad, split_k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Ci, H, W, generator=g).cuda()
+    w = torch.randn(Co, Ci, k, k, generator=g).cuda() / (Ci * k * k) ** 0.5
+    shift = (0.3 * torch.randn(Co, generator=g)).cuda()
+    s0, s1 = torch.zeros(Co).cuda(), torch.zeros(Co).cuda()
+    out = conv.conv2d(conv.pack_split32(nhwc(x)), conv.pack_weights(w), k, k, stride=stride, padding=pad, cin=Ci,
+                      split_k=split_k, stats=(s0, s1, shift))
+    ref = F.conv2d(x, w, None, stride, pad)
+    assert rel(out, nhwc(ref)) < 2e-5
+    d = out.double() - shift.double()
+    assert rel(s0, d.sum(dim=(0, 1, 2))) < 1e-5
+    assert rel(s1, (d * d).sum(dim=(0, 1, 2))) < 1e-5
+    # no shift given = plain sums
+    s0.zero_(); s1.zero_()
+    out2 = conv.conv2d(conv.pack_split32(nhwc(x)), conv.pack_weights(w), k, k, stride=stride, padding=pad, cin=Ci,
+                       split_k=split_k, stats=(s0, s1, None))
+    assert rel(s0, out2.double().sum(dim=(0, 1, 2))) < 1e-5 and rel(s1, (out2.double() ** 2).sum(dim=(0, 1, 2))) < 1e-5

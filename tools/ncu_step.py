@@ -45,10 +45,11 @@ def conv_wrapped(*a, **k):
     finally:
         orig = saved
 C.conv_taps = conv_wrapped
-ONLY = set(sys.argv[3].split(',')) if len(sys.argv) > 3 else None
+ONLY = set(sys.argv[3].split(',')) if len(sys.argv) > 3 and sys.argv[3] else None
+MAX_MS = float(sys.argv[4]) if len(sys.argv) > 4 else 1e9          # only launches cheaper than this (the latency-bound ones)
 tr.step(*bs[2], eager=True)
 torch.cuda.synchronize()
-top = sorted([l for l in log if l[2] not in SKIP and (ONLY is None or l[2] in ONLY)], reverse=True)[:K]
+top = sorted([l for l in log if l[2] not in SKIP and (ONLY is None or l[2] in ONLY) and l[0] < MAX_MS], reverse=True)[:K]
 for ms, i, name in top:
     print('%4d %-28s %.3f ms' % (i, name, ms))
 print('all calls: %d, total %.2f ms' % (len(log), sum(l[0] for l in log)))

@@ -52,6 +52,7 @@ class ConvDesc(ctypes.Structure):
         ('out_from_n', ctypes.c_int), ('rgb_w', ctypes.c_void_p), ('rgb_out', ctypes.c_void_p),
         ('group_size', ctypes.c_int), ('group_w', ctypes.c_int), ('out_h', ctypes.c_int), ('out_w', ctypes.c_int),
         ('w_layout', ctypes.c_int), ('split_k', ctypes.c_int),
+        ('stat_sum', ctypes.c_void_p), ('stat_sumsq', ctypes.c_void_p), ('stat_shift', ctypes.c_void_p),
     ]
 
 
@@ -204,7 +205,7 @@ def pack_weights(w):
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
               alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None,
               out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None, groups=None,
-              algo_macs_per_pixel=None, split_k=False):
+              algo_macs_per_pixel=None, split_k=False, stats=None):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -232,6 +233,9 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
             assert split_scale.stride(1) == 1
             d.split_scale, d.split_scale_ld = split_scale.data_ptr(), split_scale.stride(0)
     d.out_from_n = out_from_n
+    if stats is not None:                        # (sum, sumsq, shift or None): BatchNorm statistics of the output, in the epilogue
+        d.stat_sum, d.stat_sumsq = stats[0].data_ptr(), stats[1].data_ptr()
+        d.stat_shift = stats[2].data_ptr() if stats[2] is not None else None
     d.split_k = int(split_k)                     # 0 off, 1 batch-dependent (Reconstructor), 2 geometry-only (frozen generators)
     if rgb_out is not None:
         assert rgb_w.is_contiguous() and rgb_out.is_contiguous()
@@ -408,7 +412,7 @@ def conv_dgrad_merged(dys, w, in_hw, stride, padding, out=None, accumulate=False
     return dx
 
 
-def conv_transpose2d_s2_merged(x_split, w_merged, k, co, out=None, cin=None):
+def conv_transpose2d_s2_merged(x_split, w_merged, k, co, out=None, cin=None, split_k=0):
     """F.conv_transpose2d(stride=2, padding=0) for a k x k kernel in ONE launch; w_merged from
     merged_phase_weights(w[Co, Ci, k*k], *_phase_plan('convT', k, k, 2, 0))."""
     n, h, w_, _, _ = x_split.shape
@@ -418,5 +422,6 @@ def conv_transpose2d_s2_merged(x_split, w_merged, k, co, out=None, cin=None):
         out = torch.empty(n, oh, ow, co, dtype=torch.float32, device=x_split.device)
     taps = [(sy, sx, i) for i, (sy, sx) in enumerate(shifts)]
     conv_taps(x_split, w_merged, taps, out, grid=((oh + 1) // 2, (ow + 1) // 2), out_step=(2, 2), cout=G * co,
-              groups=(co, 2), algo_macs_per_pixel=_real_blocks(idx, k * k) * co * (cin or x_split.shape[3] * 32), cin=cin)
+              groups=(co, 2), algo_macs_per_pixel=_real_blocks(idx, k * k) * co * (cin or x_split.shape[3] * 32), cin=cin,
+              split_k=split_k)
     return out

@@ -89,7 +89,7 @@ bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, c
                   int relu, float* __restrict__ z, __nv_bfloat16* __restrict__ zs, long long R, int C,
                   const float* __restrict__ sum, const float* __restrict__ sumsq, float eps, float momentum,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ running_mean,
-                  float* __restrict__ running_var) {
+                  float* __restrict__ running_var, const float* __restrict__ shift) {
     const int C4 = C >> 2;
     const long long total = R * C4;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -99,7 +99,9 @@ bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, c
         // fp32 is enough here: the sums are SHIFTED (bn_stats), so E[(y-s)^2] - E[y-s]^2 does not cancel catastrophically;
         // only block 0 redoes the moments in double for the published mean / rstd / running statistics
         const float4 su = __ldg(reinterpret_cast<const float4*>(sum + c)), sq = __ldg(reinterpret_cast<const float4*>(sumsq + c));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(y + c));
+        // the shift the sums were formed with: row 0 of y (wgs_bn_stats) or the caller's vector (statistics formed in the
+        // conv epilogue, wgs_conv_desc.stat_shift)
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift ? shift + c : y + c));
         if (blockIdx.x == 0 && threadIdx.x < C4) {
             double v0, v1, v2, v3;
             bn_moments(su.x, sq.x, sh.x, R, eps, m4.x, s4.x, v0);
@@ -268,20 +270,21 @@ extern "C" int wgs_bn_act_fwd(const float* y, const float* mean, const float* rs
     WGS_REQUIRE(bn_ok(C) && R > 0, "bn_act_fwd: C must be a multiple of 4 with C/4 dividing 256");
     bn_act_fwd_kernel<false><<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
         y, mean, rstd, gamma, beta, residual, relu, z, (__nv_bfloat16*)zs, R, C, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr,
-        nullptr, nullptr);
+        nullptr, nullptr, nullptr);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int wgs_bn_fwd_fused(const float* y, const float* sum, const float* sumsq, long long R, int C, float eps, float momentum,
-                                const float* gamma, const float* beta, const float* residual, int relu, float* z, void* zs,
-                                float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
+extern "C" int wgs_bn_fwd_fused(const float* y, const float* sum, const float* sumsq, const float* shift, long long R, int C,
+                                float eps, float momentum, const float* gamma, const float* beta, const float* residual, int relu,
+                                float* z, void* zs, float* mean, float* rstd, float* running_mean, float* running_var,
+                                void* stream) {
     WGS_REQUIRE(bn_ok(C) && R > 0, "bn_fwd_fused: C must be a multiple of 4 with C/4 dividing 256");
     WGS_REQUIRE(sum && sumsq && mean && rstd, "bn_fwd_fused: sums in, mean / rstd out are required");
     bn_act_fwd_kernel<true><<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
         y, nullptr, nullptr, gamma, beta, residual, relu, z, (__nv_bfloat16*)zs, R, C, sum, sumsq, eps, momentum, mean, rstd,
-        running_mean, running_var);
+        running_mean, running_var, shift);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
@@ -411,14 +414,14 @@ bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s
                         int N, int H, int W, int C, float eps, float momentum, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float* __restrict__ out, unsigned char* __restrict__ idx,
                         __nv_bfloat16* __restrict__ outs, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                        float* __restrict__ running_mean, float* __restrict__ running_var) {
+                        float* __restrict__ running_mean, float* __restrict__ running_var, const float* __restrict__ shift) {
     const int OH = (H + 1) / 2, OW = (W + 1) / 2, C4 = C >> 2;
     const long long R = (long long)N * H * W;
     const long long total = (long long)N * OH * OW * C4;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int c = (int)(i0 % C4) * 4;                                 // fixed per thread (host: stride % C4 == 0)
     const float4 su = __ldg(reinterpret_cast<const float4*>(sum + c)), sq = __ldg(reinterpret_cast<const float4*>(sumsq + c));
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(y + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift ? shift + c : y + c));
     float4 m4, s4;
     if (blockIdx.x == 0 && threadIdx.x < C4) {
         double v0, v1, v2, v3;
@@ -608,15 +611,15 @@ static int bn_quad_blocks(long long total, int C4, int threads) {
 
 }  // namespace wgs
 
-extern "C" int wgs_bn_pool_fwd(const float* y, const float* sum, const float* sumsq, int N, int H, int W, int C, float eps,
-                               float momentum, const float* gamma, const float* beta, float* out, void* idx, void* outs,
-                               float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
+extern "C" int wgs_bn_pool_fwd(const float* y, const float* sum, const float* sumsq, const float* shift, int N, int H, int W,
+                               int C, float eps, float momentum, const float* gamma, const float* beta, float* out, void* idx,
+                               void* outs, float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
     WGS_REQUIRE(wgs::bn_ok(C) && N > 0 && H > 0 && W > 0, "bn_pool_fwd: C must be a multiple of 4 with C/4 dividing 256");
     WGS_REQUIRE(y && sum && sumsq && gamma && beta && out && idx && mean && rstd, "bn_pool_fwd: missing tensor");
     const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
     wgs::bn_relu_pool_fwd_kernel<<<wgs::bn_quad_blocks(total, C / 4, 256), 256, 0, (cudaStream_t)stream>>>(
         y, sum, sumsq, N, H, W, C, eps, momentum, gamma, beta, out, (unsigned char*)idx, (__nv_bfloat16*)outs, mean, rstd,
-        running_mean, running_var);
+        running_mean, running_var, shift);
     wgs::count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

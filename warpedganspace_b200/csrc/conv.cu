@@ -61,6 +61,9 @@ struct ConvKernelParams {
     int coalesce;                            // stage epilogue stores through shared memory (coalesced 64-byte rows)
     int tiles_per_cta, x_groups;             // multi-tile halo kernel: consecutive x tiles handled by one CTA
     int w_cout;                              // rows of the weight tensor (stacked layout addressing, SIMT twin)
+    float* stat_sum;                         // BatchNorm statistics of the output (plain epilogue): shifted sum / sum of squares
+    float* stat_sumsq;
+    const float* stat_shift;
     signed char tap_dy[WGS_MAX_TAPS], tap_dx[WGS_MAX_TAPS];
     unsigned char tap_w[WGS_MAX_TAPS];
 };
@@ -124,12 +127,28 @@ __device__ __forceinline__ void small_group_store(const float (&v)[16], int c, i
     }
 }
 
+// Column sums of a 32 (lanes = pixels) x 16 (registers = channels) block by recursive halving: 16 shuffles instead of the 80 of
+// sixteen butterfly reductions.  Afterwards lane l holds the sum of channel ((l >> 1) & 15 with its bits reversed as below)
+// over all 32 lanes: channel = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of the lane index (both lanes of a pair hold the same value).
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2], d;
+    const bool u4 = lane & 16, u3 = lane & 8, u2 = lane & 4, u1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (u4 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, u4 ? v[i] : v[i + 8], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (u3 ? a[i + 4] : a[i]) + __shfl_xor_sync(0xffffffffu, u3 ? a[i] : a[i + 4], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c[i] = (u2 ? b[i + 2] : b[i]) + __shfl_xor_sync(0xffffffffu, u2 ? b[i] : b[i + 2], 4);
+    d = (u1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, u1 ? c[0] : c[1], 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 // Epilogue shared by the tensor-core conv kernels (executed by warps 2..5, threads 64..191).
 template <bool FUSED, bool STACK>
 __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_t tmem_base, float* ep, uint64_t* acc_bar,
                                               int warp, int lane, int n0, int oy0, int ox0, int co0,
                                               uint8_t* stg = nullptr, bool stage_consts = true, uint32_t parity = 0,
-                                              uint32_t peer_s = 0, int n_ranks = 0, int my_rank = 0) {
+                                              uint32_t peer_s = 0, int n_ranks = 0, int my_rank = 0, bool flush_stats = true) {
     // peer_s / n_ranks / my_rank: cluster split-K - every CTA of the cluster parks its partial accumulator at shared offset
     // peer_s in [column/4][row] float4 order; each rank then finishes BN / n_ranks of the columns (a reduce-scatter over
     // distributed shared memory: one rank summing everything serialised 0.9 MB of remote reads per tile and was slower
@@ -162,6 +181,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
             const bool ok = n_ok && cc < p.cout;
             ep[i] = (ok && p.alpha) ? __ldg(p.alpha + (size_t)n0 * p.cout + cc) : 1.f;
             ep[BN + i] = (ok && p.beta) ? __ldg(p.beta + cc) : 0.f;
+            if constexpr (!FUSED) {
+                if (p.stat_sum) {        // per-CTA accumulators of the BatchNorm statistics and the staged shift
+                    ep[2 * BN + i] = 0.f;
+                    ep[3 * BN + i] = 0.f;
+                    ep[4 * BN + i] = (cc < p.cout && p.stat_shift) ? __ldg(p.stat_shift + cc) : 0.f;
+                }
+            }
             if constexpr (FUSED) {
                 ep[2 * BN + i] = (ok && p.split_scale) ? __ldg(p.split_scale + (size_t)n0 * p.split_scale_ld + cc) : 1.f;
 #pragma unroll
@@ -250,6 +276,27 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
             } else if (p.act == 4) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+            }
+            if constexpr (!FUSED) {
+                if (p.stat_sum) {
+                    // shifted first / second moments of this 32-pixel x 16-channel block -> the CTA's shared accumulators
+                    float dv[16], dq[16];
+                    const uint32_t es = ep_s + (uint32_t)(4 * BN + c) * 4u;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 sh = ptx::lds128(es + i * 4);
+                        dv[i + 0] = lane_ok ? v[i + 0] - sh.x : 0.f; dv[i + 1] = lane_ok ? v[i + 1] - sh.y : 0.f;
+                        dv[i + 2] = lane_ok ? v[i + 2] - sh.z : 0.f; dv[i + 3] = lane_ok ? v[i + 3] - sh.w : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dq[i] = dv[i] * dv[i];
+                    const float s1 = warp_colsum16(dv, lane), s2 = warp_colsum16(dq, lane);
+                    if ((lane & 1) == 0) {
+                        const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        atomicAdd(ep + 2 * BN + c + ch, s1);
+                        atomicAdd(ep + 3 * BN + c + ch, s2);
+                    }
+                }
             }
         } else if (!g_uniform && cs && !p.accumulate && p.group_w == 2 && p.out_sx == gsz && (gsz == 3 || gsz == 6) &&
                    px0 + 2 <= p.out_w) {
@@ -381,6 +428,18 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     if (FUSED && p.rgb_out && valid) {
         float* ro = p.rgb_out + pix * 3;
         atomicAdd(ro, rgb0); atomicAdd(ro + 1, rgb1); atomicAdd(ro + 2, rgb2);
+    }
+    if constexpr (!FUSED) {
+        if (p.stat_sum && flush_stats) {         // one global atomic per channel per CTA (after its last tile)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x - 64 + c_lo; i < c_hi; i += 128) {
+                const int cc = co0 + i;
+                if (cc < p.cout) {
+                    atomicAdd(p.stat_sum + cc, ep[2 * BN + i]);
+                    atomicAdd(p.stat_sumsq + cc, ep[3 * BN + i]);
+                }
+            }
+        }
     }
 }
 
@@ -796,7 +855,8 @@ conv_halo_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int i = 0; i < n_tiles; ++i) {
             const int acc = i & 1;
             conv_epilogue<FUSED, true>(p, tmem_base + (uint32_t)acc * acc_cols, ep, tfull_bar + acc, warp, lane, n0, oy0,
-                                       (tx0 + i) * p.bw, co0, p.coalesce ? stg : nullptr, i == 0, (uint32_t)(i >> 1) & 1u);
+                                       (tx0 + i) * p.bw, co0, p.coalesce ? stg : nullptr, i == 0, (uint32_t)(i >> 1) & 1u,
+                                       0, 0, 0, i == n_tiles - 1);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar + acc);
@@ -922,6 +982,15 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.out_split = d->out_split; p.split_scale = d->split_scale; p.split_scale_ld = d->split_scale_ld;
     p.out_from_n = d->out_from_n; p.rgb_w = d->rgb_w; p.rgb_out = d->rgb_out;
     p.group_size = d->group_size; p.group_w = d->group_w; p.out_h = d->out_h; p.out_w = d->out_w;
+    p.stat_sum = d->stat_sum; p.stat_sumsq = d->stat_sumsq; p.stat_shift = d->stat_shift;
+    WGS_REQUIRE((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), "conv: stat_sum and stat_sumsq go together");
+    if (d->stat_sum) {
+        WGS_REQUIRE(d->out != nullptr && !d->out_split && !d->rgb_out && d->out_from_n == 0 && d->group_size == 0 &&
+                    !d->accumulate && d->cout % 16 == 0,
+                    "conv: output statistics need the plain fp32 epilogue and cout % 16 == 0");
+        WGS_REQUIRE(p.bn == 1, "conv: output statistics need output maps of at least 128 pixels (one image per tile)");
+        WGS_REQUIRE(!conv_impl_is_simt(), "conv: output statistics are not available on the SIMT cross-check path");
+    }
     WGS_REQUIRE(d->group_size >= 0, "conv: bad group_size");
     if (d->group_size > 0) {
         WGS_REQUIRE(d->cout % d->group_size == 0 && d->group_w >= 1 && (d->cout / d->group_size) % d->group_w == 0,
@@ -972,7 +1041,8 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         // alone, never on the batch, so an image computed alone or inside any batch goes through the same sums in the same
         // order.  Maps up to 16 x 16 (StyleGAN2 / ProgGAN / BigGAN layers at 4^2 .. 16^2: 8 - 64 CTAs of 144 dependent
         // stages each, ~60 us per launch whatever the batch)
-        if (!stack && d->force_bn == 0 && d->group_size == 0 && k_blocks_total(d) >= 16 && d->grid_h * d->grid_w <= 256) {
+        if (!stack && d->force_bn == 0 && (d->group_size == 0 || d->group_size % 16 == 0) && k_blocks_total(d) >= 16 &&
+            d->grid_h * d->grid_w <= 256) {
             const int wide = std::min(256, (d->cout + 15) / 16 * 16);
             const int tiles1 = p.tiles_x * p.tiles_y * ceil_div(d->cout, wide);
             int ks = 1;

@@ -15,6 +15,8 @@ Launch diet (the weights change every step, so none of this can be cached across
     is neither a zero fill nor an accumulate per parameter;
   * num_batches_tracked is bumped by one multi-tensor add.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -54,18 +56,37 @@ def _bn_list(net):
     return bns
 
 
-def _bn_forward(y, bn, residual, relu, want_split, pool, want_f32=True):
-    """y [N,H,W,C] fp32 NHWC -> (z fp32 or None, zs split32 or None, (mean, rstd))."""
+# 1 = BatchNorm statistics formed in the conv epilogue (wgs_conv_desc.stat_sum) instead of by a separate pass.  Measured on one
+# B200 (profiles/r02_launch_list_summary.md): the pass it removes costs 0.32 ms per step, the epilogue work it adds 0.33 ms
+# (the multi-tile kernels of the stem / layer 1 are epilogue-bound: 73 -> 100 us per launch) - a wash, so the separate pass
+# stays the default and this is an A/B switch.
+EPILOGUE_STATS = os.environ.get('WGS_EPILOGUE_STATS', '0') == '1'
+
+
+def _stat_slots(bn, pool, shifts, out_hw):
+    """(sum, sumsq, shift) for a conv whose epilogue forms the BatchNorm statistics of its output, or None when the output
+    map is too small for that path (< 128 pixels per image: several images share a tile)."""
+    if not EPILOGUE_STATS or out_hw[0] * out_hw[1] < 128 or bn.num_features % 16 != 0:
+        return None
+    return pool.take(bn.num_features), pool.take(bn.num_features), shifts[id(bn)]
+
+
+def _bn_forward(y, bn, residual, relu, want_split, pool, want_f32=True, pre=None):
+    """y [N,H,W,C] fp32 NHWC -> (z fp32 or None, zs split32 or None, (mean, rstd)).  pre = (sum, sumsq, shift) when the conv
+    that produced y already accumulated the statistics in its epilogue."""
     n, h, w, c = y.shape
     R = n * h * w
     dev = y.device
-    s0, s1 = pool.take(c), pool.take(c)
-    _lib.call('wgs_bn_stats', _lib.ptr(y), R, c, _lib.ptr(s0), _lib.ptr(s1), _lib.stream())
+    if pre is not None:
+        s0, s1, shift = pre
+    else:
+        s0, s1, shift = pool.take(c), pool.take(c), None
+        _lib.call('wgs_bn_stats', _lib.ptr(y), R, c, _lib.ptr(s0), _lib.ptr(s1), _lib.stream())
     stats = torch.empty(2, c, device=dev, dtype=torch.float32)
     z = torch.empty_like(y) if want_f32 else None
     zs = torch.empty(n, h, w, C.chunks_of(c), 64, device=dev, dtype=torch.bfloat16) if want_split else None
     gamma, beta = bn.weight.detach(), bn.bias.detach()
-    _lib.call('wgs_bn_fwd_fused', _lib.ptr(y), _lib.ptr(s0), _lib.ptr(s1), R, c, float(bn.eps), float(bn.momentum),
+    _lib.call('wgs_bn_fwd_fused', _lib.ptr(y), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(shift), R, c, float(bn.eps), float(bn.momentum),
               _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(residual), int(relu), _lib.ptr(z), _lib.ptr(zs),
               _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.stream())
     return z, zs, (stats[0], stats[1])
@@ -189,9 +210,21 @@ class ResNetFeatures(torch.autograd.Function):
         bns = _bn_list(net)
         pool = _Pool(sum(2 * ((b.num_features + 3) // 4 * 4) for b in bns), x.device)
 
-        def conv(xs, wt, stride, padding):
+        # shift vectors of the epilogue statistics: a snapshot of every running mean (|mean - shift| ~ std after the first
+        # steps, so E[(y-s)^2] - E[y-s]^2 keeps its digits; the snapshot is one cat, taken before any BatchNorm updates them)
+        shifts, off = {}, 0
+        if EPILOGUE_STATS:
+            snap = torch.cat([b.running_mean for b in bns])
+            for b in bns:
+                shifts[id(b)] = snap[off: off + b.num_features]
+                off += b.num_features
+
+        def conv(xs, wt, stride, padding, bn=None):
             co, cin, kh, kw = wt.shape
-            return C.conv2d(xs, packs[(id(wt), 'fwd')], kh, kw, stride=stride, padding=padding, cin=cin, split_k=True)
+            oh_, ow_ = (xs.shape[1] + 2 * padding - kh) // stride + 1, (xs.shape[2] + 2 * padding - kw) // stride + 1
+            pre = _stat_slots(bn, pool, shifts, (oh_, ow_)) if bn is not None else None
+            y = C.conv2d(xs, packs[(id(wt), 'fwd')], kh, kw, stride=stride, padding=padding, cin=cin, split_k=True, stats=pre)
+            return y, pre
 
         # stem 7x7 / 2 on 6 channels: 2x2 space-to-depth (24 channels, one split32 chunk) -> stride-1 4x4-tap conv on the
         # multi-tile halo kernel (taps resident in shared memory); no im2col (it wrote 1280 B per output pixel)
@@ -201,18 +234,22 @@ class ResNetFeatures(torch.autograd.Function):
         xs2d = C.s2d_pack_split32(x_nhwc, x2_nhwc)
         taps, S = C.s2d_taps(kh, 3)
         y0 = torch.empty(n, oh, ow, co, device=x.device, dtype=torch.float32)
-        C.conv_taps(xs2d, packs[(id(w1), 'fwd')], taps, y0, grid=(oh, ow), cin=kh * kw * ci,
-                    algo_macs_per_pixel=kh * kw * ci * co)
-        # bn1 + relu + maxpool in one pass over y0: the normalised 512^2 activation is never stored
         bn1 = net.bn1
-        s0, s1 = pool.take(co), pool.take(co)
-        _lib.call('wgs_bn_stats', _lib.ptr(y0), n * oh * ow, co, _lib.ptr(s0), _lib.ptr(s1), _lib.stream())
+        pre0 = _stat_slots(bn1, pool, shifts, (oh, ow))
+        C.conv_taps(xs2d, packs[(id(w1), 'fwd')], taps, y0, grid=(oh, ow), cin=kh * kw * ci,
+                    algo_macs_per_pixel=kh * kw * ci * co, stats=pre0)
+        # bn1 + relu + maxpool in one pass over y0: the normalised 512^2 activation is never stored
+        if pre0 is not None:
+            s0, s1, sh0 = pre0
+        else:
+            s0, s1, sh0 = pool.take(co), pool.take(co), None
+            _lib.call('wgs_bn_stats', _lib.ptr(y0), n * oh * ow, co, _lib.ptr(s0), _lib.ptr(s1), _lib.stream())
         st0 = torch.empty(2, co, device=x.device, dtype=torch.float32)
         ph, pw = (oh + 1) // 2, (ow + 1) // 2
         cur = torch.empty(n, ph, pw, co, device=x.device, dtype=torch.float32)             # NHWC fp32
         pool_idx = torch.empty(n, ph, pw, co, device=x.device, dtype=torch.uint8)
         cur_s = torch.empty(n, ph, pw, C.chunks_of(co), 64, device=x.device, dtype=torch.bfloat16)
-        _lib.call('wgs_bn_pool_fwd', _lib.ptr(y0), _lib.ptr(s0), _lib.ptr(s1), n, oh, ow, co, float(bn1.eps),
+        _lib.call('wgs_bn_pool_fwd', _lib.ptr(y0), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(sh0), n, oh, ow, co, float(bn1.eps),
                   float(bn1.momentum), _lib.ptr(bn1.weight.detach()), _lib.ptr(bn1.bias.detach()), _lib.ptr(cur),
                   _lib.ptr(pool_idx), _lib.ptr(cur_s), _lib.ptr(st0[0]), _lib.ptr(st0[1]), _lib.ptr(bn1.running_mean),
                   _lib.ptr(bn1.running_var), _lib.stream())
@@ -221,15 +258,15 @@ class ResNetFeatures(torch.autograd.Function):
         for li in range(1, 5):
             for b in getattr(net, 'layer%d' % li):
                 s = b.stride
-                y1 = conv(cur_s, b.conv1.weight, s, 1)
-                z1, z1s, st1 = _bn_forward(y1, b.bn1, None, True, True, pool)
-                y2 = conv(z1s, b.conv2.weight, 1, 1)
+                y1, p1 = conv(cur_s, b.conv1.weight, s, 1, b.bn1)
+                z1, z1s, st1 = _bn_forward(y1, b.bn1, None, True, True, pool, pre=p1)
+                y2, p2 = conv(z1s, b.conv2.weight, 1, 1, b.bn2)
                 if hasattr(b, 'downsample'):
-                    yd = conv(cur_s, b.downsample[0].weight, s, 0)
-                    idt, _, std = _bn_forward(yd, b.downsample[1], None, False, False, pool)
+                    yd, pd = conv(cur_s, b.downsample[0].weight, s, 0, b.downsample[1])
+                    idt, _, std = _bn_forward(yd, b.downsample[1], None, False, False, pool, pre=pd)
                 else:
                     yd, std, idt = None, None, cur
-                out, outs, st2 = _bn_forward(y2, b.bn2, idt, True, True, pool)
+                out, outs, st2 = _bn_forward(y2, b.bn2, idt, True, True, pool, pre=p2)
                 tape['blocks'].append((b, cur_s, cur.shape, y1, z1, z1s, st1, y2, out, st2, yd, std))
                 cur, cur_s = out, outs
         torch._foreach_add_([b.num_batches_tracked for b in bns], 1)

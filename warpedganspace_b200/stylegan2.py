@@ -80,6 +80,7 @@ def _to_rgb(ci, style_dim, upsample=True):
 
 
 MERGE_PHASES = os.environ.get('WGS_MERGE_PHASES', '1') != '0'
+MERGE_WIDE = os.environ.get('WGS_MERGE_WIDE', '0') != '0'      # 1 = also the wide (> 64 channel) up-convs as one phase-packed launch (measured 1 % slower)
 _TAPS = (ctypes.c_float * 4)(0.25, 0.75, 0.75, 0.25)          # [1,3,3,1]/8 * 2 per axis (kernel * 4 overall)
 
 
@@ -153,8 +154,10 @@ class Generator(nn.Module):
                 # data-gradient weights: dx[ci] = sum_{taps,co} dy[co] * W[co,ci,tap]
                 if up:
                     ent['w_bwd'] = C.pack_weights(ws.permute(1, 0, 2, 3).contiguous())         # strided conv, same taps
-                    if co <= 64 and MERGE_PHASES:
-                        # all four output phases of the transposed conv stacked along N (one launch, conv.py)
+                    if MERGE_PHASES and (co <= 64 or MERGE_WIDE):
+                        # all four output phases of the transposed conv stacked along N (one launch, conv.py).  For the wide
+                        # layers the 16/9 extra MACs of the zero blocks cost more than three launches save (A/B on one
+                        # B200: 16.61 / 16.71 ms packed vs 16.52 / 16.44 ms as four phase launches): opt-in
                         shifts, idx, G = C._phase_plan('convT', 3, 3, 2, 0, dev)
                         ent['w_up'] = C.merged_phase_weights(ws.reshape(co, ci, 9).contiguous(), idx, len(shifts), G)
                 else:
@@ -378,7 +381,7 @@ def synthesis(G, w, tape=None, grad_from=0):
         s_next = style_of(nxt) if nxt else None
         if e['up']:
             if 'w_up' in e:
-                y = C.conv_transpose2d_s2_merged(xs, e['w_up'], 3, e['co'])    # [B, 2h+1, 2w+1, Co] raw
+                y = C.conv_transpose2d_s2_merged(xs, e['w_up'], 3, e['co'], split_k=2)    # [B, 2h+1, 2w+1, Co] raw
             else:
                 y = C.conv_transpose2d_s2(xs, e['w_fwd'], 3, split_k=2)
             _lib.call('wgs_fir4_act', _lib.ptr(y), _lib.ptr(a), n, 2 * h + 1, 2 * wd + 1, oh, ow, e['co'], 1,
