@@ -117,8 +117,8 @@ class ProgGANGenerator(_Frozen):
         """Both images of a training pair in one batched pass: rows [x_plain; x_shifted], only the shifted rows are taped."""
         b = x_plain.shape[0]
         x_all = torch.cat([x_plain.detach().float(), x_shifted.float()], dim=0).contiguous()
-        img = _ProgGANFn.apply(self, x_all, b).permute(0, 3, 1, 2)
-        return img[:b], img[b:]
+        plain, shifted = _ProgGANPairFn.apply(self, x_all, b)          # NHWC halves of one buffer
+        return plain.permute(0, 3, 1, 2), shifted.permute(0, 3, 1, 2)
 
     def forward(self, x):
         self._require_cuda(x)
@@ -159,9 +159,9 @@ def _proggan_forward(G, x, tape, grad_from):
         xs = _pixelnorm_pack(a)
         h, w = a.shape[1], a.shape[2]
         if e['up']:
-            a = up_conv_forward(xs, e['w_fwd'], e['taps'], e['co'], e['ci'], beta=e['bias'], act=2)
+            a = up_conv_forward(xs, e['w_fwd'], e['taps'], e['co'], e['ci'], beta=e['bias'], act=2, split_k=2)
         else:
-            a = C.conv2d(xs, e['w_fwd'], e['k'], e['k'], padding=e['pad'], beta=e['bias'], act=2, cin=e['ci'])
+            a = C.conv2d(xs, e['w_fwd'], e['k'], e['k'], padding=e['pad'], beta=e['bias'], act=2, cin=e['ci'], split_k=2)
     acts.append(a[grad_from:])
     img = C.conv2d(_pixelnorm_pack(a), P['w_out'], 1, 1, beta=P['b_out'], cin=P['c_out'])
     if tape is not None:
@@ -178,9 +178,9 @@ def _proggan_backward(G, tape, dimg):
         e = P['blocks'][i]
         gs = _pixelnorm_bwd(dxn, acts[i + 1], 0.2, split=True)      # gradient w.r.t. block i's pre-activation, packed
         if e['up']:
-            dxn = C.conv2d(gs, e['w_bwd'], 4, 4, stride=2, padding=1, cout=e['ci'], cin=e['co'])
+            dxn = C.conv2d(gs, e['w_bwd'], 4, 4, stride=2, padding=1, cout=e['ci'], cin=e['co'], split_k=2)
         else:
-            dxn = C.conv2d(gs, e['w_bwd'], e['k'], e['k'], padding=e['k'] - 1 - e['pad'], cout=e['ci'], cin=e['co'])
+            dxn = C.conv2d(gs, e['w_bwd'], e['k'], e['k'], padding=e['k'] - 1 - e['pad'], cout=e['ci'], cin=e['co'], split_k=2)
     return _pixelnorm_bwd(dxn, acts[0], -1.0, split=False).reshape(dxn.shape[0], -1)
 
 
@@ -201,6 +201,31 @@ class _ProgGANFn(torch.autograd.Function):
         ctx.tape = None
         if ctx.n_plain == 0:
             return None, dx, None
+        full = dx.new_zeros(ctx.rows, dx.shape[1])
+        full[ctx.n_plain:] = dx
+        return None, full, None
+
+
+class _ProgGANPairFn(torch.autograd.Function):
+    """Both halves of the batched pass as separate outputs: the gradient of the shifted half arrives as it is (no
+    zero-padded full-batch gradient, no slice copies)."""
+
+    @staticmethod
+    def forward(ctx, G, x_all, n_plain):
+        need = ctx.needs_input_grad[1]
+        tape = {} if need else None
+        img = _proggan_forward(G, x_all.detach(), tape, n_plain)
+        ctx.G, ctx.tape, ctx.n_plain, ctx.rows = G, tape, n_plain, x_all.shape[0]
+        plain, shifted = img[:n_plain], img[n_plain:]
+        ctx.mark_non_differentiable(plain)
+        return plain, shifted
+
+    @staticmethod
+    def backward(ctx, _dplain, dimg):
+        if ctx.tape is None or dimg is None:
+            return None, None, None
+        dx = _proggan_backward(ctx.G, ctx.tape, dimg)
+        ctx.tape = None
         full = dx.new_zeros(ctx.rows, dx.shape[1])
         full[ctx.n_plain:] = dx
         return None, full, None
