@@ -337,10 +337,12 @@ int wgs_bn_fwd_fused(const float* y, const float* sum, const float* sumsq, const
 int wgs_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                    const float* residual, int relu, float* z, void* zs, long long R, int C, void* stream);
 int wgs_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
-                          int relu, long long R, int C, float* sum_dz, float* sum_dzx, void* stream);  /* accumulates */
+                          const float* gamma, const float* beta, int relu, long long R, int C, float* sum_dz,
+                          float* sum_dzx, void* stream);  /* accumulates; z may be NULL (no residual): the ReLU mask is then
+                                                             re-derived from y, gamma, beta - the activation need not be kept */
 int wgs_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
-                         const float* gamma, const float* sum_dz, const float* sum_dzx, int relu, long long R,
-                         int C, void* dys, float* dy, float* dres, void* stream);
+                         const float* gamma, const float* beta, const float* sum_dz, const float* sum_dzx, int relu,
+                         long long R, int C, void* dys, float* dy, float* dres, void* stream);
 
 /* 3x3 / stride 2 / pad 1 max-pool of the ResNet stem (torchvision resnet18.maxpool; lib/reconstructor.py:54), NHWC.
  * fwd: out fp32 [N,OH,OW,C], idx uint8 argmax tap, optional split32 pack; bwd: gather, dz [N,H,W,C] fully written.   */

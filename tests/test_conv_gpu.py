@@ -462,3 +462,16 @@ def test_batchnorm_statistics_in_the_conv_epilogue(case):
     out2 = conv.conv2d(conv.pack_split32(nhwc(x)), conv.pack_weights(w), k, k, stride=stride, padding=pad, cin=Ci,
                        split_k=split_k, stats=(s0, s1, None))
     assert rel(s0, out2.double().sum(dim=(0, 1, 2))) < 1e-5 and rel(s1, (out2.double() ** 2).sum(dim=(0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize('c', [3, 5])
+def test_space_to_depth_pack_of_two_images_equals_the_pack_of_their_concatenation(c):
+    """wgs_s2d_pack_split32_pair (the Reconstructor's cat([x1, x2], 1) folded into its stem's operand pack): bit-identical to
+    packing the materialised concatenation; c = 3 takes the specialised one-thread-per-output-pixel kernel."""
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(5 + c)
+    x1 = torch.randn(2, 12, 20, c, generator=g).cuda()
+    x2 = torch.randn(2, 12, 20, c, generator=g).cuda()
+    pair = conv.s2d_pack_split32(x1, x2)
+    whole = conv.s2d_pack_split32(torch.cat([x1, x2], dim=3).contiguous())
+    assert pair.shape == whole.shape and torch.equal(pair, whole)

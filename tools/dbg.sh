@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 1 0; do
-WGS_EPI_FRAG=$v ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/dbg_frag$v python tools/ncu_step.py 2 "" wgs_conv_split32 > gpurun_out/dbg_frag$v.log 2>&1
-tail -3 gpurun_out/dbg_frag$v.log
-done
+python -m pytest tests -q -m gpu > gpurun_out/dbg_tests.log 2>&1; tail -5 gpurun_out/dbg_tests.log
+for i in 1 2; do python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-200; done

@@ -162,7 +162,8 @@ bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, c
 __global__ void __launch_bounds__(BN_THREADS)
 bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
                          const float* __restrict__ mean, const float* __restrict__ rstd, int relu, long long R, int C,
-                         float* __restrict__ sum_dz, float* __restrict__ sum_dzx) {
+                         float* __restrict__ sum_dz, float* __restrict__ sum_dzx, const float* __restrict__ gamma,
+                         const float* __restrict__ beta) {
     extern __shared__ float sm[];
     const int C4 = C >> 2, PL = BN_THREADS / C4;
     const int q = threadIdx.x % C4, pl = threadIdx.x / C4;
@@ -170,12 +171,22 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__
     const long long r0 = blockIdx.x * per, r1 = min(R, r0 + per);
     const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + q * 4));
     const float4 s4 = __ldg(reinterpret_cast<const float4*>(rstd + q * 4));
+    // z == nullptr (no residual): the ReLU mask is re-derived from y - the normalised activation was never stored
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = k4;
+    if (relu && !z) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + q * 4));
+        b4 = __ldg(reinterpret_cast<const float4*>(beta + q * 4));
+        k4 = make_float4(s4.x * g4.x, s4.y * g4.y, s4.z * g4.z, s4.w * g4.w);
+    }
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
     for (long long r = r0 + pl; r < r1; r += PL) {
         const long long off = r * C + q * 4;
         float4 g = __ldg(reinterpret_cast<const float4*>(dz + off));
         const float4 v = __ldg(reinterpret_cast<const float4*>(y + off));
-        if (relu) {
+        if (relu && !z) {
+            g.x = (v.x - m4.x) * k4.x + b4.x > 0.f ? g.x : 0.f; g.y = (v.y - m4.y) * k4.y + b4.y > 0.f ? g.y : 0.f;
+            g.z = (v.z - m4.z) * k4.z + b4.z > 0.f ? g.z : 0.f; g.w = (v.w - m4.w) * k4.w + b4.w > 0.f ? g.w : 0.f;
+        } else if (relu) {
             const float4 zz = __ldg(reinterpret_cast<const float4*>(z + off));
             g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f;
             g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
@@ -193,7 +204,8 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y,
                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                         const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx, int relu, long long R, int C,
-                        __nv_bfloat16* __restrict__ dys, float* __restrict__ dy, float* __restrict__ dres) {
+                        __nv_bfloat16* __restrict__ dys, float* __restrict__ dy, float* __restrict__ dres,
+                        const float* __restrict__ beta) {
     const int C4 = C >> 2;
     const long long total = R * C4;
     const float inv_r = 1.f / (float)R;
@@ -205,15 +217,19 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ 
         const long long off = r * C + c;
         float4 g = __ldg(reinterpret_cast<const float4*>(dz + off));
         const float4 v = __ldg(reinterpret_cast<const float4*>(y + off));
-        if (relu) {
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        if (relu && !z) {                           // mask re-derived from y (same expression as the reduce pass)
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+            g.x = (v.x - m4.x) * (s4.x * g4.x) + b4.x > 0.f ? g.x : 0.f; g.y = (v.y - m4.y) * (s4.y * g4.y) + b4.y > 0.f ? g.y : 0.f;
+            g.z = (v.z - m4.z) * (s4.z * g4.z) + b4.z > 0.f ? g.z : 0.f; g.w = (v.w - m4.w) * (s4.w * g4.w) + b4.w > 0.f ? g.w : 0.f;
+        } else if (relu) {
             const float4 zz = __ldg(reinterpret_cast<const float4*>(z + off));
             g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f;
             g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
         }
         if (dres) *reinterpret_cast<float4*>(dres + off) = g;
-        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c));
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
         const float4 a4 = __ldg(reinterpret_cast<const float4*>(sum_dz + c));
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(sum_dzx + c));
         float o[4];
@@ -291,22 +307,25 @@ extern "C" int wgs_bn_fwd_fused(const float* y, const float* sum, const float* s
 }
 
 extern "C" int wgs_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
-                                     int relu, long long R, int C, float* sum_dz, float* sum_dzx, void* stream) {
+                                     const float* gamma, const float* beta, int relu, long long R, int C, float* sum_dz,
+                                     float* sum_dzx, void* stream) {
     WGS_REQUIRE(bn_ok(C) && R > 0, "bn_act_bwd_reduce: C must be a multiple of 4 with C/4 dividing 256");
+    WGS_REQUIRE(!relu || z || (gamma && beta), "bn_act_bwd_reduce: without z the ReLU mask needs gamma and beta");
     const size_t smem = 2 * (size_t)(BN_THREADS / (C / 4)) * C * sizeof(float);
     bn_act_bwd_reduce_kernel<<<bn_red_blocks(R, C), BN_THREADS, smem, (cudaStream_t)stream>>>(dz, z, y, mean, rstd, relu, R, C,
-                                                                                         sum_dz, sum_dzx);
+                                                                                         sum_dz, sum_dzx, gamma, beta);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int wgs_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
-                                    const float* gamma, const float* sum_dz, const float* sum_dzx, int relu, long long R,
-                                    int C, void* dys, float* dy, float* dres, void* stream) {
+                                    const float* gamma, const float* beta, const float* sum_dz, const float* sum_dzx, int relu,
+                                    long long R, int C, void* dys, float* dy, float* dres, void* stream) {
     WGS_REQUIRE(C % 4 == 0 && R > 0, "bn_act_bwd_apply: C must be a multiple of 4");
+    WGS_REQUIRE(!relu || z || beta, "bn_act_bwd_apply: without z the ReLU mask needs beta");
     bn_act_bwd_apply_kernel<<<bn_ew_blocks(R * (C / 4)), BN_THREADS, 0, (cudaStream_t)stream>>>(
-        dz, z, y, mean, rstd, gamma, sum_dz, sum_dzx, relu, R, C, (__nv_bfloat16*)dys, dy, dres);
+        dz, z, y, mean, rstd, gamma, sum_dz, sum_dzx, relu, R, C, (__nv_bfloat16*)dys, dy, dres, beta);
     count_launch();
     WGS_LAUNCH_CHECK();
     return 0;

@@ -322,7 +322,55 @@ s2d_pack_split32_kernel(const float* __restrict__ x, const float* __restrict__ x
 }
 }  // namespace wgs
 
+namespace wgs {
+// The paired step's case, two 3-channel images (24 space-to-depth channels = one chunk): one thread per output pixel reads its
+// 2 x 2 input pixels of both images as six 8-byte words per image (two pixels of a row are 24 contiguous bytes) and writes the
+// whole 128-byte row with eight 128-bit stores - the generic kernel above does a division and a scalar load per element and
+// ran at 1.7 TB/s (135 us at 4 x 1024^2).
+__global__ void __launch_bounds__(256)
+s2d_pack_pair3_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int N, int H, int W,
+                      __nv_bfloat16* __restrict__ out) {
+    const int OH = H >> 1, OW = W >> 1;
+    const long long total = (long long)N * OH * OW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % OW);
+        const long long r = i / OW;
+        const int Y = (int)(r % OH), n = (int)(r / OH);
+        float v[32];
+#pragma unroll
+        for (int k = 24; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            const long long row = (((long long)n * H + 2 * Y + py) * W + 2 * X) * 3;      // 6 floats: pixels 2X, 2X+1
+            const float2* a = reinterpret_cast<const float2*>(x1 + row);
+            const float2* b = reinterpret_cast<const float2*>(x2 + row);
+            const float2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2), b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
+            // channel (py*2 + px)*6 + c, c = 0..2 from x1, 3..5 from x2
+            float* o = v + py * 12;
+            o[0] = a0.x; o[1] = a0.y; o[2] = a1.x; o[3] = b0.x; o[4] = b0.y; o[5] = b1.x;             // px = 0
+            o[6] = a1.y; o[7] = a2.x; o[8] = a2.y; o[9] = b1.y; o[10] = b2.x; o[11] = b2.y;           // px = 1
+        }
+        __align__(16) __nv_bfloat162 hi[16], lo[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) split_bf16x2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+        uint4* d = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[k] = reinterpret_cast<const uint4*>(hi)[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[4 + k] = reinterpret_cast<const uint4*>(lo)[k];
+    }
+}
+}  // namespace wgs
+
 static int s2d_launch(const float* x, const float* x2, int C1, int N, int H, int W, int C, void* out, void* stream) {
+    if (x2 && C1 == 3 && C == 6 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(x2) & 7) == 0) {
+        const long long total = (long long)N * (H / 2) * (W / 2);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)wgs::num_sms() * 16);
+        wgs::s2d_pack_pair3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x2, N, H, W, (__nv_bfloat16*)out);
+        wgs::count_launch();
+        WGS_LAUNCH_CHECK();
+        return 0;
+    }
     const int chunks = (4 * C + 31) / 32;
     const long long total = (long long)N * (H / 2) * (W / 2) * chunks * 8;
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)wgs::num_sms() * 32);

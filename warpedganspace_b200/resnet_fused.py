@@ -102,13 +102,13 @@ def _bn_backward(dz, z, y, stats, bn, relu, want_res, pool, grads):
     if d_beta is None or d_gamma is None:
         d_beta, d_gamma = pool.take(c), pool.take(c)
         grads[bn.weight], grads[bn.bias] = d_gamma, d_beta
-    _lib.call('wgs_bn_act_bwd_reduce', _lib.ptr(dz), _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), int(relu),
-              R, c, _lib.ptr(d_beta), _lib.ptr(d_gamma), _lib.stream())
+    gamma, beta = bn.weight.detach(), bn.bias.detach()
+    _lib.call('wgs_bn_act_bwd_reduce', _lib.ptr(dz), _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
+              _lib.ptr(beta), int(relu), R, c, _lib.ptr(d_beta), _lib.ptr(d_gamma), _lib.stream())
     dys = torch.empty(n, h, w, C.chunks_of(c), 64, device=dev, dtype=torch.bfloat16)
     dres = torch.empty_like(y) if want_res else None
-    gamma = bn.weight.detach()
     _lib.call('wgs_bn_act_bwd_apply', _lib.ptr(dz), _lib.ptr(z), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd),
-              _lib.ptr(gamma), _lib.ptr(d_beta), _lib.ptr(d_gamma), int(relu), R, c, _lib.ptr(dys), None,
+              _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(d_beta), _lib.ptr(d_gamma), int(relu), R, c, _lib.ptr(dys), None,
               _lib.ptr(dres), _lib.stream())
     return dys, dres
 
@@ -259,7 +259,9 @@ class ResNetFeatures(torch.autograd.Function):
             for b in getattr(net, 'layer%d' % li):
                 s = b.stride
                 y1, p1 = conv(cur_s, b.conv1.weight, s, 1, b.bn1)
-                z1, z1s, st1 = _bn_forward(y1, b.bn1, None, True, True, pool, pre=p1)
+                # (the mid-block activation is only needed as the next conv's operand: its ReLU mask is re-derived from y1 in
+                # the backward pass, so the fp32 copy is neither written here nor read there)
+                z1, z1s, st1 = _bn_forward(y1, b.bn1, None, True, True, pool, want_f32=False, pre=p1)
                 y2, p2 = conv(z1s, b.conv2.weight, 1, 1, b.bn2)
                 if hasattr(b, 'downsample'):
                     yd, pd = conv(cur_s, b.downsample[0].weight, s, 0, b.downsample[1])
