@@ -1,0 +1,103 @@
+"""CPU oracle: the two ResNet-based attribute predictors of the attribute-space traversal, restated functionally over
+torchvision-named state dicts (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+
+  * FairFace: ``torchvision.models.resnet34`` with ``fc = Linear(512, 18)`` in eval mode (traverse_attribute_space.py:178-183)
+    followed by the race / gender / age score arithmetic of :412-433;
+  * Hopenet: ResNet-50 trunk + three 66-bin heads (lib/evaluation/hopenet/hopenet.py:5-66) followed by the soft-argmax pose of
+    traverse_attribute_space.py:448-456.
+
+Third-party arithmetic: torchvision's BasicBlock / Bottleneck (no version pinned by the reference's requirements.txt; 0.26.0
+installed here).  Pinned by oracle/gen_golden.py::pin_eval_nets against torchvision.models.resnet34 and the reference's own
+Hopenet class on seeded weights with randomised BatchNorm statistics; fixture tests/golden/eval_nets.pt.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+LAYERS = (3, 4, 6, 3)
+
+
+def init_state(block, heads, generator, layers=LAYERS):
+    """Seeded random state with torchvision's key names; BatchNorm statistics are randomised so that eval-mode BatchNorm is
+    not the identity.  block: 'basic' | 'bottleneck'; heads: {name: out_features}."""
+    exp = 1 if block == 'basic' else 4
+    sd = {}
+
+    def conv(name, co, ci, k):
+        sd[name + '.weight'] = torch.randn(co, ci, k, k, generator=generator) * math.sqrt(2.0 / (k * k * co))
+
+    def bn(name, c):
+        sd[name + '.weight'] = 0.5 + torch.rand(c, generator=generator)
+        sd[name + '.bias'] = 0.1 * torch.randn(c, generator=generator)
+        sd[name + '.running_mean'] = 0.1 * torch.randn(c, generator=generator)
+        sd[name + '.running_var'] = 0.5 + torch.rand(c, generator=generator)
+        sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+    conv('conv1', 64, 3, 7)
+    bn('bn1', 64)
+    inplanes = 64
+    for li, (planes, n) in enumerate(zip((64, 128, 256, 512), layers), start=1):
+        for bi in range(n):
+            p = 'layer%d.%d' % (li, bi)
+            stride = 2 if (bi == 0 and li > 1) else 1
+            if block == 'basic':
+                conv(p + '.conv1', planes, inplanes, 3); bn(p + '.bn1', planes)
+                conv(p + '.conv2', planes, planes, 3); bn(p + '.bn2', planes)
+            else:
+                conv(p + '.conv1', planes, inplanes, 1); bn(p + '.bn1', planes)
+                conv(p + '.conv2', planes, planes, 3); bn(p + '.bn2', planes)
+                conv(p + '.conv3', planes * 4, planes, 1); bn(p + '.bn3', planes * 4)
+            if stride != 1 or inplanes != planes * exp:
+                conv(p + '.downsample.0', planes * exp, inplanes, 1); bn(p + '.downsample.1', planes * exp)
+            inplanes = planes * exp
+    for name, out in heads.items():
+        bound = 1.0 / math.sqrt(inplanes)
+        sd[name + '.weight'] = (torch.rand(out, inplanes, generator=generator) * 2 - 1) * bound
+        sd[name + '.bias'] = (torch.rand(out, generator=generator) * 2 - 1) * bound
+    return sd
+
+
+def _bn(sd, name, x, eps=1e-5):
+    return F.batch_norm(x, sd[name + '.running_mean'], sd[name + '.running_var'], sd[name + '.weight'], sd[name + '.bias'],
+                        False, 0.0, eps)
+
+
+def resnet_forward(sd, x, block, heads, layers=LAYERS):
+    """Eval-mode forward (torchvision/models/resnet.py ResNet._forward_impl; Hopenet.forward, hopenet.py:51-66).
+    Returns the tuple of head outputs in `heads` order."""
+    x = F.max_pool2d(F.relu(_bn(sd, 'bn1', F.conv2d(x, sd['conv1.weight'], None, 2, 3))), 3, 2, 1)
+    for li, n in enumerate(layers, start=1):
+        for bi in range(n):
+            p = 'layer%d.%d' % (li, bi)
+            stride = 2 if (bi == 0 and li > 1) else 1
+            idt = x
+            if block == 'basic':
+                h = F.relu(_bn(sd, p + '.bn1', F.conv2d(x, sd[p + '.conv1.weight'], None, stride, 1)))
+                h = _bn(sd, p + '.bn2', F.conv2d(h, sd[p + '.conv2.weight'], None, 1, 1))
+            else:
+                h = F.relu(_bn(sd, p + '.bn1', F.conv2d(x, sd[p + '.conv1.weight'])))
+                h = F.relu(_bn(sd, p + '.bn2', F.conv2d(h, sd[p + '.conv2.weight'], None, stride, 1)))
+                h = _bn(sd, p + '.bn3', F.conv2d(h, sd[p + '.conv3.weight']))
+            if p + '.downsample.0.weight' in sd:
+                idt = _bn(sd, p + '.downsample.1', F.conv2d(x, sd[p + '.downsample.0.weight'], None, stride, 0))
+            x = F.relu(h + idt)
+    f = x.mean(dim=(2, 3))          # AvgPool2d(7) on the 7 x 7 map of a 224 x 224 crop == AdaptiveAvgPool2d(1)
+    return tuple(F.linear(f, sd[h + '.weight'], sd[h + '.bias']) for h in heads)
+
+
+def fairface_scores(outputs):
+    """traverse_attribute_space.py:412-433 -> (femaleness, age, race) score vectors."""
+    o = outputs.double()
+    gender = torch.softmax(o[:, 7:9], dim=1)[:, 1]
+    age_s = torch.softmax(o[:, 9:18], dim=1)
+    age = (age_s.argmax(dim=1) + age_s.max(dim=1).values) / 9.0
+    race_s = torch.softmax(o[:, :7], dim=1)
+    race = (race_s.argmax(dim=1) + race_s.max(dim=1).values) / 7.0
+    return gender, age, race
+
+
+def hopenet_pose(yaw, pitch, roll):
+    """traverse_attribute_space.py:448-456: expectation over the 66 bins * 3 - 99, in degrees."""
+    idx = torch.arange(66, dtype=yaw.dtype)
+    return tuple(torch.sum(torch.softmax(t, dim=1) * idx, 1) * 3 - 99 for t in (yaw, pitch, roll))

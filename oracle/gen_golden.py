@@ -653,6 +653,40 @@ def pin_latent_pool():
     save('latent_pool.pt', entries)
 
 
+def pin_eval_nets():
+    """The two ResNet-based attribute predictors: oracle.eval_nets against torchvision's resnet34 and the
+    reference's own Hopenet class, seeded weights, randomised BatchNorm statistics, one 224 x 224 crop pair."""
+    import torchvision
+    import oracle.eval_nets as o_en
+    print('[attribute predictors: FairFace resnet34 / Hopenet resnet50]')
+    hop = importlib.import_module('lib.evaluation.hopenet.hopenet')
+    x = torch.randn(2, 3, 224, 224, generator=gen(811))
+    fx = {'seed_x': 811}
+    sd = o_en.init_state('basic', {'fc': 18}, gen(812))
+    ref = torchvision.models.resnet34()
+    ref.fc = torch.nn.Linear(ref.fc.in_features, 18)                       # traverse_attribute_space.py:179
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(x)
+        got = o_en.resnet_forward(sd, x, 'basic', ('fc',))[0]
+    check('FairFace resnet34 logits', got, want, 1e-5)
+    fx['fairface'] = dict(seed=812, checksum=checksum(sd), out=want)
+    heads = {'fc_yaw': 66, 'fc_pitch': 66, 'fc_roll': 66}
+    sd = o_en.init_state('bottleneck', heads, gen(813))
+    ref = hop.Hopenet(torchvision.models.resnet.Bottleneck, [3, 4, 6, 3], 66)    # traverse_attribute_space.py:186
+    missing = ref.load_state_dict(sd, strict=False)
+    assert set(missing.missing_keys) == {'fc_finetune.weight', 'fc_finetune.bias'} and not missing.unexpected_keys
+    ref.eval()
+    with torch.no_grad():
+        want = ref(x)
+        got = o_en.resnet_forward(sd, x, 'bottleneck', tuple(heads))
+    for name, g, w in zip(heads, got, want):
+        check('Hopenet %s' % name, g, w, 1e-5)
+    fx['hopenet'] = dict(seed=813, checksum=checksum(sd), out=[w.clone() for w in want])
+    save('eval_nets.pt', fx)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.chdir('/tmp')
@@ -674,6 +708,7 @@ def main():
     pin_proggan()
     pin_biggan()
     pin_stylegan2_1024_step(model)
+    pin_eval_nets()
     print('oracle pinned against the reference; fixtures in', OUT)
 
 

@@ -1,0 +1,152 @@
+"""Attribute-space traversal: oracle of the two ResNet predictors against the reference-pinned fixture
+(CPU), the driver's score arithmetic / file layout with stub predictors (CPU), and the B200 kernel chains against the same
+fixture (GPU)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.eval_nets as o_en
+
+HEADS = {'fc_yaw': 66, 'fc_pitch': 66, 'fc_roll': 66}
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def test_oracle_resnets_match_the_reference_fixture(golden):
+    fx = golden('eval_nets.pt')
+    x = torch.randn(2, 3, 224, 224, generator=gen(fx['seed_x']))
+    sd = o_en.init_state('basic', {'fc': 18}, gen(fx['fairface']['seed']))
+    assert rel(o_en.resnet_forward(sd, x, 'basic', ('fc',))[0], fx['fairface']['out']) < 1e-5
+    sd = o_en.init_state('bottleneck', HEADS, gen(fx['hopenet']['seed']))
+    for got, want in zip(o_en.resnet_forward(sd, x, 'bottleneck', tuple(HEADS)), fx['hopenet']['out']):
+        assert rel(got, want) < 1e-5
+
+
+def _fake_traversal(tmp_path, n_paths=2, n_img=5, size=64):
+    from PIL import Image
+    exp = tmp_path / 'exp'
+    h_dir = exp / 'results' / 'pool' / '4_0.2_0.8' / 'abc123'
+    rng = np.random.RandomState(3)
+    for d in range(n_paths):
+        pdir = h_dir / 'paths_images' / ('path_%03d' % d)
+        pdir.mkdir(parents=True)
+        for t in range(n_img):
+            Image.fromarray(rng.randint(0, 256, (size, size, 3), dtype=np.uint8)).save(str(pdir / ('%06d.jpg' % t)), quality=95)
+    torch.save(torch.zeros(n_paths, n_img, 8), str(h_dir / 'paths_latent_codes.pt'))
+    (exp / 'args.json').write_text(json.dumps({'gan_type': 'StyleGAN2'}))
+    return str(exp), str(h_dir)
+
+
+def test_driver_files_and_score_arithmetic_with_stub_predictors(tmp_path):
+    """Directory walk, per-path batches, the reference's score formulas and output files - with stub predictors that
+    return fixed logits, so this runs without a GPU."""
+    from warpedganspace_b200 import attribute_space as A
+    exp, h_dir = _fake_traversal(tmp_path)
+    g = gen(9)
+    ff_logits = torch.randn(5, 18, generator=g)
+    pose_logits = [torch.randn(5, 66, generator=g) for _ in range(3)]
+    seen = {}
+
+    def fairface(x):
+        seen['fairface'] = tuple(x.shape)
+        return ff_logits
+
+    def hopenet(x):
+        seen['hopenet'] = tuple(x.shape)
+        return tuple(pose_logits)
+
+    def detector(x):          # one box on even frames, none on odd ones
+        return [[[60.0, 70.0, 200.0, 220.0, 0.99]] if t % 2 == 0 else [] for t in range(x.shape[0])]
+
+    done = A.traverse_attribute_space(exp, 'pool', shift_steps=2, eps=0.2, device='cpu',
+                                      predictors={'fairface': fairface, 'hopenet': hopenet, 'face_detector': detector})
+    assert done == [h_dir]
+    assert seen == {'fairface': (5, 3, 224, 224), 'hopenet': (5, 3, 224, 224)}
+    gender, age, race = o_en.fairface_scores(ff_logits)
+    yaw, pitch, roll = o_en.hopenet_pose(*pose_logits)
+    nd, jd = os.path.join(h_dir, 'eval_np'), os.path.join(h_dir, 'eval_json')
+    for name, want in (('gender', gender), ('age', age), ('race', race)):
+        got = np.load(os.path.join(nd, name + '.npy'))
+        assert got.shape == (2, 5) and np.allclose(got[0], want.numpy(), atol=1e-6) and np.allclose(got[1], want.numpy(), atol=1e-6)
+    for name, want in (('yaw', yaw), ('pitch', pitch), ('roll', roll)):
+        assert np.allclose(np.load(os.path.join(nd, name + '.npy'))[1], want.numpy() * np.pi / 180, atol=1e-5)
+    pose = json.load(open(os.path.join(jd, 'pose.json')))
+    assert sorted(pose) == ['0', '1'] and np.allclose(pose['0'][0], yaw.numpy(), atol=1e-4)
+    fw = np.load(os.path.join(nd, 'face_width.npy'))
+    assert np.allclose(fw[0], [140 / 256.0, 256.0, 140 / 256.0, 256.0, 140 / 256.0])       # (sic: 256.0 when nothing is detected)
+    bbox = json.load(open(os.path.join(jd, 'face_bbox.json')))
+    assert len(bbox['0']) == 3 and bbox['0'][0][:4] == [60.0, 70.0, 200.0, 220.0]
+    assert not os.path.exists(os.path.join(nd, 'identity.npy'))            # predictors that were not given write nothing
+
+
+def test_crop_face_follows_the_reference():
+    from warpedganspace_b200 import attribute_space as A
+    imgs = torch.arange(2 * 3 * 256 * 256, dtype=torch.float32).reshape(2, 3, 256, 256)
+    c = A.crop_face(imgs, 1, [60, 70, 200, 220], padding=0.25)
+    # x: int(0.75*60) - 50 < 0 -> 0 .. int(1.25*200) + 50 > 256 -> 256;  y: int(0.75*70) - 50 = 2 .. min(256, int(1.25*220) + 30)
+    assert c.shape == (1, 3, 256, 254) and torch.equal(c[0], imgs[1, :, 0:256, 2:256])
+
+
+@pytest.mark.gpu
+def test_fairface_and_hopenet_kernel_chains_match_the_reference_fixture(golden):
+    from warpedganspace_b200.eval_resnet import fairface_resnet34, hopenet_resnet50
+    torch.backends.cudnn.allow_tf32 = False
+    fx = golden('eval_nets.pt')
+    x = torch.randn(2, 3, 224, 224, generator=gen(fx['seed_x'])).cuda()
+    sd = o_en.init_state('basic', {'fc': 18}, gen(fx['fairface']['seed']))
+    net = fairface_resnet34()
+    assert set(net.state_dict()) == set(sd)                    # torchvision's key names: published checkpoints load as they are
+    net.load_state_dict(sd, strict=True)
+    net.cuda()
+    out = net(x)
+    assert rel(out, fx['fairface']['out']) < 1e-3              # 36 convs, bf16x3 operands; measured ~1e-5
+    assert torch.equal(out.argmax(1).cpu(), fx['fairface']['out'].argmax(1))
+    sd = o_en.init_state('bottleneck', HEADS, gen(fx['hopenet']['seed']))
+    net = hopenet_resnet50()
+    assert set(net.state_dict()) - set(sd) == {'fc_finetune.weight', 'fc_finetune.bias'}
+    net.load_state_dict(sd, strict=False)
+    net.cuda()
+    for got, want in zip(net(x), fx['hopenet']['out']):
+        assert rel(got, want) < 1e-3
+    with pytest.raises(RuntimeError):
+        net(x.cpu())                                           # no CPU fallback
+
+
+@pytest.mark.gpu
+def test_attribute_traversal_end_to_end_on_the_gpu(tmp_path):
+    """Frames on disk -> crops -> the two kernel-chain predictors -> the reference's files, against the oracle run on the
+    very same crops."""
+    from warpedganspace_b200 import attribute_space as A
+    from warpedganspace_b200.eval_resnet import fairface_resnet34, hopenet_resnet50
+    exp, h_dir = _fake_traversal(tmp_path, n_paths=1, n_img=3, size=96)
+    sd_f = o_en.init_state('basic', {'fc': 18}, gen(21))
+    sd_h = o_en.init_state('bottleneck', HEADS, gen(22))
+    ff, hp = fairface_resnet34(), hopenet_resnet50()
+    ff.load_state_dict(sd_f)
+    hp.load_state_dict(sd_h, strict=False)
+    ff.cuda(); hp.cuda()
+    crops = {}
+
+    def tap(name, net):
+        def run(x):
+            crops[name] = x.detach().cpu()
+            return net(x)
+        return run
+
+    A.traverse_attribute_space(exp, 'pool', shift_steps=2, eps=0.2, predictors={'fairface': tap('f', ff), 'hopenet': tap('h', hp)})
+    gender, age, race = o_en.fairface_scores(o_en.resnet_forward(sd_f, crops['f'], 'basic', ('fc',))[0])
+    nd = os.path.join(h_dir, 'eval_np')
+    assert np.allclose(np.load(os.path.join(nd, 'gender.npy'))[0], gender.numpy(), atol=2e-3)
+    assert np.allclose(np.load(os.path.join(nd, 'race.npy'))[0], race.numpy(), atol=2e-3)
+    yaw, _, _ = o_en.hopenet_pose(*o_en.resnet_forward(sd_h, crops['h'], 'bottleneck', tuple(HEADS)))
+    assert np.allclose(np.load(os.path.join(nd, 'yaw.npy'))[0], yaw.numpy() * np.pi / 180, atol=2e-3)
