@@ -1,17 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_attribute_space.py -q -m gpu 2>&1 | tail -15
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/n2.json 2> gpurun_out/n2.err
+cut -c1-400 gpurun_out/n2.json; tail -5 gpurun_out/n2.err
 python - <<'PY'
-import torch, time
-from warpedganspace_b200.eval_resnet import fairface_resnet34, hopenet_resnet50
-for name, mk in (('fairface resnet34', fairface_resnet34), ('hopenet resnet50', hopenet_resnet50)):
-    net = mk().cuda()
-    x = torch.randn(33, 3, 224, 224, device='cuda')
-    for _ in range(3): net(x)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): net(x)
-    e1.record(); torch.cuda.synchronize()
-    print('%s: %.2f ms per batch of 33 crops (eager)' % (name, e0.elapsed_time(e1) / 10))
+import json
+for l in open('gpurun_out/n2.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print({k:d.get(k) for k in ('value','ms_per_step','n_gpus','cuda_graph','e2e')})
 PY
