@@ -475,3 +475,16 @@ def test_space_to_depth_pack_of_two_images_equals_the_pack_of_their_concatenatio
     pair = conv.s2d_pack_split32(x1, x2)
     whole = conv.s2d_pack_split32(torch.cat([x1, x2], dim=3).contiguous())
     assert pair.shape == whole.shape and torch.equal(pair, whole)
+
+
+@pytest.mark.parametrize('N,Ci,H,W,Co', [(2, 16, 64, 264, 3), (1, 3, 72, 256, 16), (2, 32, 64, 320, 32)])
+def test_single_chunk_1x1_conv_on_a_wide_map(N, Ci, H, W, Co):
+    """ProgGAN's to-RGB layer (16 -> 3, 1 x 1, models/ProgGAN/model.py:86-90) and its data gradient at 1024^2 are bandwidth
+    work: they run on the multi-tile kernel with the single tap resident instead of one 128-pixel tile per CTA."""
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(N * 7 + Ci + Co)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda()
+    w = (torch.randn(Co, Ci, 1, 1, generator=g) / Ci ** 0.5).cuda()
+    b = torch.randn(Co, generator=g).cuda()
+    got = conv.conv2d(conv.pack_split32(nhwc(x)), conv.pack_weights(w), 1, 1, beta=b, cin=Ci)
+    assert rel(got, nhwc(F.conv2d(x, w, b))) < 2e-5

@@ -1,10 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/n2.json 2> gpurun_out/n2.err
-cut -c1-400 gpurun_out/n2.json; tail -5 gpurun_out/n2.err
-python - <<'PY'
-import json
-for l in open('gpurun_out/n2.json'):
-    if l.startswith('{'):
-        d=json.loads(l); print({k:d.get(k) for k in ('value','ms_per_step','n_gpus','cuda_graph','e2e')})
-PY
+python -m pytest tests/test_conv_gpu.py tests/test_generators_gpu.py -q -m gpu 2>&1 | tail -4
+for c in c2 c3; do python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | cut -c1-200; done

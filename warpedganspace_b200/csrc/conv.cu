@@ -1156,7 +1156,11 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
                          2 * d->num_taps * hBN * 128 + 3 * a_bytes + MT_STG_BYTES + 4096 <= 227 * 1024;
         while (!big_mt && !mt2 && hBN > 32 && hBN % 32 == 0 && a_bytes + d->num_taps * hBN * 128 > h_limit) hBN /= 2;
         const int h_stage = a_bytes + d->num_taps * hBN * 128;
-        const bool eligible = halo_mode && p.ksplit == 1 && d->in_stride == 1 && d->num_taps >= 3 && wy <= 7 && wx <= 7 &&
+        // (single-chunk 1 x 1 convs on wide maps too - ProgGAN's 16 -> 3 to-RGB layer at 1024^2 and its data gradient: on the
+        // one-tile-per-CTA kernel that is 131072 CTAs and 1.14 ms for a bandwidth-bound 1 GB read; the multi-tile kernel
+        // keeps its single tap resident and streams the pixel rows)
+        const bool narrow_1x1 = stack && d->c_chunks == 1 && d->num_taps < 3 && ceil_div(d->grid_w, 8) >= 32 && d->grid_h >= 64;
+        const bool eligible = halo_mode && p.ksplit == 1 && d->in_stride == 1 && (d->num_taps >= 3 || narrow_1x1) && wy <= 7 && wx <= 7 &&
                               d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && (h_stage <= h_limit || big_mt || mt2) &&
                               (d->c_chunks == 1 || mt2 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4) ||
                                (halo_wide && d->c_chunks == 2 && d->cout <= 64 && d->num_taps >= 4));
