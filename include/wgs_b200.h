@@ -203,6 +203,12 @@ typedef struct wgs_conv_desc {
     float* stat_sum;
     float* stat_sumsq;
     const float* stat_shift;
+    /* > 0: the split32 output holds pixel_norm(act) = act * rsqrt(mean_c act^2 + pixnorm_eps) instead of act (ProgGAN's
+     * PixelNormLayer, models/ProgGAN/model.py:17-18, fused with the conv that feeds it and the pack of the conv that follows):
+     * cout <= 256 (one channel tile holds every channel of a pixel), output maps of >= 128 pixels.  The fp32 output stays the
+     * un-normalised activation (the backward pass needs it).  With a strided output mapping (output-phase launches of an
+     * up-sampling conv) out_split is addressed by output pixel and out_h / out_w give its dims.                           */
+    float pixnorm_eps;
 } wgs_conv_desc;
 
 /* One implicit-GEMM convolution on tcgen05 tensor cores (see csrc/conv.cu).  Replaces the cuDNN calls

@@ -488,3 +488,36 @@ def test_single_chunk_1x1_conv_on_a_wide_map(N, Ci, H, W, Co):
     b = torch.randn(Co, generator=g).cuda()
     got = conv.conv2d(conv.pack_split32(nhwc(x)), conv.pack_weights(w), 1, 1, beta=b, cin=Ci)
     assert rel(got, nhwc(F.conv2d(x, w, b))) < 2e-5
+
+
+@pytest.mark.parametrize('N,Ci,H,W,Co,up', [(2, 32, 16, 40, 16, False), (2, 64, 24, 24, 32, False), (3, 128, 16, 16, 128, False),
+                                            (2, 32, 16, 24, 16, True), (2, 256, 16, 16, 128, True), (1, 32, 64, 136, 16, False)])
+def test_pixel_norm_fused_into_the_conv_epilogue(N, Ci, H, W, Co, up):
+    """wgs_conv_desc.pixnorm_eps: the split32 output holds pixel_norm(leaky_relu(conv + b)) (ProgGAN's block boundary,
+    models/ProgGAN/model.py:17-18,42-62), the fp32 output the un-normalised activation of the back-propagated rows only;
+    16-channel outputs fill half a chunk (upper half written as zeros); with `up` the four output-phase launches of
+    conv3x3(nearest_x2(x)) address the split32 tensor by output pixel."""
+    from warpedganspace_b200 import conv
+    from warpedganspace_b200.generators import up_conv_weights, up_conv_forward
+    g = torch.Generator().manual_seed(N + Ci + Co + H)
+    x = torch.randn(N, Ci, H, W, generator=g).cuda()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (Ci * 9) ** 0.5).cuda()
+    b = torch.randn(Co, generator=g).cuda()
+    xs = conv.pack_split32(nhwc(x))
+    src = F.interpolate(x, scale_factor=2, mode='nearest') if up else x
+    act = F.leaky_relu(F.conv2d(src, w, b, padding=1), 0.2)
+    want = nhwc(act * torch.rsqrt((act * act).mean(dim=1, keepdim=True) + 1e-8))
+    oh, ow = act.shape[2], act.shape[3]
+    out = torch.full((N, oh, ow, Co), 7.0).cuda()
+    nxt = torch.full((N, oh, ow, (Co + 31) // 32, 64), 3.0, dtype=torch.bfloat16).cuda()
+    if up:
+        w_fwd, taps, _ = up_conv_weights(w)
+        up_conv_forward(xs, w_fwd, taps, Co, Ci, out=out, beta=b, act=2, out_split=nxt, pixnorm_eps=1e-8, out_from_n=1)
+    else:
+        conv.conv2d(xs, conv.pack_weights(w), 3, 3, padding=1, out=out, beta=b, act=2, cin=Ci, out_split=nxt, pixnorm_eps=1e-8,
+                    out_from_n=1)
+    assert float((out[0] - 7.0).abs().max()) == 0.0 and rel(out[1:], nhwc(act)[1:]) < 2e-5
+    got = _unsplit(nxt)
+    assert rel(got[..., :Co], want) < 3e-5
+    if Co % 32:
+        assert float(got[..., Co:].abs().max()) == 0.0                  # the padding half-chunk is zero, not stale

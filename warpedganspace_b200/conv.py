@@ -53,6 +53,7 @@ class ConvDesc(ctypes.Structure):
         ('group_size', ctypes.c_int), ('group_w', ctypes.c_int), ('out_h', ctypes.c_int), ('out_w', ctypes.c_int),
         ('w_layout', ctypes.c_int), ('split_k', ctypes.c_int),
         ('stat_sum', ctypes.c_void_p), ('stat_sumsq', ctypes.c_void_p), ('stat_shift', ctypes.c_void_p),
+        ('pixnorm_eps', ctypes.c_float),
     ]
 
 
@@ -205,7 +206,7 @@ def pack_weights(w):
 def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 0), out_step=(1, 1), cout=None,
               alpha=None, beta=None, act=0, accumulate=False, force_bn=0, noise=None, noise_w=0.0, cin=None,
               out_split=None, split_scale=None, out_from_n=0, rgb_w=None, rgb_out=None, out_n=None, groups=None,
-              algo_macs_per_pixel=None, split_k=False, stats=None):
+              algo_macs_per_pixel=None, split_k=False, stats=None, pixnorm_eps=0.0):
     """Generic tap-list conv.  x_split [N, H, W, chunks, 64] bf16; w_split [T, Co, chunks, 64] bf16;
     taps: list of (dy, dx, weight_tap); out: fp32 NHWC [N, OH, OW, Cstride] (any strides, channel stride 1);
     grid: (grid_h, grid_w) virtual output grid; output pixel = grid*out_step + out_origin."""
@@ -249,6 +250,9 @@ def conv_taps(x_split, w_split, taps, out, *, grid, in_stride=1, out_origin=(0, 
     if groups is not None:                       # phase-packed output: (group_size, group_w), see include/wgs_b200.h
         d.group_size, d.group_w = groups
         d.out_h, d.out_w = out.shape[1], out.shape[2]
+    d.pixnorm_eps = float(pixnorm_eps)
+    if out_split is not None and (tuple(out_origin) != (0, 0) or tuple(out_step) != (1, 1)):
+        d.out_h, d.out_w = out_split.shape[1], out_split.shape[2]      # split32 output addressed by output pixel
     if noise is not None:
         assert noise.is_contiguous() and noise.dim() == 2
         d.noise, d.noise_w, d.noise_ld = noise.data_ptr(), float(noise_w), noise.shape[1]

@@ -61,6 +61,8 @@ struct ConvKernelParams {
     int coalesce;                            // stage epilogue stores through shared memory (coalesced 64-byte rows)
     int tiles_per_cta, x_groups;             // multi-tile halo kernel: consecutive x tiles handled by one CTA
     int w_cout;                              // rows of the weight tensor (stacked layout addressing, SIMT twin)
+    float pixnorm_eps;                       // > 0: out_split holds pixel_norm(act) = act * rsqrt(mean_c act^2 + eps) (ProgGAN)
+    int split_hw;                            // out_split addressed by OUTPUT pixel (strided output mapping), dims out_h x out_w
     float* stat_sum;                         // BatchNorm statistics of the output (plain epilogue): shifted sum / sum of squares
     float* stat_sumsq;
     const float* stat_shift;
@@ -207,6 +209,38 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
     const uint32_t ep_s = ptx::smem_u32(ep);                 // explicit ld.shared: the generic pointer costs LD.E + a stall per use
     const uint32_t stg_s = stg ? ptx::smem_u32(stg) + (uint32_t)q * 2048u : 0u;
     float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+    // split32 output addressed by grid pixel (identity mapping) or, for the output-phase launches of an up-sampling conv,
+    // by OUTPUT pixel
+    const size_t pix_split = (FUSED && p.split_hw) ? ((size_t)n * p.out_h + py0) * p.out_w + px0 : pix;
+    // ProgGAN's pixel norm of the activation (models/ProgGAN/model.py:17-18), fused: the tile holds every channel of its
+    // pixels (one channel tile, host-checked), a thread owns a pixel, so mean_c act^2 is a private sum over a first pass
+    // through the accumulator columns (TMEM is re-read below: cheaper than 256 live registers)
+    float pn = 1.f;
+    if constexpr (FUSED) {
+        if (p.pixnorm_eps > 0.f) {
+            float ss = 0.f;
+            for (int c = 0; c < BN; c += 16) {
+                float t[16];
+                if constexpr (STACK)
+                    ptx::tmem_ld16_sum(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c,
+                                       tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), t);
+                else
+                    ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, t);
+                const uint32_t ea = ep_s + (uint32_t)c * 4u, eb = ea + (uint32_t)BN * 4u;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 al = ptx::lds128(ea + i * 4), be = ptx::lds128(eb + i * 4);
+                    const float a0 = apply_act(fmaf(t[i + 0], al.x, nz) + be.x, p.act), a1 = apply_act(fmaf(t[i + 1], al.y, nz) + be.y, p.act),
+                                a2 = apply_act(fmaf(t[i + 2], al.z, nz) + be.z, p.act), a3 = apply_act(fmaf(t[i + 3], al.w, nz) + be.w, p.act);
+                    if (co0 + c + i + 0 < p.cout) ss += a0 * a0;
+                    if (co0 + c + i + 1 < p.cout) ss += a1 * a1;
+                    if (co0 + c + i + 2 < p.cout) ss += a2 * a2;
+                    if (co0 + c + i + 3 < p.cout) ss += a3 * a3;
+                }
+            }
+            pn = rsqrtf(ss / (float)p.cout + p.pixnorm_eps);
+        }
+    }
     const int c_lo = n_ranks ? my_rank * (BN / n_ranks) : 0, c_hi = n_ranks ? c_lo + BN / n_ranks : BN;
     for (int c = c_lo; c < c_hi; c += 16) {
         float v[16];
@@ -379,7 +413,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                 const uint32_t es = ep_s + (uint32_t)(2 * BN + c) * 4u;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                    const float4 sc4 = ptx::lds128(es + i * 4);
+                    float4 sc4 = ptx::lds128(es + i * 4);
+                    sc4.x *= pn; sc4.y *= pn; sc4.z *= pn; sc4.w *= pn;
                     split_bf16x2(v[i + 0] * sc4.x, v[i + 1] * sc4.y, reinterpret_cast<__nv_bfloat162*>(hi)[i >> 1],
                                  reinterpret_cast<__nv_bfloat162*>(lo)[i >> 1]);
                     split_bf16x2(v[i + 2] * sc4.z, v[i + 3] * sc4.w, reinterpret_cast<__nv_bfloat162*>(hi)[(i >> 1) + 1],
@@ -389,19 +424,29 @@ __device__ __forceinline__ void conv_epilogue(const ConvKernelParams& p, uint32_
                 const float* sc = (!cs && p.split_scale) ? p.split_scale + (size_t)n_rd * p.split_scale_ld + co : nullptr;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    split_bf16(cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i]), hi[i], lo[i]);
+                    split_bf16(pn * (cs ? v[i] * ep[2 * BN + c + i] : (sc ? v[i] * __ldg(sc + i) : v[i])), hi[i], lo[i]);
             }
-            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix * (size_t)(p.cout * 2) +
+            __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + pix_split * (size_t)(((p.cout + 31) >> 5) * 64) +
                                 (size_t)(co >> 5) * 64 + (co & 16);
+            // cout = 16 (mod 32): the last chunk is half full - its upper 16 channels are written as zeros (warp-uniform)
+            const bool pad_half = ((p.cout & 31) == 16) && (co + 16 == p.cout);
             if (stg_s) {
                 const uint4 q4[4] = {reinterpret_cast<const uint4*>(hi)[0], reinterpret_cast<const uint4*>(hi)[1],
                                      reinterpret_cast<const uint4*>(lo)[0], reinterpret_cast<const uint4*>(lo)[1]};
                 warp_store_rows64(stg_s, lane, q4, lane_ok ? sp : nullptr, 64u);
-            } else {
+                if (pad_half) {
+                    const uint4 z4[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                    warp_store_rows64(stg_s, lane, z4, lane_ok ? sp + 16 : nullptr, 64u);
+                }
+            } else if (lane_ok) {
                 reinterpret_cast<uint4*>(sp)[0] = reinterpret_cast<const uint4*>(hi)[0];
                 reinterpret_cast<uint4*>(sp)[1] = reinterpret_cast<const uint4*>(hi)[1];
                 reinterpret_cast<uint4*>(sp + 32)[0] = reinterpret_cast<const uint4*>(lo)[0];
                 reinterpret_cast<uint4*>(sp + 32)[1] = reinterpret_cast<const uint4*>(lo)[1];
+                if (pad_half) {
+                    reinterpret_cast<uint4*>(sp + 16)[0] = make_uint4(0, 0, 0, 0); reinterpret_cast<uint4*>(sp + 16)[1] = make_uint4(0, 0, 0, 0);
+                    reinterpret_cast<uint4*>(sp + 48)[0] = make_uint4(0, 0, 0, 0); reinterpret_cast<uint4*>(sp + 48)[1] = make_uint4(0, 0, 0, 0);
+                }
             }
         }
         // (write_f32 is per image, hence per lane when a tile spans images; the collective path needs every lane)
@@ -983,6 +1028,14 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     p.out_from_n = d->out_from_n; p.rgb_w = d->rgb_w; p.rgb_out = d->rgb_out;
     p.group_size = d->group_size; p.group_w = d->group_w; p.out_h = d->out_h; p.out_w = d->out_w;
     p.stat_sum = d->stat_sum; p.stat_sumsq = d->stat_sumsq; p.stat_shift = d->stat_shift;
+    p.pixnorm_eps = d->pixnorm_eps;
+    WGS_REQUIRE(d->pixnorm_eps >= 0.f, "conv: bad pixnorm_eps");
+    if (d->pixnorm_eps > 0.f) {
+        WGS_REQUIRE(d->out_split != nullptr && d->cout <= 256,
+                    "conv: the fused pixel norm needs a split32 output and at most 256 output channels (one channel tile)");
+        WGS_REQUIRE(p.bn == 1, "conv: the fused pixel norm needs output maps of at least 128 pixels (one image per tile)");
+        WGS_REQUIRE(!conv_impl_is_simt(), "conv: the fused pixel norm is not available on the SIMT cross-check path");
+    }
     WGS_REQUIRE((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), "conv: stat_sum and stat_sumsq go together");
     if (d->stat_sum) {
         WGS_REQUIRE(d->out != nullptr && !d->out_split && !d->rgb_out && d->out_from_n == 0 && d->group_size == 0 &&
@@ -1000,9 +1053,12 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         WGS_REQUIRE(d->out_h > 0 && d->out_w > 0, "conv: phase-packed output needs out_h / out_w");
     }
     WGS_REQUIRE(d->out != nullptr || d->out_split != nullptr || d->rgb_out != nullptr, "conv: no output requested");
-    WGS_REQUIRE((!d->out_split && !d->rgb_out) || (d->out_ystep == 1 && d->out_xstep == 1 && d->out_y0 == 0 && d->out_x0 == 0),
-                "conv: fused split32 / ToRGB outputs need the identity output mapping");
-    WGS_REQUIRE(!d->out_split || d->cout % 32 == 0, "conv: split32 output needs cout % 32 == 0");
+    const bool identity_map = d->out_ystep == 1 && d->out_xstep == 1 && d->out_y0 == 0 && d->out_x0 == 0;
+    WGS_REQUIRE(!d->rgb_out || identity_map, "conv: the fused ToRGB output needs the identity output mapping");
+    WGS_REQUIRE(!d->out_split || identity_map || (d->group_size == 0 && d->out_h > 0 && d->out_w > 0),
+                "conv: a split32 output under a strided output mapping needs out_h / out_w (the dims of that tensor)");
+    p.split_hw = (d->out_split && !identity_map) ? 1 : 0;
+    WGS_REQUIRE(!d->out_split || d->cout % 16 == 0, "conv: split32 output needs cout % 16 == 0");
     WGS_REQUIRE(!d->accumulate || d->out != nullptr, "conv: accumulate needs an fp32 output");
     for (int i = 0; i < d->num_taps; ++i) {
         WGS_REQUIRE(d->tap_dy[i] >= -64 && d->tap_dy[i] <= 64 && d->tap_dx[i] >= -64 && d->tap_dx[i] <= 64,
@@ -1015,6 +1071,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     int BN = std::min(256, (d->cout + 15) / 16 * 16);
     while (BN > 64 && m_tiles * ceil_div(d->cout, BN) < num_sms() && BN % 32 == 0) BN /= 2;
+    if (d->pixnorm_eps > 0.f) BN = (d->cout + 15) / 16 * 16;      // every channel of a pixel in one tile
     if (d->force_bn > 0) BN = d->force_bn;
     WGS_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "conv: bad N tile");
     static int coalesce_mode = -1;
@@ -1031,7 +1088,8 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         const char* e = getenv("WGS_CONV_SPLITK");
         splitk_mode = e ? ((e[0] == '1') ? 1 : 0) : -1;
     }
-    const bool splitk_on = splitk_mode < 0 ? (d->split_k != 0) : (splitk_mode == 1);
+    // (the fused pixel norm needs every channel of a pixel in ONE accumulator: never split)
+    const bool splitk_on = (splitk_mode < 0 ? (d->split_k != 0) : (splitk_mode == 1)) && d->pixnorm_eps <= 0.f;
     const bool stack = d->w_layout == 1;
     // Cluster split-K for tiny-M, deep-K launches: widest N tile (math-bound MMAs, one patch load per tile), then as many
     // K splits as fill about two CTAs per SM (<= 8: portable cluster size)
@@ -1161,6 +1219,7 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
         // keeps its single tap resident and streams the pixel rows)
         const bool narrow_1x1 = stack && d->c_chunks == 1 && d->num_taps < 3 && ceil_div(d->grid_w, 8) >= 32 && d->grid_h >= 64;
         const bool eligible = halo_mode && p.ksplit == 1 && d->in_stride == 1 && (d->num_taps >= 3 || narrow_1x1) && wy <= 7 && wx <= 7 &&
+                              (d->pixnorm_eps <= 0.f || hBN >= (d->cout + 15) / 16 * 16) &&
                               d->grid_h >= 16 && d->grid_w >= 8 && d->force_bn == 0 && (h_stage <= h_limit || big_mt || mt2) &&
                               (d->c_chunks == 1 || mt2 || (d->c_chunks == 2 && d->cout <= 32 && d->num_taps >= 4) ||
                                (halo_wide && d->c_chunks == 2 && d->cout <= 64 && d->num_taps >= 4));

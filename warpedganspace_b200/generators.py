@@ -13,6 +13,8 @@ over the low-resolution operand (2.25x fewer MACs).  Still library calls: BigGAN
 """
 import math
 
+import os
+
 import torch
 from torch import nn
 import torch.nn.functional as F
@@ -147,26 +149,51 @@ def _pixelnorm_bwd(dxn, a, slope, split):
     return out
 
 
+# 1 = the conv epilogue emits pixel_norm(act) as the next block's split32 operand (wgs_conv_desc.pixnorm_eps) instead of a
+# separate pixel-norm + pack pass.  Measured on one B200 (same call, B = 8): 23.5 / 23.3 ms fused vs 22.9 / 22.8 ms separate -
+# the <= 64-channel convs at 256^2 .. 1024^2 are epilogue / shared-memory-pipe bound, so work moved INTO their epilogue costs
+# more than a full-bandwidth pass of its own (the same outcome as BatchNorm statistics in the epilogue,
+# profiles/r02_experiments.md).  Kept as a tested A/B switch.
+FUSE_PIXNORM = os.environ.get('WGS_FUSE_PIXNORM', '0') == '1'
+
+
 def _proggan_forward(G, x, tape, grad_from):
-    """x [N, 512] -> image NHWC [N, H, W, 3]; tape (rows >= grad_from): the input activation of every block."""
+    """x [N, 512] -> image NHWC [N, H, W, 3]; tape (rows >= grad_from): the input activation of every block.
+
+    With FUSE_PIXNORM, from 64 x 64 upwards (one image per 128-pixel tile, <= 256 channels) the conv epilogue itself emits
+    the NEXT block's operand: pixel_norm(act) as split32 (wgs_conv_desc.pixnorm_eps) next to the fp32 activation of the
+    back-propagated rows, instead of the separate pixel-norm + pack pass."""
     P = G.plan()
     n = x.shape[0]
-    a = x.view(n, 1, 1, -1)
+    dev = x.device
+    a = x.view(n, 1, 1, -1).contiguous()
+    xs = _pixelnorm_pack(a)
     acts = []
     for e in P['blocks']:
-        a = a.contiguous()
-        acts.append(a[grad_from:])
-        xs = _pixelnorm_pack(a)
-        h, w = a.shape[1], a.shape[2]
-        if e['up']:
-            a = up_conv_forward(xs, e['w_fwd'], e['taps'], e['co'], e['ci'], beta=e['bias'], act=2, split_k=2)
+        if tape is not None:
+            acts.append(a[grad_from:])
+        h, w = xs.shape[1], xs.shape[2]
+        co = e['co']
+        oh, ow = (2 * h, 2 * w) if e['up'] else (h + 2 * e['pad'] - e['k'] + 1, w + 2 * e['pad'] - e['k'] + 1)
+        grid_px = h * w if e['up'] else oh * ow                        # pixels per image of one launch's output grid
+        fuse = FUSE_PIXNORM and co <= 256 and co % 16 == 0 and grid_px >= 128
+        need_f32 = (tape is not None) or not fuse
+        a = torch.empty(n, oh, ow, co, device=dev, dtype=torch.float32) if need_f32 else None
+        kw = dict(beta=e['bias'], act=2)
+        if fuse:
+            xs_next = torch.empty(n, oh, ow, C.chunks_of(co), 64, device=dev, dtype=torch.bfloat16)
+            kw.update(out_split=xs_next, pixnorm_eps=1e-8, out_from_n=grad_from if tape is not None else 0)
         else:
-            a = C.conv2d(xs, e['w_fwd'], e['k'], e['k'], padding=e['pad'], beta=e['bias'], act=2, cin=e['ci'], split_k=2)
-    acts.append(a[grad_from:])
-    img = C.conv2d(_pixelnorm_pack(a), P['w_out'], 1, 1, beta=P['b_out'], cin=P['c_out'])
+            kw.update(split_k=2)
+        if e['up']:
+            up_conv_forward(xs, e['w_fwd'], e['taps'], co, e['ci'], out=a, out_n=n, **kw)
+        else:
+            C.conv2d(xs, e['w_fwd'], e['k'], e['k'], padding=e['pad'], out=a, no_f32=a is None, cin=e['ci'], **kw)
+        xs = xs_next if fuse else _pixelnorm_pack(a)
     if tape is not None:
+        acts.append(a[grad_from:])
         tape['acts'] = acts
-    return img
+    return C.conv2d(xs, P['w_out'], 1, 1, beta=P['b_out'], cin=P['c_out'])
 
 
 def _proggan_backward(G, tape, dimg):
@@ -259,9 +286,10 @@ def up_conv_weights(w):
 
 
 def up_conv_forward(xs, w_fwd, taps, co, ci, out=None, **epilogue):
-    """conv3x3(nearest_x2(x)) from the low-resolution split32 operand xs [N, h, w, chunks, 64] -> fp32 [N, 2h, 2w, co]."""
+    """conv3x3(nearest_x2(x)) from the low-resolution split32 operand xs [N, h, w, chunks, 64] -> fp32 [N, 2h, 2w, co]
+    (with a fused split32 output in `epilogue`, `out` may stay None when `out_n` is given)."""
     n, h, w = xs.shape[0], xs.shape[1], xs.shape[2]
-    if out is None:
+    if out is None and epilogue.get('out_split') is None:
         out = torch.empty(n, 2 * h, 2 * w, co, device=xs.device, dtype=torch.float32)
     for (py, px), tp in taps.items():
         C.conv_taps(xs, w_fwd, tp, out, grid=(h, w), out_origin=(py, px), out_step=(2, 2), cout=co, cin=ci, **epilogue)
