@@ -17,5 +17,5 @@ ncu --profile-from-start off --clock-control none --metrics dram__bytes_read.sum
 python tools/ncu_traffic.py gpurun_out/${tag}_conv_traffic.csv gpurun_out/${tag}_conv_traffic.json > /dev/null 2>&1; head -c 300 gpurun_out/${tag}_conv_traffic.json
 ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/${tag}_top python tools/ncu_step.py 16 > gpurun_out/${tag}_top_ncu.log 2>&1
 python tools/ncu_table.py gpurun_out/${tag}_top.ncu-rep > gpurun_out/${tag}_top_table.md 2>&1
-SANITIZE_TIMEOUT=900 bash tools/sanitize.sh memcheck tests
-SANITIZE_TIMEOUT=600 bash tools/sanitize.sh racecheck tests/test_conv_gpu.py tests/test_rbf_gpu.py tests/test_stylegan2_gpu.py
+SANITIZE_TIMEOUT=1200 bash tools/sanitize.sh memcheck tests
+SANITIZE_TIMEOUT=900 bash tools/sanitize.sh racecheck tests/test_conv_gpu.py tests/test_rbf_gpu.py tests/test_stylegan2_gpu.py tests/test_reconstructor_gpu.py
