@@ -59,13 +59,17 @@ def algo_flops_per_unit(cfg):
     return cfg['F_G'] if cfg is CONFIGS['c5'] else 3 * cfg['F_G'] + 3 * cfg['F_R']
 
 
+CONV_SOURCES = ('warpedganspace_b200/csrc/conv.cu', 'warpedganspace_b200/csrc/ptx.cuh', 'warpedganspace_b200/csrc/common.cuh',
+                'include/wgs_b200.h')
+
+
 def source_stamp():
-    """sha1 over the CUDA sources: ties a committed ncu traffic capture to the kernels it measured."""
-    import glob
+    """sha1 over the sources of the tensor-core conv family (the kernels whose DRAM traffic the capture measures): ties a
+    committed ncu traffic capture to the kernels it measured."""
     import hashlib
     h = hashlib.sha1()
-    for p in sorted(glob.glob(os.path.join(ROOT, 'warpedganspace_b200', 'csrc', '*.cu*'))):
-        with open(p, 'rb') as f:
+    for rel in CONV_SOURCES:
+        with open(os.path.join(ROOT, rel), 'rb') as f:
             h.update(f.read())
     return h.hexdigest()[:16]
 
