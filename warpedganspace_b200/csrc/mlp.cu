@@ -17,7 +17,8 @@
 namespace wgs {
 
 constexpr int MLP_CLUSTER = 8;
-constexpr int MLP_THREADS = 1024;                 // 32 warps: two output features per warp per layer at d = 512, all loads in flight
+constexpr int MLP_THREADS = 512;                  // 16 warps x MLP_F output features each per pass (d = 512: one pass per layer)
+constexpr int MLP_F = 4;                          // features per warp per pass: every activation load is used for four rows of W
 constexpr int MLP_BT = 8;
 
 struct MlpChain {
@@ -70,18 +71,27 @@ mlp_chain_kernel(const __grid_constant__ MlpChain g) {
             __syncthreads();
         }
         const uint32_t nxt_s = ptx::smem_u32(nxt);
-        for (int o = rank * per + warp; o < (int)(rank + 1) * per; o += MLP_THREADS / 32) {
-            const float* wrow = q.W + (size_t)o * d;
+        // A warp computes MLP_F output features at once: the weight rows (MLP_F x 4 float4 per lane for d = 512) are all in
+        // flight together and every activation quad read from shared memory feeds MLP_F dot products - one feature per warp
+        // re-read the whole [B, d] activation block per feature, 1 MB of shared-memory traffic per CTA and layer.
+        for (int o0 = rank * per + warp * MLP_F; o0 < (int)(rank + 1) * per; o0 += (MLP_THREADS / 32) * MLP_F) {
             for (int b0 = 0; b0 < B; b0 += MLP_BT) {
-                float acc[MLP_BT];
+                float acc[MLP_F][MLP_BT];
 #pragma unroll
-                for (int t = 0; t < MLP_BT; ++t) acc[t] = 0.f;
+                for (int f = 0; f < MLP_F; ++f)
+#pragma unroll
+                    for (int t = 0; t < MLP_BT; ++t) acc[f][t] = 0.f;
                 for (int i0 = lane * 4; i0 < d; i0 += 512) {
-                    float4 w4[4];                                   // the whole 512-wide slice of the row in flight at once
+                    float4 w4[MLP_F][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = i0 + j * 128;
-                        w4[j] = i < d ? __ldg(reinterpret_cast<const float4*>(wrow + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int f = 0; f < MLP_F; ++f) {
+                        const bool f_ok = o0 + f < (int)(rank + 1) * per;
+                        const float* wrow = q.W + (size_t)(f_ok ? o0 + f : o0) * d;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = i0 + j * 128;
+                            w4[f][j] = (f_ok && i < d) ? __ldg(reinterpret_cast<const float4*>(wrow + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
 #pragma unroll
                     for (int t = 0; t < MLP_BT; ++t) {
@@ -91,22 +101,31 @@ mlp_chain_kernel(const __grid_constant__ MlpChain g) {
                                 const int i = i0 + j * 128;
                                 if (i < d) {
                                     const float4 x4 = *reinterpret_cast<const float4*>(cur + (size_t)(b0 + t) * d + i);
-                                    acc[t] += w4[j].x * x4.x + w4[j].y * x4.y + w4[j].z * x4.z + w4[j].w * x4.w;
+#pragma unroll
+                                    for (int f = 0; f < MLP_F; ++f)
+                                        acc[f][t] += w4[f][j].x * x4.x + w4[f][j].y * x4.y + w4[f][j].z * x4.z + w4[f][j].w * x4.w;
                                 }
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int t = 0; t < MLP_BT; ++t) acc[t] = warp_sum(acc[t]);
-                if (lane < MLP_BT && b0 + lane < B) {
-                    float v = 0.f;
+                for (int f = 0; f < MLP_F; ++f) {
 #pragma unroll
-                    for (int t = 0; t < MLP_BT; ++t) if (t == lane) v = acc[t];
+                    for (int t = 0; t < MLP_BT; ++t) acc[f][t] = warp_sum(acc[f][t]);
+                }
+                // lane (f * MLP_BT + t) finishes feature o0 + f of batch row b0 + t
+                const int f_mine = lane / MLP_BT, t_mine = lane % MLP_BT;
+                float v = 0.f;
+#pragma unroll
+                for (int f = 0; f < MLP_F; ++f)
+#pragma unroll
+                    for (int t = 0; t < MLP_BT; ++t) if (f == f_mine && t == t_mine) v = acc[f][t];
+                const int o = o0 + f_mine, b = b0 + t_mine;
+                if (f_mine < MLP_F && o < (int)(rank + 1) * per && b < B) {
                     v *= g.wscale;
                     if (q.bias) v += g.bscale * __ldg(q.bias + o);
                     if (g.epi == 1) v = 1.41421356237309515f * (v > 0.f ? v : 0.2f * v);
-                    const int b = b0 + lane;
                     if (q.out) q.out[(size_t)b * d + o] = v;
                     const uint32_t off = nxt_s + (uint32_t)((size_t)b * d + o) * 4u;
 #pragma unroll
