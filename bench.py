@@ -489,7 +489,7 @@ def conv_roofline(prof, prof_ms_total, n_prof, cfg, units_per_step, ms_step):
                      % (3 * issued_fl / (conv_ms * 1e-3) / 1e12 / pk['bf16_tflops'] if conv_ms else 0.0),
         'launches': len(conv), 'avg_launch_ms': conv_ms / max(1, len(conv)),
         'share_of_step': conv_ms / prof_ms_total if prof_ms_total else None,
-        'measured_over': '%d instrumented eager step(s) (CUDA events around every launch; %.2f ms/step eager)' % (n_prof, prof_ms_total / n_prof),
+        'measured_over': '%d instrumented eager step(s) on ONE stream (CUDA events around every launch, side streams off so that no launch shares the SMs; %.2f ms/step eager)' % (n_prof, prof_ms_total / n_prof),
         'wgrad_kernel': {'achieved': (sum(r[1] for r in wg) / (sum(t_of(r) for r in wg) * 1e-3) / 1e12) if wg else None,
                          'launches': len(wg), 'share_of_step': sum(t_of(r) for r in wg) / prof_ms_total if prof_ms_total and wg else None},
         'whole_step_algorithmic_tflops': algo_flops_per_unit(cfg) * units_per_step / (ms_step * 1e-3) / 1e12,
@@ -603,6 +603,10 @@ def main():
     # ---- instrumented eager steps: per-launch CUDA-event timing of the tensor-core kernels (roofline) -----------------
     # (events cannot be recorded inside a CUDA graph, so the per-launch numbers come from eager steps of the same
     #  workload run right after the timed regions)
+    # The side streams are switched off for these steps: a per-launch event pair must bracket ONE kernel running alone, not a
+    # conv sharing the SMs with a weight-gradient kernel of the side stream (that is what the timed regions above measure).
+    side_env = os.environ.get('WGS_SIDE_STREAMS')
+    os.environ['WGS_SIDE_STREAMS'] = '0'
     for i in range(2):
         trainer.step(*batches[i], eager=True)
     torch.cuda.synchronize()
@@ -617,6 +621,10 @@ def main():
     torch.cuda.synchronize()
     launches = _lib.launch_count() / n_prof
     prof, C.PROFILE = C.PROFILE, None
+    if side_env is None:
+        os.environ.pop('WGS_SIDE_STREAMS', None)
+    else:
+        os.environ['WGS_SIDE_STREAMS'] = side_env
     if rank != 0:
         return
     roofline = conv_roofline(prof, p0.elapsed_time(p1), n_prof, cfg, B, ms_step)
