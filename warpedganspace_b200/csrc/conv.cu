@@ -1070,7 +1070,15 @@ extern "C" int wgs_conv_split32(const wgs_conv_desc* d, void* stream) {
     // N tile: as wide as possible (fewer re-reads of the input patch) but keep >= ~1 wave of CTAs
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     int BN = std::min(256, (d->cout + 15) / 16 * 16);
-    while (BN > 64 && m_tiles * ceil_div(d->cout, BN) < num_sms() && BN % 32 == 0) BN /= 2;
+    static int bn_fill = -1;
+    if (bn_fill < 0) {
+        // percent of the SMs a launch must fill before its N tile stops halving.  80: a launch that reaches 118 .. 147 CTAs with the
+        // widest tile keeps it (256 -> 256 @64^2 x 4 images: 128 CTAs of N = 256 instead of 256 CTAs of N = 128 - these
+        // launches are L2 -> SM bound, and the wide tile re-loads the pixel operand half as often; same call 16.22 vs 16.37 ms)
+        const char* e = getenv("WGS_BN_FILL");
+        bn_fill = e ? atoi(e) : 80;
+    }
+    while (BN > 64 && m_tiles * ceil_div(d->cout, BN) * 100 < num_sms() * bn_fill && BN % 32 == 0) BN /= 2;
     if (d->pixnorm_eps > 0.f) BN = (d->cout + 15) / 16 * 16;      // every channel of a pixel in one tile
     if (d->force_bn > 0) BN = d->force_bn;
     WGS_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, "conv: bad N tile");
