@@ -562,11 +562,13 @@ class _GBlockFn(torch.autograd.Function):
         co = e['co']
         r1s = affine_act_pack(x, A1.detach(), B1.detach(), relu=True)
         xs = affine_act_pack(x, relu=False)
+        # (split_k = 2: batch-independent cluster split-K for the 4 x 4 .. 16 x 16 blocks - 1536 .. 384 channels, up to 432
+        # dependent contraction steps per CTA otherwise)
         out = up_conv_forward(xs, e['wsc'], {(py, px): [(0, 0, 0)] for py in range(2) for px in range(2)}, co, ci,
-                              beta=e['b_conv_sc'])
-        h1 = up_conv_forward(r1s, e['w1'], e['taps1'], co, ci, beta=e['b_conv1'])
+                              beta=e['b_conv_sc'], split_k=2)
+        h1 = up_conv_forward(r1s, e['w1'], e['taps1'], co, ci, beta=e['b_conv1'], split_k=2)
         r2s = affine_act_pack(h1, A2.detach(), B2.detach(), relu=True)
-        C.conv2d(r2s, e['w2'], 3, 3, padding=1, out=out, accumulate=True, beta=e['b_conv2'], cin=co)
+        C.conv2d(r2s, e['w2'], 3, 3, padding=1, out=out, accumulate=True, beta=e['b_conv2'], cin=co, split_k=2)
         if any(ctx.needs_input_grad[:5]):
             ctx.save_for_backward(x, h1, A1, B1, A2, B2)
         ctx.e = e
@@ -579,13 +581,13 @@ class _GBlockFn(torch.autograd.Function):
         n, h, w, ci = x.shape
         co = e['co']
         ds = C.pack_split32(d_out.contiguous())
-        dr2 = C.conv2d(ds, e['w2_bwd'], 3, 3, padding=1, cout=co, cin=co)
+        dr2 = C.conv2d(ds, e['w2_bwd'], 3, 3, padding=1, cout=co, cin=co, split_k=2)
         dh1s, dA2, dB2 = affine_act_bwd(dr2, h1, A2.detach(), B2.detach(), relu=True, split=True)
-        dr1 = C.conv2d(dh1s, e['w1_bwd'], 4, 4, stride=2, padding=1, cout=ci, cin=co)                # adjoint of up + conv1
+        dr1 = C.conv2d(dh1s, e['w1_bwd'], 4, 4, stride=2, padding=1, cout=ci, cin=co, split_k=2)     # adjoint of up + conv1
         dx, dA1, dB1 = affine_act_bwd(dr1, x, A1.detach(), B1.detach(), relu=True, split=False)
         # shortcut: adjoint of up(conv_sc(x)) = conv_sc^T of the 2x2 sum-pooled gradient = four stride-2 taps of the 1x1 weight
         C.conv_taps(ds, e['wsc_bwd'], [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)], dx, grid=(h, w), in_stride=2, cout=ci,
-                    cin=co, accumulate=True)
+                    cin=co, accumulate=True, split_k=2)
         return dx, dA1, dB1, dA2, dB2, None
 
 
