@@ -90,6 +90,13 @@ class BigGANWrapper(nn.Module):
         classes = self.mixed_classes(z.shape[0]).to(z.device)
         return self.G(z if shift is None else z + shift, self.G.shared(classes))
 
+    def forward_pair(self, z, shift):
+        """(G(z), G(z, shift)) in one batched pass (fast path of lib/trainer.py:200,239).  The class ids are drawn exactly as
+        the two separate calls would draw them: once for the un-shifted images, then once for the shifted ones."""
+        c_plain = self.mixed_classes(z.shape[0]).to(z.device)
+        c_shift = self.mixed_classes(z.shape[0]).to(z.device)
+        return self.G.synthesize_pair(z, self.G.shared(c_plain), z + shift, self.G.shared(c_shift))
+
 
 def build_biggan(pretrained_gan_weights, target_classes, config_path=None):
     """models/gan_load.py:84-101 (generator_config.json of the I128 model: G_ch 96, dim_z 120, hier, shared_dim 128)."""

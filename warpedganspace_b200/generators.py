@@ -513,8 +513,10 @@ class BigGANGenerator(_Frozen):
         wa_t, ba, wb_t, bb = e[bn]
         return torch.addmm(ba, y, wa_t), torch.addmm(bb, y, wb_t)
 
-    def forward(self, z, y):
-        """-> logical NCHW image (channels-last memory).  models/BigGAN/BigGAN.py:222-243."""
+    def forward(self, z, y, grad_from=0):
+        """-> logical NCHW image (channels-last memory).  models/BigGAN/BigGAN.py:222-243.
+        grad_from > 0 (the batched pair pass): rows [0, grad_from) are the un-shifted images, which need no gradient - the
+        hand-scheduled nodes back-propagate rows >= grad_from only."""
         self._require_cuda(z)
         P = self.plan()
         sn = P['sn']
@@ -532,10 +534,23 @@ class BigGANGenerator(_Frozen):
             p = 'blocks.%d.0' % i
             A1, B1 = self._ccbn_affine(sn, e, p, 'bn1', ys[i])
             A2, B2 = self._ccbn_affine(sn, e, p, 'bn2', ys[i])
-            h = _GBlockFn.apply(h, A1, B1, A2, B2, e)
+            h = _GBlockFn.apply(h, A1, B1, A2, B2, e, grad_from)
             if self.arch['attn'][i]:
-                h = self._attention(sn, t, 'blocks.%d.1' % i, h)
-        return _OutputFn.apply(h, P['out']).permute(0, 3, 1, 2)
+                if grad_from > 0:          # library ops under autograd: keep the un-shifted rows out of the graph
+                    with torch.no_grad():
+                        h_plain = self._attention(sn, t, 'blocks.%d.1' % i, h[:grad_from])
+                    h = torch.cat([h_plain, self._attention(sn, t, 'blocks.%d.1' % i, h[grad_from:])], dim=0)
+                else:
+                    h = self._attention(sn, t, 'blocks.%d.1' % i, h)
+        return _OutputFn.apply(h, P['out'], grad_from).permute(0, 3, 1, 2)
+
+    def synthesize_pair(self, z_plain, y_plain, z_shifted, y_shifted):
+        """Both images of a training pair in ONE batched pass (rows [plain; shifted]); only the shifted rows are
+        back-propagated.  The 4 x 4 .. 32 x 32 blocks are latency-bound: two passes of B images cost twice one pass of 2B."""
+        b = z_plain.shape[0]
+        img = self.forward(torch.cat([z_plain.detach(), z_shifted], dim=0), torch.cat([y_plain.detach(), y_shifted], dim=0),
+                           grad_from=b)
+        return img[:b].detach(), img[b:]
 
     def _attention(self, sn, t, q, h):
         """layers.py:153-166.  The four 1x1 convs run on the tensor-core kernel; the two batched matrix products
@@ -562,7 +577,7 @@ class _GBlockFn(torch.autograd.Function):
     Backward carries the data gradient and the per-sample dA / dB (which autograd takes on to z through the ccbn linears)."""
 
     @staticmethod
-    def forward(ctx, x, A1, B1, A2, B2, e):
+    def forward(ctx, x, A1, B1, A2, B2, e, grad_from=0):
         x = x.contiguous()
         n, h, w, ci = x.shape
         co = e['co']
@@ -576,14 +591,23 @@ class _GBlockFn(torch.autograd.Function):
         r2s = affine_act_pack(h1, A2.detach(), B2.detach(), relu=True)
         C.conv2d(r2s, e['w2'], 3, 3, padding=1, out=out, accumulate=True, beta=e['b_conv2'], cin=co, split_k=2)
         if any(ctx.needs_input_grad[:5]):
-            ctx.save_for_backward(x, h1, A1, B1, A2, B2)
-        ctx.e = e
+            g0 = grad_from
+            ctx.save_for_backward(x[g0:], h1[g0:], A1[g0:], B1[g0:], A2[g0:], B2[g0:])
+        ctx.e, ctx.g0, ctx.rows = e, grad_from, n
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        x, h1, A1, B1, A2, B2 = ctx.saved_tensors
-        e = ctx.e
+        x, h1, A1, B1, A2, B2 = ctx.saved_tensors           # rows >= grad_from only
+        e, g0 = ctx.e, ctx.g0
+        if g0:
+            res = _GBlockFn._backward_rows(x, h1, A1, B1, A2, B2, e, d_out[g0:])
+            pad = lambda t: torch.cat([t.new_zeros(g0, *t.shape[1:]), t], dim=0)
+            return tuple(pad(t) for t in res) + (None, None)
+        return _GBlockFn._backward_rows(x, h1, A1, B1, A2, B2, e, d_out) + (None, None)
+
+    @staticmethod
+    def _backward_rows(x, h1, A1, B1, A2, B2, e, d_out):
         n, h, w, ci = x.shape
         co = e['co']
         ds = C.pack_split32(d_out.contiguous())
@@ -594,7 +618,7 @@ class _GBlockFn(torch.autograd.Function):
         # shortcut: adjoint of up(conv_sc(x)) = conv_sc^T of the 2x2 sum-pooled gradient = four stride-2 taps of the 1x1 weight
         C.conv_taps(ds, e['wsc_bwd'], [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)], dx, grid=(h, w), in_stride=2, cout=ci,
                     cin=co, accumulate=True, split_k=2)
-        return dx, dA1, dB1, dA2, dB2, None
+        return dx, dA1, dB1, dA2, dB2
 
 
 class _OutputFn(torch.autograd.Function):
@@ -602,19 +626,21 @@ class _OutputFn(torch.autograd.Function):
     pack pass + one conv with bias and tanh in its epilogue."""
 
     @staticmethod
-    def forward(ctx, h, o):
+    def forward(ctx, h, o, grad_from=0):
         h = h.contiguous()
         img = C.conv2d(affine_act_pack(h, o['A'], o['B'], relu=True), o['w'], 3, 3, padding=1, beta=o['bias'], act=4, cin=o['ci'])
         if ctx.needs_input_grad[0]:
-            ctx.save_for_backward(h, img)
-        ctx.o = o
+            ctx.save_for_backward(h[grad_from:], img[grad_from:])
+        ctx.o, ctx.g0 = o, grad_from
         return img
 
     @staticmethod
     def backward(ctx, dimg):
-        h, img = ctx.saved_tensors
-        o = ctx.o
-        g = (dimg * (1.0 - img * img)).contiguous()                             # tanh'
+        h, img = ctx.saved_tensors                                              # rows >= grad_from only
+        o, g0 = ctx.o, ctx.g0
+        g = (dimg[g0:] * (1.0 - img * img)).contiguous()                        # tanh'
         dr = C.conv2d(C.pack_split32(g), o['w_bwd'], 3, 3, padding=1, cout=o['ci'], cin=3)
         dh, _, _ = affine_act_bwd(dr, h, o['A'], o['B'], relu=True, split=False, want_sums=False)
-        return dh, None
+        if g0:
+            dh = torch.cat([dh.new_zeros(g0, *dh.shape[1:]), dh], dim=0)
+        return dh, None, None
