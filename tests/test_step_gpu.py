@@ -261,3 +261,37 @@ def test_other_generator_steps_match_oracle(gan):
     cos = float(torch.nn.functional.cosine_similarity(gs.flatten().double(), ws.flatten().double(), dim=0))
     print('%s dSUPPORT_SETS rel err %.2e cos %.6f' % (gan, rel(gs, ws), cos))
     assert cos > 0.995 and rel(gs, ws) < 1e-1
+
+
+def test_side_streams_change_the_schedule_not_the_step(monkeypatch):
+    """R's weight gradients / Adam update on the side stream and the weight pack on a second one (trainer.PairedTrainer,
+    WGS_SIDE_STREAMS) against the same step on one stream: same forward, gradients complete when forward_backward returns,
+    forward_backward alone leaves the parameters alone, step() updates both parameter sets."""
+    ch = {4: 64, 8: 64, 16: 32, 32: 32, 64: 32}
+    from warpedganspace_b200.trainer import PairedTrainer
+    g = gen(77)
+    z = torch.randn(4, 512, generator=g).cuda()
+    idx = torch.randint(0, 16, (4,), generator=g).cuda()
+    mag = o_step.sample_shift_magnitudes(4, 0.1, 0.2, generator=g).cuda()
+    res = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('WGS_SIDE_STREAMS', mode)
+        _, (W, S, R) = build(64, ch, 16, 4, 500)
+        T = PairedTrainer(W, S, R)
+        r0, s0 = T.flat_r.flat.clone(), T.flat_s.flat.clone()
+        out = T.forward_backward(z, idx, mag)
+        torch.cuda.synchronize()
+        assert torch.equal(T.flat_r.flat, r0) and torch.equal(T.flat_s.flat, s0)          # no optimiser step was asked for
+        g_r, g_s = T.flat_r.grad.clone(), T.flat_s.grad.clone()
+        assert bool(torch.isfinite(g_r).all()) and float(g_r.abs().sum()) > 0 and float(g_s.abs().sum()) > 0
+        T.step(z, idx, mag)
+        torch.cuda.synchronize()
+        assert not torch.equal(T.flat_r.flat, r0) and not torch.equal(T.flat_s.flat, s0)
+        assert T.flat_r.step_count == 1 and T.flat_s.step_count == 1
+        res[mode] = (out['loss'].clone(), out['logits'].clone(), g_r, g_s, T.flat_r.flat.clone())
+    a, b = res['1'], res['0']
+    assert rel(a[0], b[0]) < 1e-5 and rel(a[1], b[1]) < 1e-4
+    # (train-mode BatchNorm statistics are summed atomically: the two runs differ in the last bits, which the graph amplifies)
+    cos = lambda u, v: float(torch.nn.functional.cosine_similarity(u.double().flatten(), v.double().flatten(), dim=0))
+    assert cos(a[2], b[2]) > 0.999 and cos(a[3], b[3]) > 0.999
+    assert rel(a[4], b[4]) < 1e-3                                   # one Adam step of 1e-4 on parameters of size ~1e-1
