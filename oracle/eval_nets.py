@@ -66,6 +66,12 @@ def _bn(sd, name, x, eps=1e-5):
 def resnet_forward(sd, x, block, heads, layers=LAYERS):
     """Eval-mode forward (torchvision/models/resnet.py ResNet._forward_impl; Hopenet.forward, hopenet.py:51-66).
     Returns the tuple of head outputs in `heads` order."""
+    f = resnet_features(sd, x, block, layers)
+    return tuple(F.linear(f, sd[h + '.weight'], sd[h + '.bias']) for h in heads)
+
+
+def resnet_features(sd, x, block, layers=LAYERS):
+    """Pooled trunk features [N, 512 * expansion]."""
     x = F.max_pool2d(F.relu(_bn(sd, 'bn1', F.conv2d(x, sd['conv1.weight'], None, 2, 3))), 3, 2, 1)
     for li, n in enumerate(layers, start=1):
         for bi in range(n):
@@ -82,8 +88,49 @@ def resnet_forward(sd, x, block, heads, layers=LAYERS):
             if p + '.downsample.0.weight' in sd:
                 idt = _bn(sd, p + '.downsample.1', F.conv2d(x, sd[p + '.downsample.0.weight'], None, stride, 0))
             x = F.relu(h + idt)
-    f = x.mean(dim=(2, 3))          # AvgPool2d(7) on the 7 x 7 map of a 224 x 224 crop == AdaptiveAvgPool2d(1)
-    return tuple(F.linear(f, sd[h + '.weight'], sd[h + '.bias']) for h in heads)
+    return x.mean(dim=(2, 3))       # AvgPool2d(7) on the 7 x 7 map of a 224 x 224 crop == AdaptiveAvgPool2d(1)
+
+
+CELEBA_5 = (('6', 'Bangs', 6), ('16', 'Eyeglasses', 6), ('25', 'No_Beard', 6), ('32', 'Smiling', 6), ('40', 'Young', 6))
+
+
+def init_celeba_state(generator, attr_info=CELEBA_5):
+    """State of the CelebA attribute predictor (celeba_attr_predictor.py:106-135): ResNet-50 trunk + stem + classifiers."""
+    sd = init_state('bottleneck', {}, generator)
+
+    def fc_block(name, i, o):
+        sd[name + '.fc.weight'] = (torch.rand(o, i, generator=generator) * 2 - 1) / math.sqrt(i)
+        sd[name + '.fc.bias'] = (torch.rand(o, generator=generator) * 2 - 1) / math.sqrt(i)
+        sd[name + '.bn.weight'] = 0.5 + torch.rand(o, generator=generator)
+        sd[name + '.bn.bias'] = 0.1 * torch.randn(o, generator=generator)
+        sd[name + '.bn.running_mean'] = 0.1 * torch.randn(o, generator=generator)
+        sd[name + '.bn.running_var'] = 0.5 + torch.rand(o, generator=generator)
+        sd[name + '.bn.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+    fc_block('stem', 2048, 512)
+    for key, name, num in attr_info:
+        c = 'classifier' + str(key).zfill(2) + name
+        fc_block(c + '.0', 512, 256)
+        sd[c + '.1.weight'] = (torch.rand(num, 256, generator=generator) * 2 - 1) / 16.0
+        sd[c + '.1.bias'] = (torch.rand(num, generator=generator) * 2 - 1) / 16.0
+    return sd
+
+
+def celeba_forward(sd, x, attr_info=CELEBA_5):
+    """celeba_attr_predictor.py:163-182 in eval mode -> {attribute name: logits}."""
+    f = resnet_features(sd, x, 'bottleneck')
+
+    def fc_block(name, t):
+        t = F.linear(t, sd[name + '.fc.weight'], sd[name + '.fc.bias'])
+        return F.relu(F.batch_norm(t, sd[name + '.bn.running_mean'], sd[name + '.bn.running_var'], sd[name + '.bn.weight'],
+                                   sd[name + '.bn.bias'], False, 0.0, 1e-5))
+
+    f = fc_block('stem', f)
+    out = {}
+    for key, name, _ in attr_info:
+        c = 'classifier' + str(key).zfill(2) + name
+        out[name] = F.linear(fc_block(c + '.0', f), sd[c + '.1.weight'], sd[c + '.1.bias'])
+    return out
 
 
 def fairface_scores(outputs):

@@ -684,6 +684,19 @@ def pin_eval_nets():
     for name, g, w in zip(heads, got, want):
         check('Hopenet %s' % name, g, w, 1e-5)
     fx['hopenet'] = dict(seed=813, checksum=checksum(sd), out=[w.clone() for w in want])
+    cel = importlib.import_module('lib.evaluation.celeba_attributes.celeba_attr_predictor')
+    sd = o_en.init_celeba_state(gen(814))
+    ref = cel.ResNet(cel.Bottleneck, [3, 4, 6, 3],                               # celeba_attr_predictor.py:185-186, no download
+                     attr_file=os.path.join(REF, 'lib', 'evaluation', 'celeba_attributes', 'attributes_5.json'))
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(x)
+        got = o_en.celeba_forward(sd, x)
+    assert list(want) == list(got)
+    for name in want:
+        check('CelebA predictor %s' % name, got[name], want[name], 1e-5)
+    fx['celeba'] = dict(seed=814, checksum=checksum(sd), out={k: v.clone() for k, v in want.items()})
     save('eval_nets.pt', fx)
 
 

@@ -30,6 +30,11 @@ def test_oracle_resnets_match_the_reference_fixture(golden):
     sd = o_en.init_state('bottleneck', HEADS, gen(fx['hopenet']['seed']))
     for got, want in zip(o_en.resnet_forward(sd, x, 'bottleneck', tuple(HEADS)), fx['hopenet']['out']):
         assert rel(got, want) < 1e-5
+    sd = o_en.init_celeba_state(gen(fx['celeba']['seed']))
+    got = o_en.celeba_forward(sd, x)
+    assert list(got) == ['Bangs', 'Eyeglasses', 'No_Beard', 'Smiling', 'Young']
+    for name, want in fx['celeba']['out'].items():
+        assert rel(got[name], want) < 1e-5
 
 
 def _fake_traversal(tmp_path, n_paths=2, n_img=5, size=64):
@@ -65,13 +70,23 @@ def test_driver_files_and_score_arithmetic_with_stub_predictors(tmp_path):
         seen['hopenet'] = tuple(x.shape)
         return tuple(pose_logits)
 
+    cel_logits = {n: torch.randn(5, 6, generator=g) for n in ('Bangs', 'Eyeglasses', 'No_Beard', 'Smiling', 'Young')}
+
+    def celeba(x):
+        seen['celeba'] = (tuple(x.shape), float(x.min()) < -1.0)          # normalised [-1, 1] frames: values below -1 exist
+        return cel_logits
+
     def detector(x):          # one box on even frames, none on odd ones
         return [[[60.0, 70.0, 200.0, 220.0, 0.99]] if t % 2 == 0 else [] for t in range(x.shape[0])]
 
     done = A.traverse_attribute_space(exp, 'pool', shift_steps=2, eps=0.2, device='cpu',
-                                      predictors={'fairface': fairface, 'hopenet': hopenet, 'face_detector': detector})
+                                      predictors={'fairface': fairface, 'hopenet': hopenet, 'face_detector': detector,
+                                                  'celeba': celeba})
     assert done == [h_dir]
-    assert seen == {'fairface': (5, 3, 224, 224), 'hopenet': (5, 3, 224, 224)}
+    assert seen == {'fairface': (5, 3, 224, 224), 'hopenet': (5, 3, 224, 224), 'celeba': ((5, 3, 224, 224), True)}
+    sm = torch.softmax(cel_logits['Smiling'], dim=1)           # traverse_attribute_space.py:352-356
+    want_sm = ((sm.argmax(1) + sm.max(1).values) / 6.0).numpy()
+    assert np.allclose(np.load(os.path.join(h_dir, 'eval_np', 'celeba_smiling.npy'))[0], want_sm, atol=1e-6)
     gender, age, race = o_en.fairface_scores(ff_logits)
     yaw, pitch, roll = o_en.hopenet_pose(*pose_logits)
     nd, jd = os.path.join(h_dir, 'eval_np'), os.path.join(h_dir, 'eval_json')
@@ -120,6 +135,15 @@ def test_fairface_and_hopenet_kernel_chains_match_the_reference_fixture(golden):
         assert rel(got, want) < 1e-3
     with pytest.raises(RuntimeError):
         net(x.cpu())                                           # no CPU fallback
+    from warpedganspace_b200.eval_resnet import celeba_attr_resnet50
+    sd = o_en.init_celeba_state(gen(fx['celeba']['seed']))
+    net = celeba_attr_resnet50()
+    assert set(net.state_dict()) == set(sd)                    # the reference's keys (stem.fc.weight, classifier06Bangs.0.bn.running_var ...)
+    net.load_state_dict(sd, strict=True)
+    net.cuda()
+    got = net(x)
+    for name, want in fx['celeba']['out'].items():
+        assert rel(got[name], want) < 1e-3 and torch.equal(got[name].argmax(1).cpu(), want.argmax(1))
 
 
 @pytest.mark.gpu

@@ -4,12 +4,13 @@ latent-space traversal and record how each attribute predictor responds along ev
 Built here (the consumer of the traversal frames):
   * the driver - directory conventions, per-path batches, the reference's score arithmetic, the ``eval_json`` / ``eval_np``
     files with the reference's names and layouts;
-  * the two predictors that are plain ImageNet ResNets, as inference-only kernel chains on libwgs_b200
-    (eval_resnet.fairface_resnet34 / hopenet_resnet50: age / race / gender and yaw / pitch / roll);
+  * the three predictors that are ImageNet-style ResNets, as inference-only kernel chains on libwgs_b200
+    (eval_resnet.fairface_resnet34 / hopenet_resnet50 / celeba_attr_resnet50: age / race / gender, yaw / pitch / roll and the
+    five CelebA attributes);
   * face cropping, resize + centre crop + normalisation on the device.
-NOT built: the SFD face detector, the ArcFace identity comparator, the AU hourglass detector and the CelebA attribute
-predictor (lib/evaluation/{sfd,archface,au_detector,celeba_attributes}; their weights are downloads that do not exist here).
-They plug in as callables (``predictors['face_detector' | 'id_comparator' | 'au_detector' | 'celeba']``) with the
+NOT built: the SFD face detector, the ArcFace identity comparator and the AU hourglass detector
+(lib/evaluation/{sfd,archface,au_detector}; their weights are downloads that do not exist here).
+They plug in as callables (``predictors['face_detector' | 'id_comparator' | 'au_detector']``) with the
 reference's call signatures; without a face detector every frame uses the reference's own no-detection fallback
 (the full 256 x 256 frame, traverse_attribute_space.py:396-399), and files of absent predictors are not written.
 """

@@ -185,3 +185,45 @@ def hopenet_resnet50(num_bins=66):
     for p in m.fc_finetune.parameters():
         p.requires_grad_(False)
     return m
+
+
+# attributes_5.json of the reference (lib/evaluation/celeba_attributes/attributes_5.json): CelebA attribute id -> (name, classes)
+CELEBA_5 = (('6', 'Bangs', 6), ('16', 'Eyeglasses', 6), ('25', 'No_Beard', 6), ('32', 'Smiling', 6), ('40', 'Young', 6))
+
+
+class _FcBlock(nn.Module):
+    """celeba_attr_predictor.py:86-103 in eval mode: Linear -> BatchNorm1d -> ReLU (the drop-out is inactive)."""
+
+    def __init__(self, inplanes, planes):
+        super().__init__()
+        self.fc = nn.Linear(inplanes, planes)
+        self.bn = nn.BatchNorm1d(planes)
+
+    def forward(self, x):
+        return F.relu(self.bn(self.fc(x)))
+
+
+class CelebAPredictor(FrozenResNet):
+    """lib/evaluation/celeba_attributes/celeba_attr_predictor.py:106-182: ResNet-50 trunk (the kernel chain above), a
+    2048 -> 512 ``stem`` block and one small classifier per attribute (``classifier06Bangs`` ...); forward returns
+    {attribute name: logits}.  Same state-dict keys as the reference's ``ResNet(Bottleneck, [3, 4, 6, 3], attr_file)``."""
+
+    def __init__(self, attr_info=CELEBA_5):
+        super().__init__('bottleneck', (3, 4, 6, 3), {})
+        self.attr_info = tuple(attr_info)
+        self.stem = _FcBlock(512 * 4, 512)
+        for key, name, num in self.attr_info:
+            setattr(self, 'classifier' + str(key).zfill(2) + name, nn.Sequential(_FcBlock(512, 256), nn.Linear(256, num)))
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.eval()
+
+    def forward(self, x):
+        f = self.stem(self.features(x))
+        return {name: getattr(self, 'classifier' + str(key).zfill(2) + name)(f) for key, name, _ in self.attr_info}
+
+
+def celeba_attr_resnet50(attr_info=CELEBA_5):
+    """traverse_attribute_space.py:206-207."""
+    return CelebAPredictor(attr_info)
+
