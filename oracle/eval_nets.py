@@ -148,3 +148,93 @@ def hopenet_pose(yaw, pitch, roll):
     """traverse_attribute_space.py:448-456: expectation over the 66 bins * 3 - 99, in degrees."""
     idx = torch.arange(66, dtype=yaw.dtype)
     return tuple(torch.sum(torch.softmax(t, dim=1) * idx, 1) * 3 - 99 for t in (yaw, pitch, roll))
+
+
+# ---- S3FD face detector (lib/evaluation/sfd/net_s3fd.py:21-129) ---------------------------------------------------------------
+S3FD_TRUNK = (('conv1_1', 3, 64, 3, 1, 1), ('conv1_2', 64, 64, 3, 1, 1), '|', ('conv2_1', 64, 128, 3, 1, 1), ('conv2_2', 128, 128, 3, 1, 1), '|',
+              ('conv3_1', 128, 256, 3, 1, 1), ('conv3_2', 256, 256, 3, 1, 1), ('conv3_3', 256, 256, 3, 1, 1), '|',
+              ('conv4_1', 256, 512, 3, 1, 1), ('conv4_2', 512, 512, 3, 1, 1), ('conv4_3', 512, 512, 3, 1, 1), '|',
+              ('conv5_1', 512, 512, 3, 1, 1), ('conv5_2', 512, 512, 3, 1, 1), ('conv5_3', 512, 512, 3, 1, 1), '|',
+              ('fc6', 512, 1024, 3, 1, 3), ('fc7', 1024, 1024, 1, 1, 0), ('conv6_1', 1024, 256, 1, 1, 0), ('conv6_2', 256, 512, 3, 2, 1),
+              ('conv7_1', 512, 128, 1, 1, 0), ('conv7_2', 128, 256, 3, 2, 1))
+S3FD_HEADS = (('conv3_3_norm', 'conv3_3', 256, 4, 10.0), ('conv4_3_norm', 'conv4_3', 512, 2, 8.0), ('conv5_3_norm', 'conv5_3', 512, 2, 5.0),
+              ('fc7', 'fc7', 1024, 2, None), ('conv6_2', 'conv6_2', 512, 2, None), ('conv7_2', 'conv7_2', 256, 2, None))
+
+
+def init_s3fd_state(generator):
+    sd = {}
+
+    def conv(name, ci, co, k, wscale=1.0):
+        sd[name + '.weight'] = torch.randn(co, ci, k, k, generator=generator) * math.sqrt(2.0 / (ci * k * k)) * wscale
+        sd[name + '.bias'] = 0.05 * torch.randn(co, generator=generator)
+
+    for spec in S3FD_TRUNK:
+        if spec != '|':
+            conv(spec[0], spec[1], spec[2], spec[3])
+    for head, _, c, ncls, scale in S3FD_HEADS:
+        if scale is not None:
+            sd[head + '.weight'] = scale * (0.8 + 0.4 * torch.rand(c, generator=generator))
+        conv(head + '_mbox_conf', c, ncls, 3, wscale=0.6)       # spread-out face scores: some positions above 0.5, most below
+        sd[head + '_mbox_conf.bias'][-1] -= 2.0                  # (the face class is the last channel)
+        conv(head + '_mbox_loc', c, 4, 3, wscale=0.3)
+    return sd
+
+
+def s3fd_forward(sd, x):
+    """net_s3fd.py:71-129 -> [cls1, reg1, ..., cls6, reg6]."""
+    taps, h = {}, x
+    for spec in S3FD_TRUNK:
+        if spec == '|':
+            h = F.max_pool2d(h, 2, 2)
+            continue
+        name, _, _, _, s, p = spec
+        h = F.relu(F.conv2d(h, sd[name + '.weight'], sd[name + '.bias'], s, p))
+        taps[name] = h
+    outs = []
+    for head, src, _, _, scale in S3FD_HEADS:
+        f = taps[src]
+        if scale is not None:                                     # L2Norm, :9-19
+            f = f / (f.pow(2).sum(dim=1, keepdim=True).sqrt() + 1e-10) * sd[head + '.weight'].view(1, -1, 1, 1)
+        outs.append(F.conv2d(f, sd[head + '_mbox_conf.weight'], sd[head + '_mbox_conf.bias'], 1, 1))
+        outs.append(F.conv2d(f, sd[head + '_mbox_loc.weight'], sd[head + '_mbox_loc.bias'], 1, 1))
+    c = torch.chunk(outs[0], 4, 1)
+    outs[0] = torch.cat([torch.max(torch.max(c[0], c[1]), c[2]), c[3]], dim=1)
+    return outs
+
+
+def sfd_detect_from_batch(olist):
+    """sfd_detector.py:23-40 + detect.py:26-62 + bbox.py:48-66,94-111 restated per image: soft-max, positions with face score >
+    0.05, anchor decode (stride 2^(i+2), anchor 4 x stride, variances 0.1 / 0.2), NMS 0.3, keep score > 0.5.
+    Returns per-image [M_j, 5] arrays.  (The reference gathers the candidate positions over the whole batch for every image;
+    the extra low-score entries are removed again by its NMS + 0.5 filter - pinned in gen_golden.pin_eval_nets.)"""
+    import numpy as np
+    res = []
+    for j in range(olist[0].shape[0]):
+        rows = []
+        for i in range(len(olist) // 2):
+            ocls = torch.softmax(olist[i * 2][j: j + 1], dim=1)[0, 1]
+            oreg = olist[i * 2 + 1][j]
+            stride = 2 ** (i + 2)
+            hh, ww = torch.nonzero(ocls > 0.05, as_tuple=True)
+            for h_, w_ in zip(hh.tolist(), ww.tolist()):
+                axc, ayc, a = stride / 2 + w_ * stride, stride / 2 + h_ * stride, stride * 4.0
+                loc = oreg[:, h_, w_]
+                xc, yc = axc + float(loc[0]) * 0.1 * a, ayc + float(loc[1]) * 0.1 * a
+                bw, bh = a * math.exp(float(loc[2]) * 0.2), a * math.exp(float(loc[3]) * 0.2)
+                rows.append([xc - bw / 2, yc - bh / 2, xc - bw / 2 + bw, yc - bh / 2 + bh, float(ocls[h_, w_])])
+        d = np.array(rows, dtype=np.float64).reshape(-1, 5)
+        keep = []
+        order = d[:, 4].argsort()[::-1]
+        areas = (d[:, 2] - d[:, 0] + 1) * (d[:, 3] - d[:, 1] + 1)
+        while order.size > 0:
+            i0 = order[0]
+            keep.append(i0)
+            rest = order[1:]
+            w_ = np.maximum(0.0, np.minimum(d[i0, 2], d[rest, 2]) - np.maximum(d[i0, 0], d[rest, 0]) + 1)
+            h_ = np.maximum(0.0, np.minimum(d[i0, 3], d[rest, 3]) - np.maximum(d[i0, 1], d[rest, 1]) + 1)
+            ovr = w_ * h_ / (areas[i0] + areas[rest] - w_ * h_)
+            order = rest[ovr <= 0.3]
+        kept = d[keep] if keep else d
+        res.append(kept[kept[:, 4] > 0.5])
+    return res
+

@@ -697,6 +697,35 @@ def pin_eval_nets():
     for name in want:
         check('CelebA predictor %s' % name, got[name], want[name], 1e-5)
     fx['celeba'] = dict(seed=814, checksum=checksum(sd), out={k: v.clone() for k, v in want.items()})
+    # S3FD face detector: network against the reference class, post-processing against the reference's batch_detect + nms
+    import numpy as np
+    net_mod = importlib.import_module('lib.evaluation.sfd.net_s3fd')
+    det_mod = importlib.import_module('lib.evaluation.sfd.detect')
+    sd = o_en.init_s3fd_state(gen(815))
+    ref = net_mod.s3fd()
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    xf = 255.0 * torch.rand(2, 3, 128, 128, generator=gen(816))
+    with torch.no_grad():
+        want = ref(xf)
+        got = o_en.s3fd_forward(sd, xf)
+    for i, (g_, w_) in enumerate(zip(got, want)):
+        check('S3FD output %d %s' % (i, tuple(w_.shape)), g_, w_, 1e-5)
+    boxes_ref = det_mod.batch_detect(ref, xf, 'cpu')                      # [B, M, 5] (positions gathered over the batch)
+    dets_ref = []
+    for i in range(boxes_ref.shape[0]):                                   # sfd_detector.py:29-36
+        bl = boxes_ref[i].astype(np.float64)
+        keep = det_mod.nms(bl, 0.3)
+        dets_ref.append(np.array([b for b in bl[keep, :] if b[-1] > 0.5]).reshape(-1, 5))
+    dets = o_en.sfd_detect_from_batch(got)
+    for j in range(2):
+        print('  image %d: %d candidate boxes in the reference list, %d detections' % (j, boxes_ref.shape[1], len(dets_ref[j])))
+        assert dets[j].shape == dets_ref[j].shape and len(dets[j]) > 0, (dets[j].shape, dets_ref[j].shape)
+        a = dets[j][np.lexsort(dets[j].T)]
+        b = dets_ref[j][np.lexsort(dets_ref[j].T)]
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-3), float(np.abs(a - b).max())
+    fx['s3fd'] = dict(seed=815, seed_x=816, checksum=checksum(sd), out=[w_[:, :, ::2, ::2].clone() for w_ in want],
+                      detections=[torch.from_numpy(d) for d in dets_ref])
     save('eval_nets.pt', fx)
 
 

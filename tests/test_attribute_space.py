@@ -37,6 +37,20 @@ def test_oracle_resnets_match_the_reference_fixture(golden):
         assert rel(got[name], want) < 1e-5
 
 
+def test_oracle_s3fd_matches_the_reference_fixture(golden):
+    fx = golden('eval_nets.pt')['s3fd']
+    sd = o_en.init_s3fd_state(gen(fx['seed']))
+    x = 255.0 * torch.rand(2, 3, 128, 128, generator=gen(fx['seed_x']))
+    outs = o_en.s3fd_forward(sd, x)
+    for got, want in zip(outs, fx['out']):
+        assert rel(got[:, :, ::2, ::2], want) < 1e-5
+    dets = o_en.sfd_detect_from_batch(outs)
+    for d, want in zip(dets, fx['detections']):
+        assert d.shape == tuple(want.shape)
+        a, b = d[np.lexsort(d.T)], want.numpy()[np.lexsort(want.numpy().T)]
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-3)
+
+
 def _fake_traversal(tmp_path, n_paths=2, n_img=5, size=64):
     from PIL import Image
     exp = tmp_path / 'exp'
@@ -174,3 +188,32 @@ def test_attribute_traversal_end_to_end_on_the_gpu(tmp_path):
     assert np.allclose(np.load(os.path.join(nd, 'race.npy'))[0], race.numpy(), atol=2e-3)
     yaw, _, _ = o_en.hopenet_pose(*o_en.resnet_forward(sd_h, crops['h'], 'bottleneck', tuple(HEADS)))
     assert np.allclose(np.load(os.path.join(nd, 'yaw.npy'))[0], yaw.numpy() * np.pi / 180, atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_s3fd_detector_kernel_chain_matches_the_reference_fixture(golden):
+    """The face detector on the tensor-core convs: the twelve head outputs against the reference network, the detections
+    (soft-max, anchor decode, NMS 0.3, score > 0.5) against the reference's batch_detect + nms."""
+    from warpedganspace_b200.eval_sfd import S3FD, SFDDetector
+    torch.backends.cudnn.allow_tf32 = False
+    fx = golden('eval_nets.pt')['s3fd']
+    sd = o_en.init_s3fd_state(gen(fx['seed']))
+    det = SFDDetector()
+    assert set(det.face_detector.state_dict()) == set(sd)          # the reference's key names: s3fd-619a316812.pth loads as it is
+    det.face_detector.load_state_dict(sd, strict=True)
+    det.face_detector.cuda()
+    x = (255.0 * torch.rand(2, 3, 128, 128, generator=gen(fx['seed_x']))).cuda()
+    outs = det.face_detector(x)
+    for got, want in zip(outs, fx['out']):
+        assert rel(got[:, :, ::2, ::2], want) < 1e-3
+    found, error, _ = det.detect_from_batch(x)
+    assert not error
+    for mine, want in zip(found, fx['detections']):
+        mine, want = np.array(mine, dtype=np.float64).reshape(-1, 5), want.numpy()
+        assert abs(len(mine) - len(want)) <= 2                       # (a score within 1e-5 of 0.5 / an IoU within 1e-5 of 0.3 may flip)
+        # random weights put exp(0.2 * loc) anywhere from 1e-3 to 1e9 pixels: compare relative to the box's own scale
+        dist = (np.abs(mine[:, None, :] - want[None, :, :]) / (1.0 + np.abs(want[None, :, :]))).max(axis=2)
+        assert (dist.min(axis=1) < 2e-2).mean() > 0.9 and (dist.min(axis=0) < 2e-2).mean() > 0.9
+    with pytest.raises(RuntimeError):
+        S3FD()(x.cpu())                                              # no CPU fallback
+

@@ -7,12 +7,13 @@ Built here (the consumer of the traversal frames)
   * the three predictors that are ImageNet-style ResNets, as inference-only kernel chains on libwgs_b200
     (eval_resnet.fairface_resnet34 / hopenet_resnet50 / celeba_attr_resnet50: age / race / gender, yaw / pitch / roll and the
     five CelebA attributes);
+  * the S3FD face detector (eval_sfd.SFDDetector: VGG trunk + heads on the same convs, soft-max / anchor decode / NMS as the
+    reference's batch_detect);
   * face cropping, resize + centre crop + normalisation on the device.
-NOT built: the SFD face detector, the ArcFace identity comparator and the AU hourglass detector
-(lib/evaluation/{sfd,archface,au_detector}; their weights are downloads that do not exist here).
-They plug in as callables (``predictors['face_detector' | 'id_comparator' | 'au_detector']``) with the
-reference's call signatures; without a face detector every frame uses the reference's own no-detection fallback
-(the full 256 x 256 frame, traverse_attribute_space.py:396-399), and files of absent predictors are not written.
+NOT built: the ArcFace identity comparator and the AU hourglass detector (lib/evaluation/{archface,au_detector}).
+They plug in as callables (``predictors['id_comparator' | 'au_detector']``) with the reference's call signatures; files of
+absent predictors are not written.  Without a face detector every frame uses the reference's own no-detection fallback
+(the full 256 x 256 frame, traverse_attribute_space.py:396-399).
 """
 import glob
 import json
