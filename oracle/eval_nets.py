@@ -1,10 +1,13 @@
-"""CPU oracle: the two ResNet-based attribute predictors of the attribute-space traversal, restated functionally over
-torchvision-named state dicts (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+"""CPU oracle: the attribute predictors of the attribute-space traversal, restated functionally over state dicts with the
+reference's key names (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
 
   * FairFace: ``torchvision.models.resnet34`` with ``fc = Linear(512, 18)`` in eval mode (traverse_attribute_space.py:178-183)
     followed by the race / gender / age score arithmetic of :412-433;
   * Hopenet: ResNet-50 trunk + three 66-bin heads (lib/evaluation/hopenet/hopenet.py:5-66) followed by the soft-argmax pose of
     traverse_attribute_space.py:448-456.
+
+  * the CelebA attribute predictor, the S3FD face detector, the ArcFace identity comparator (IR-SE-50) and the action-unit
+    hourglass detector (sections below, each citing its reference file).
 
 Third-party arithmetic: torchvision's BasicBlock / Bottleneck (no version pinned by the reference's requirements.txt; 0.26.0
 installed here).  Pinned by oracle/gen_golden.py::pin_eval_nets against torchvision.models.resnet34 and the reference's own
@@ -238,3 +241,182 @@ def sfd_detect_from_batch(olist):
         res.append(kept[kept[:, 4] > 0.5])
     return res
 
+
+
+# ---- ArcFace identity comparator (lib/evaluation/archface/arcface.py:9-24,119-164) -------------------------------------------
+ARCFACE_STAGES = ((64, 64, 3), (64, 128, 4), (128, 256, 14), (256, 512, 3))          # get_blocks(50), arcface.py:103-108
+
+
+def _bn_state(sd, name, c, generator, gain=1.0):
+    sd[name + '.weight'] = gain * (0.5 + torch.rand(c, generator=generator))
+    sd[name + '.bias'] = 0.1 * torch.randn(c, generator=generator)
+    sd[name + '.running_mean'] = 0.1 * torch.randn(c, generator=generator)
+    sd[name + '.running_var'] = 0.5 + torch.rand(c, generator=generator)
+    sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+
+def arcface_units():
+    """(in_channel, depth, stride) of the 24 body units."""
+    return [(ci if i == 0 else d, d, 2 if i == 0 else 1) for ci, d, n in ARCFACE_STAGES for i in range(n)]
+
+
+def init_arcface_state(generator):
+    """Seeded SE_IR(50, mode='ir_se') state with the reference's key names (BatchNorm statistics randomised)."""
+    sd = {}
+
+    def conv(name, co, ci, k, gain=1.0):
+        sd[name + '.weight'] = torch.randn(co, ci, k, k, generator=generator) * math.sqrt(2.0 / (ci * k * k)) * gain
+
+    conv('input_layer.0', 64, 3, 3)
+    _bn_state(sd, 'input_layer.1', 64, generator)
+    sd['input_layer.2.weight'] = 0.1 + 0.3 * torch.rand(64, generator=generator)
+    for i, (ci, d, s) in enumerate(arcface_units()):
+        p = 'body.%d' % i
+        if ci != d:
+            conv(p + '.shortcut_layer.0', d, ci, 1)
+            _bn_state(sd, p + '.shortcut_layer.1', d, generator)
+        _bn_state(sd, p + '.res_layer.0', ci, generator)
+        conv(p + '.res_layer.1', d, ci, 3)
+        sd[p + '.res_layer.2.weight'] = 0.1 + 0.3 * torch.rand(d, generator=generator)
+        conv(p + '.res_layer.3', d, d, 3)
+        _bn_state(sd, p + '.res_layer.4', d, generator, gain=0.5)
+        conv(p + '.res_layer.5.fc1', d // 16, d, 1)
+        conv(p + '.res_layer.5.fc2', d, d // 16, 1)
+    _bn_state(sd, 'output_layer.0', 512, generator)
+    sd['output_layer.3.weight'] = torch.randn(512, 512 * 7 * 7, generator=generator) / math.sqrt(512 * 7 * 7)
+    sd['output_layer.3.bias'] = 0.05 * torch.randn(512, generator=generator)
+    _bn_state(sd, 'output_layer.4', 512, generator)
+    return sd
+
+
+def arcface_backbone(sd, x):
+    """SE_IR.forward (arcface.py:159-163) in eval mode: x [N, 3, 112, 112] -> unit-norm embeddings [N, 512]."""
+    x = F.prelu(_bn(sd, 'input_layer.1', F.conv2d(x, sd['input_layer.0.weight'], None, 1, 1)), sd['input_layer.2.weight'])
+    for i, (ci, d, s) in enumerate(arcface_units()):
+        p = 'body.%d' % i
+        if ci == d:
+            sc = x[:, :, ::s, ::s]                                            # MaxPool2d(1, stride), :64-65
+        else:
+            sc = _bn(sd, p + '.shortcut_layer.1', F.conv2d(x, sd[p + '.shortcut_layer.0.weight'], None, s))
+        r = F.conv2d(_bn(sd, p + '.res_layer.0', x), sd[p + '.res_layer.1.weight'], None, 1, 1)
+        r = F.prelu(r, sd[p + '.res_layer.2.weight'])
+        r = _bn(sd, p + '.res_layer.4', F.conv2d(r, sd[p + '.res_layer.3.weight'], None, s, 1))
+        g = F.conv2d(F.relu(F.conv2d(r.mean(dim=(2, 3), keepdim=True), sd[p + '.res_layer.5.fc1.weight'])),
+                     sd[p + '.res_layer.5.fc2.weight'])                       # SEModule, :51-58
+        x = r * torch.sigmoid(g) + sc
+    x = _bn(sd, 'output_layer.0', x).flatten(1)                               # Dropout is inactive in eval mode
+    x = F.linear(x, sd['output_layer.3.weight'], sd['output_layer.3.bias'])
+    x = F.batch_norm(x, sd['output_layer.4.running_mean'], sd['output_layer.4.running_var'], sd['output_layer.4.weight'],
+                     sd['output_layer.4.bias'], False, 0.0, 1e-5)
+    return x / torch.norm(x, 2, 1, True)
+
+
+def arcface_extract_feats(sd, x):
+    """IDComparator.extract_feats (arcface.py:16-19): fixed face region of a 256 x 256 frame, pooled to 112 x 112."""
+    return arcface_backbone(sd, F.adaptive_avg_pool2d(x[:, :, 35:223, 32:220], (112, 112)))
+
+
+def id_similarity(sd, x, x_prime):
+    """IDComparator.forward (arcface.py:21-22)."""
+    return F.cosine_similarity(arcface_extract_feats(sd, x), arcface_extract_feats(sd, x_prime), dim=1, eps=1e-6).mean()
+
+
+# ---- Action-unit detector (lib/evaluation/au_detector/hourglass.py:17-243, AU_detector.py:29-46) ----------------------------
+def _convblock_state(sd, name, ci, co, generator, lightweight=False):
+    k = 1 if lightweight else 3
+    for j, (a, b) in enumerate(((ci, co // 2), (co // 2, co // 4), (co // 4, co // 4)), start=1):
+        sd['%s.conv%d.weight' % (name, j)] = torch.randn(b, a, k, k, generator=generator) * math.sqrt(2.0 / (a * k * k))
+        _bn_state(sd, '%s.bn%d' % (name, j), b, generator)
+    if ci != co:
+        sd[name + '.downsample.0.weight'] = torch.randn(co, ci, 1, 1, generator=generator) * math.sqrt(2.0 / ci)
+        _bn_state(sd, name + '.downsample.1', co, generator)
+
+
+def _hourglass_blocks(depth=4):
+    """Module names of HourGlass(1, depth, .) in registration order, with the lightweight flag of b1 (hourglass.py:78-89)."""
+    names = []
+
+    def gen_(level):
+        names.append(('b1_%d' % level, True))
+        names.append(('b2_%d' % level, False))
+        if level > 1:
+            gen_(level - 1)
+        else:
+            names.append(('b2_plus_%d' % level, False))
+        names.append(('b3_%d' % level, False))
+
+    gen_(depth)
+    return names
+
+
+def init_au_state(generator, n_points=12):
+    """Seeded FANAU(num_modules=1, n_points=12) state with the reference's key names."""
+    sd = {}
+
+    def conv_b(name, co, ci, k):
+        sd[name + '.weight'] = torch.randn(co, ci, k, k, generator=generator) * math.sqrt(2.0 / (ci * k * k))
+        sd[name + '.bias'] = 0.05 * torch.randn(co, generator=generator)
+
+    conv_b('fan.conv1', 64, 3, 7)
+    _bn_state(sd, 'fan.bn1', 64, generator)
+    _convblock_state(sd, 'fan.conv2', 64, 64, generator)
+    _convblock_state(sd, 'fan.conv3', 64, 128, generator)
+    _convblock_state(sd, 'fan.conv4', 128, 128, generator)
+    for name, _ in _hourglass_blocks():
+        _convblock_state(sd, 'fan.m0.' + name, 128, 128, generator)          # the landmark hourglass has no lightweight blocks
+    _convblock_state(sd, 'fan.top_m_0', 128, 128, generator)
+    conv_b('fan.conv_last0', 128, 128, 1)
+    _bn_state(sd, 'fan.bn_end0', 128, generator)
+    conv_b('fan.l0', 68, 128, 1)
+    conv_b('conv1.0', 128, 68, 1)
+    _bn_state(sd, 'conv1.1', 128, generator)
+    conv_b('conv2.0', 128, 128, 1)
+    _bn_state(sd, 'conv2.1', 128, generator)
+    for name, light in _hourglass_blocks():
+        _convblock_state(sd, 'net.' + name, 128, 128, generator, lightweight=light)
+    conv_b('conv_last.0', 128, 128, 1)
+    _bn_state(sd, 'conv_last.1', 128, generator)
+    conv_b('l', n_points, 128, 1)
+    return sd
+
+
+def _convblock(sd, name, x):
+    """ConvBlock.forward (hourglass.py:46-68); kernel size and padding follow the stored weights (lightweight = 1 x 1)."""
+    pad = (sd[name + '.conv1.weight'].shape[-1] - 1) // 2
+    o1 = F.relu6(_bn(sd, name + '.bn1', F.conv2d(x, sd[name + '.conv1.weight'], None, 1, pad)))
+    o2 = F.relu6(_bn(sd, name + '.bn2', F.conv2d(o1, sd[name + '.conv2.weight'], None, 1, pad)))
+    o3 = F.relu6(_bn(sd, name + '.bn3', F.conv2d(o2, sd[name + '.conv3.weight'], None, 1, pad)))
+    res = x
+    if name + '.downsample.0.weight' in sd:
+        res = F.relu6(_bn(sd, name + '.downsample.1', F.conv2d(x, sd[name + '.downsample.0.weight'])))
+    return torch.cat((o1, o2, o3), 1) + res
+
+
+def _hourglass(sd, name, level, x):
+    """HourGlass._forward (hourglass.py:91-113)."""
+    up1 = _convblock(sd, '%s.b1_%d' % (name, level), x)
+    low = _convblock(sd, '%s.b2_%d' % (name, level), F.max_pool2d(x, 2, 2))
+    low = _hourglass(sd, name, level - 1, low) if level > 1 else _convblock(sd, '%s.b2_plus_%d' % (name, level), low)
+    low = _convblock(sd, '%s.b3_%d' % (name, level), low)
+    return up1 + F.interpolate(low, scale_factor=2, mode='nearest')
+
+
+def au_heatmaps(sd, x):
+    """FANAU.forward (hourglass.py:224-243) over QFAN.forward (:154-185) in eval mode: x [N, 3, 256, 256] -> [N, 12, 64, 64]."""
+    h = F.relu(_bn(sd, 'fan.bn1', F.conv2d(x, sd['fan.conv1.weight'], sd['fan.conv1.bias'], 2, 3)))
+    h = F.max_pool2d(_convblock(sd, 'fan.conv2', h), 2, 2)
+    feat = _convblock(sd, 'fan.conv4', _convblock(sd, 'fan.conv3', h))
+    ll = _convblock(sd, 'fan.top_m_0', _hourglass(sd, 'fan.m0', 4, feat))
+    ll = F.relu(_bn(sd, 'fan.bn_end0', F.conv2d(ll, sd['fan.conv_last0.weight'], sd['fan.conv_last0.bias'])))
+    lmk = F.conv2d(ll, sd['fan.l0.weight'], sd['fan.l0.bias'])
+    a = F.relu6(_bn(sd, 'conv1.1', F.conv2d(lmk, sd['conv1.0.weight'], sd['conv1.0.bias'])))
+    b = F.relu6(_bn(sd, 'conv2.1', F.conv2d(feat, sd['conv2.0.weight'], sd['conv2.0.bias'])))
+    h = _hourglass(sd, 'net', 4, a + b)
+    h = F.relu6(_bn(sd, 'conv_last.1', F.conv2d(h, sd['conv_last.0.weight'], sd['conv_last.0.bias'])))
+    return F.conv2d(h, sd['l.weight'], sd['l.bias'])
+
+
+def detect_au(sd, img):
+    """AUdetector.detect_AU (AU_detector.py:35-46): min-max normalised batch -> heat-map maxima [N, 12]."""
+    x = (img - img.min()) / (img.max() - img.min())
+    return F.max_pool2d(au_heatmaps(sd, x), (64, 64)).squeeze(2).squeeze(2)

@@ -726,6 +726,40 @@ def pin_eval_nets():
         assert np.allclose(a, b, rtol=1e-4, atol=1e-3), float(np.abs(a - b).max())
     fx['s3fd'] = dict(seed=815, seed_x=816, checksum=checksum(sd), out=[w_[:, :, ::2, ::2].clone() for w_ in want],
                       detections=[torch.from_numpy(d) for d in dets_ref])
+    # ArcFace identity comparator: the reference IDComparator (its constructor reads the checkpoint: torch.load is patched
+    # to hand it the seeded state) on two 256 x 256 frames
+    from unittest import mock
+    arc = importlib.import_module('lib.evaluation.archface.arcface')
+    sd = o_en.init_arcface_state(gen(817))
+    with mock.patch('torch.load', return_value=sd):
+        idc = arc.IDComparator()
+    idc.eval()
+    assert set(idc.backbone.state_dict()) == set(sd)
+    xa = torch.rand(3, 3, 256, 256, generator=gen(818)) * 2 - 1
+    xa[2] = 0.7 * xa[0] + 0.3 * xa[1]                                     # a related frame: similarity away from 0
+    with torch.no_grad():
+        want_f = idc.extract_feats(xa)
+        got_f = o_en.arcface_extract_feats(sd, xa)
+        want_s = torch.stack([idc(xa[0:1], xa[t: t + 1]) for t in range(3)])
+        got_s = torch.stack([o_en.id_similarity(sd, xa[0:1], xa[t: t + 1]) for t in range(3)])
+    check('ArcFace embeddings', got_f, want_f, 1e-5)
+    check('ArcFace similarity to frame 0 %s' % [round(float(v), 4) for v in want_s], got_s, want_s, 1e-5)
+    fx['arcface'] = dict(seed=817, seed_x=818, checksum=checksum(sd), feats=want_f.clone(), sim=want_s.clone())
+    # Action-unit detector: the reference AUdetector (same patch for its checkpoint read) on two 256 x 256 crops
+    aud = importlib.import_module('lib.evaluation.au_detector.AU_detector')
+    sd = o_en.init_au_state(gen(819))
+    with mock.patch('torch.load', return_value={'state_dict': sd}):
+        ref = aud.AUdetector(use_cuda=False)
+    assert set(ref.AUdetector.FAN.state_dict()) == set(sd)
+    xu = 255.0 * torch.rand(2, 3, 256, 256, generator=gen(820))
+    with torch.no_grad():
+        want_i = ref.detect_AU(xu)
+        want_h = ref.AUdetector.forward_FAN((xu - xu.min()) / (xu.max() - xu.min()))
+        got_i = o_en.detect_au(sd, xu)
+        got_h = o_en.au_heatmaps(sd, (xu - xu.min()) / (xu.max() - xu.min()))
+    check('AU heat maps %s' % (tuple(want_h.shape),), got_h, want_h, 1e-5)
+    check('AU intensities', got_i, want_i, 1e-5)
+    fx['au'] = dict(seed=819, seed_x=820, checksum=checksum(sd), heat=want_h[:, :, ::4, ::4].clone(), intensities=want_i.clone())
     save('eval_nets.pt', fx)
 
 

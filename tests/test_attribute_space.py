@@ -51,6 +51,20 @@ def test_oracle_s3fd_matches_the_reference_fixture(golden):
         assert np.allclose(a, b, rtol=1e-4, atol=1e-3)
 
 
+def test_oracle_arcface_and_au_match_the_reference_fixture(golden):
+    fx = golden('eval_nets.pt')
+    sd = o_en.init_arcface_state(gen(fx['arcface']['seed']))
+    xa = torch.rand(3, 3, 256, 256, generator=gen(fx['arcface']['seed_x'])) * 2 - 1
+    xa[2] = 0.7 * xa[0] + 0.3 * xa[1]
+    assert rel(o_en.arcface_extract_feats(sd, xa), fx['arcface']['feats']) < 1e-5
+    sims = torch.stack([o_en.id_similarity(sd, xa[0:1], xa[t: t + 1]) for t in range(3)])
+    assert rel(sims, fx['arcface']['sim']) < 1e-5
+    sd = o_en.init_au_state(gen(fx['au']['seed']))
+    xu = 255.0 * torch.rand(2, 3, 256, 256, generator=gen(fx['au']['seed_x']))
+    assert rel(o_en.detect_au(sd, xu), fx['au']['intensities']) < 1e-5
+    assert rel(o_en.au_heatmaps(sd, (xu - xu.min()) / (xu.max() - xu.min()))[:, :, ::4, ::4], fx['au']['heat']) < 1e-5
+
+
 def _fake_traversal(tmp_path, n_paths=2, n_img=5, size=64):
     from PIL import Image
     exp = tmp_path / 'exp'
@@ -216,4 +230,85 @@ def test_s3fd_detector_kernel_chain_matches_the_reference_fixture(golden):
         assert (dist.min(axis=1) < 2e-2).mean() > 0.9 and (dist.min(axis=0) < 2e-2).mean() > 0.9
     with pytest.raises(RuntimeError):
         S3FD()(x.cpu())                                              # no CPU fallback
+
+
+@pytest.mark.gpu
+def test_arcface_identity_comparator_kernel_chain_matches_the_reference_fixture(golden):
+    from warpedganspace_b200.eval_arcface import IDComparator
+    fx = golden('eval_nets.pt')['arcface']
+    sd = o_en.init_arcface_state(gen(fx['seed']))
+    idc = IDComparator()
+    assert set(idc.backbone.state_dict()) == set(sd)               # model_ir_se50.pth loads as it is
+    idc.backbone.load_state_dict(sd, strict=True)
+    idc.cuda()
+    xa = torch.rand(3, 3, 256, 256, generator=gen(fx['seed_x'])) * 2 - 1
+    xa[2] = 0.7 * xa[0] + 0.3 * xa[1]
+    xa = xa.cuda()
+    with torch.no_grad():
+        assert rel(idc.extract_feats(xa), fx['feats']) < 1e-3
+        sims = torch.stack([idc(xa[0:1], xa[t: t + 1]) for t in range(3)])
+    assert (sims.cpu() - fx['sim']).abs().max() < 1e-4
+    with pytest.raises(RuntimeError):
+        idc.backbone(xa[:, :, :112, :112].cpu())
+
+
+@pytest.mark.gpu
+def test_au_detector_kernel_chain_matches_the_reference_fixture(golden):
+    from warpedganspace_b200.eval_au import AUdetector
+    fx = golden('eval_nets.pt')['au']
+    sd = o_en.init_au_state(gen(fx['seed']))
+    det = AUdetector()
+    assert set(det.FAN.state_dict()) == set(sd)                    # disfa_adaptation_f0.pth['state_dict'] loads as it is
+    det.FAN.load_state_dict(sd, strict=True)
+    det.FAN.cuda()
+    xu = (255.0 * torch.rand(2, 3, 256, 256, generator=gen(fx['seed_x']))).cuda()
+    with torch.no_grad():
+        heat = det.FAN((xu - xu.min()) / (xu.max() - xu.min()))
+    assert rel(heat[:, :, ::4, ::4], fx['heat']) < 1e-3
+    assert rel(det.detect_AU(xu), fx['intensities']) < 1e-3
+    with pytest.raises(RuntimeError):
+        det.FAN(xu.cpu())
+
+
+@pytest.mark.gpu
+def test_attribute_traversal_with_every_predictor_on_the_gpu(tmp_path):
+    """All six predictors as kernel chains (seeded weights): every file of the reference's eval_json / eval_np layout is written,
+    the identity score is the batched cosine similarity to the centre frame, the AU table has one row per action unit."""
+    from warpedganspace_b200 import attribute_space as A
+    from warpedganspace_b200.eval_resnet import fairface_resnet34, hopenet_resnet50, celeba_attr_resnet50
+    from warpedganspace_b200.eval_sfd import SFDDetector
+    from warpedganspace_b200.eval_arcface import IDComparator
+    from warpedganspace_b200.eval_au import AUdetector
+    exp, h_dir = _fake_traversal(tmp_path, n_paths=2, n_img=3, size=96)
+    det, idc, au = SFDDetector(), IDComparator().cuda(), AUdetector()
+    det.face_detector.load_state_dict(o_en.init_s3fd_state(gen(31)))
+    det.face_detector.cuda()
+    idc.backbone.load_state_dict(o_en.init_arcface_state(gen(32)))
+    au.FAN.load_state_dict(o_en.init_au_state(gen(33)))
+    au.FAN.cuda()
+    def detector(x):        # seeded weights give boxes far outside the frame: run the detector, hand the driver a plausible box
+        found = det(x)
+        assert len(found) == x.shape[0]
+        return [[np.array([60.0, 70.0, 190.0, 200.0, 0.9], dtype=np.float32)] for _ in found]
+
+    preds = {'face_detector': detector, 'id_comparator': idc, 'au_detector': au, 'fairface': fairface_resnet34().cuda(),
+             'hopenet': hopenet_resnet50().cuda(), 'celeba': celeba_attr_resnet50().cuda()}
+    A.traverse_attribute_space(exp, 'pool', shift_steps=2, eps=0.2, predictors=preds, gan_type='StyleGAN2')
+    nd, jd = os.path.join(h_dir, 'eval_np'), os.path.join(h_dir, 'eval_json')
+    want = ['face_width', 'face_height', 'identity', 'age', 'race', 'gender', 'yaw', 'pitch', 'roll', 'celeba_bangs',
+            'celeba_eyeglasses', 'celeba_beard', 'celeba_smiling', 'celeba_age'] + ['%s_%s' % kv for kv in A.AUs.items()]
+    for name in want:
+        t = np.load(os.path.join(nd, name + '.npy'))
+        assert t.shape == (2, 3) and np.isfinite(t).all(), name
+    ident = np.load(os.path.join(nd, 'identity.npy'))
+    assert np.allclose(ident[:, 1], 1.0, atol=1e-5) and (ident <= 1.0 + 1e-5).all()
+    import json
+    with open(os.path.join(jd, 'au.json')) as f:
+        au_rows = json.load(f)
+    assert len(au_rows['0']) == 12 and len(au_rows['0'][0]) == 3
+    frames = A.load_path_images(os.path.join(h_dir, 'paths_images', 'path_000'), 'cuda')
+    small = A.resize_center_crop(frames, 256)
+    with torch.no_grad():                                          # the per-pair call of the reference gives the same scores
+        pair = [float(idc(small[1:2] / 255.0 * 2.0 - 1.0, small[t: t + 1] / 255.0 * 2.0 - 1.0)) for t in range(3)]
+    assert np.allclose(ident[0], pair, atol=1e-5)
 

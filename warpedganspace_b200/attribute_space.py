@@ -10,10 +10,11 @@ Built here (the consumer of the traversal frames)
   * the S3FD face detector (eval_sfd.SFDDetector: VGG trunk + heads on the same convs, soft-max / anchor decode / NMS as the
     reference's batch_detect);
   * face cropping, resize + centre crop + normalisation on the device.
-NOT built: the ArcFace identity comparator and the AU hourglass detector (lib/evaluation/{archface,au_detector}).
-They plug in as callables (``predictors['id_comparator' | 'au_detector']``) with the reference's call signatures; files of
-absent predictors are not written.  Without a face detector every frame uses the reference's own no-detection fallback
-(the full 256 x 256 frame, traverse_attribute_space.py:396-399).
+  * the ArcFace identity comparator (eval_arcface.IDComparator, IR-SE-50) and the action-unit detector
+    (eval_au.AUdetector, face-alignment network + lightweight hourglass).
+Every predictor is optional (``predictors[...]`` holds callables with the reference's call signatures, so a reference module
+can stand in for any of them); files of absent predictors are not written.  Without a face detector every frame uses the
+reference's own no-detection fallback (the full 256 x 256 frame, traverse_attribute_space.py:396-399).
 """
 import glob
 import json
@@ -128,9 +129,13 @@ def path_attributes(frames, predictors, gan_type='StyleGAN2'):
             out[key] = ((s.argmax(dim=1) + s.max(dim=1).values) / 6.0).cpu().numpy().tolist()
     idc = predictors.get('id_comparator')
     if idc is not None:                                                            # :374-392: similarity to the centre frame
-        ref_img = small[T // 2: T // 2 + 1] / 255.0 * 2.0 - 1.0
         with torch.no_grad():
-            out['identity'] = [float(idc(ref_img, small[t: t + 1] / 255.0 * 2.0 - 1.0)) for t in range(T)]
+            if hasattr(idc, 'extract_feats'):                                      # one batched pass instead of T pairs
+                feats = idc.extract_feats(small / 255.0 * 2.0 - 1.0)
+                out['identity'] = F.cosine_similarity(feats[T // 2: T // 2 + 1], feats, dim=1, eps=1e-6).cpu().numpy().tolist()
+            else:
+                ref_img = small[T // 2: T // 2 + 1] / 255.0 * 2.0 - 1.0
+                out['identity'] = [float(idc(ref_img, small[t: t + 1] / 255.0 * 2.0 - 1.0)) for t in range(T)]
     ff = predictors.get('fairface')
     if ff is not None:                                                             # :394-433
         with torch.no_grad():
