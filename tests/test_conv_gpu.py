@@ -117,6 +117,33 @@ def test_conv_transpose_stride2(N, Ci, H, Co):
     assert rel(got6, nhwc(want6)) < 2e-5
 
 
+def test_conv_transpose_phases_on_forked_streams_equal_the_serial_launches(monkeypatch):
+    """conv.PHASE_STREAMS_MAX: the four output-phase launches of a small up-conv run on forked streams (parallel branches of a
+    captured graph); same kernels, disjoint output pixels -> bit-identical to the serial order, eagerly and under capture."""
+    from warpedganspace_b200 import conv
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 64, 8, 8, generator=g).cuda()
+    wt = torch.randn(64, 96, 3, 3, generator=g).cuda() / 24.0
+    xs, ws = conv.pack_split32(nhwc(x)), conv.pack_weights(wt.permute(1, 0, 2, 3).contiguous())
+    monkeypatch.setattr(conv, 'PHASE_STREAMS_MAX', 0)
+    serial = conv.conv_transpose2d_s2(xs, ws, 3)
+    monkeypatch.setattr(conv, 'PHASE_STREAMS_MAX', 1 << 30)
+    forked = conv.conv_transpose2d_s2(xs, ws, 3)
+    torch.cuda.synchronize()
+    assert torch.equal(serial, forked)
+    out = torch.zeros_like(serial)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            conv.conv_transpose2d_s2(xs, ws, 3, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(serial, out)
+
+
 def test_simt_twin_matches(monkeypatch):
     """The CUDA-core twin of the same contract agrees with the tensor-core kernel bit-for-bit-ish."""
     import subprocess, sys, os

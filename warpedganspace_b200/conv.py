@@ -308,6 +308,7 @@ def conv_transpose2d_s2(x_split, w_split, k, *, out=None, crop=0, **kw_args):
     co = kw_args.get('cout') or w_split.shape[1]
     if out is None:
         out = torch.empty(n, oh, ow, co, dtype=torch.float32, device=x_split.device)
+    phases = []
     for py in range(2):
         for px in range(2):
             # output Y = 2*q + py (in cropped coords); uncropped Yf = Y + crop = 2*iy + ky
@@ -318,8 +319,39 @@ def conv_transpose2d_s2(x_split, w_split, k, *, out=None, crop=0, **kw_args):
             if gh <= 0 or gw <= 0 or not kys or not kxs:
                 continue
             taps = [((py + crop - ky) // 2, (px + crop - kx) // 2, ky * k + kx) for ky in kys for kx in kxs]
-            conv_taps(x_split, w_split, taps, out, grid=(gh, gw), out_origin=(py, px), out_step=(2, 2), **kw_args)
+            phases.append((taps, (gh, gw), (py, px)))
+    # The phase launches write disjoint pixels of `out`.  On the low-resolution layers each of them fills a fraction of the SMs
+    # (8 .. 256 CTAs of ~30 us), so they run side by side on forked streams (event fork / join; inside a CUDA graph capture
+    # this becomes four parallel branches).  PHASE_STREAMS_MAX bounds the layer size (output elements of one phase).
+    fork = len(phases) > 1 and PROFILE is None and n * phases[0][1][0] * phases[0][1][1] * co <= PHASE_STREAMS_MAX
+    cur = torch.cuda.current_stream() if fork else None
+    if fork:
+        side = _phase_streams(x_split.device, len(phases) - 1)
+        start = torch.cuda.Event()
+        start.record(cur)
+    for i, (taps, grid, origin) in enumerate(phases):
+        if fork and i > 0:
+            side[i - 1].wait_event(start)
+            with torch.cuda.stream(side[i - 1]):
+                conv_taps(x_split, w_split, taps, out, grid=grid, out_origin=origin, out_step=(2, 2), **kw_args)
+                done = torch.cuda.Event()
+                done.record(side[i - 1])
+            cur.wait_event(done)
+        else:
+            conv_taps(x_split, w_split, taps, out, grid=grid, out_origin=origin, out_step=(2, 2), **kw_args)
     return out
+
+
+PHASE_STREAMS_MAX = int(os.environ.get('WGS_PHASE_STREAMS_MAX', '4500000'))      # up to 512 ch @ 33 x 33 x 8 images per phase
+_PHASE_STREAMS = {}
+
+
+def _phase_streams(device, count):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _PHASE_STREAMS.setdefault(key, [])
+    while len(pool) < count:
+        pool.append(torch.cuda.Stream(device=device, priority=-1))
+    return pool[:count]
 
 
 # ---- phase-packed (merged) strided data-gradients / transposed convs -----------------------------------------------
