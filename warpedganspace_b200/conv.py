@@ -320,29 +320,39 @@ def conv_transpose2d_s2(x_split, w_split, k, *, out=None, crop=0, **kw_args):
                 continue
             taps = [((py + crop - ky) // 2, (px + crop - kx) // 2, ky * k + kx) for ky in kys for kx in kxs]
             phases.append((taps, (gh, gw), (py, px)))
-    # The phase launches write disjoint pixels of `out`.  On the low-resolution layers each of them fills a fraction of the SMs
-    # (8 .. 256 CTAs of ~30 us), so they run side by side on forked streams (event fork / join; inside a CUDA graph capture
-    # this becomes four parallel branches).  PHASE_STREAMS_MAX bounds the layer size (output elements of one phase).
-    fork = len(phases) > 1 and PROFILE is None and n * phases[0][1][0] * phases[0][1][1] * co <= PHASE_STREAMS_MAX
-    cur = torch.cuda.current_stream() if fork else None
-    if fork:
-        side = _phase_streams(x_split.device, len(phases) - 1)
-        start = torch.cuda.Event()
-        start.record(cur)
-    for i, (taps, grid, origin) in enumerate(phases):
-        if fork and i > 0:
-            side[i - 1].wait_event(start)
-            with torch.cuda.stream(side[i - 1]):
-                conv_taps(x_split, w_split, taps, out, grid=grid, out_origin=origin, out_step=(2, 2), **kw_args)
-                done = torch.cuda.Event()
-                done.record(side[i - 1])
-            cur.wait_event(done)
-        else:
-            conv_taps(x_split, w_split, taps, out, grid=grid, out_origin=origin, out_step=(2, 2), **kw_args)
+    run_phases([lambda taps=taps, grid=grid, origin=origin: conv_taps(x_split, w_split, taps, out, grid=grid, out_origin=origin,
+                                                                      out_step=(2, 2), **kw_args)
+                for taps, grid, origin in phases], n * phases[0][1][0] * phases[0][1][1] * co, x_split.device)
     return out
 
 
-PHASE_STREAMS_MAX = int(os.environ.get('WGS_PHASE_STREAMS_MAX', '4500000'))      # up to 512 ch @ 33 x 33 x 8 images per phase
+def run_phases(launches, elements, device):
+    """Run the output-phase launches of one up-sampling conv (callables; they write disjoint pixels of one tensor).  On the
+    low-resolution layers each of them fills a fraction of the SMs (8 .. 256 CTAs of ~30 us), so they run side by side on forked
+    streams (event fork / join; inside a CUDA graph capture this becomes parallel branches).  PHASE_STREAMS_MAX bounds the layer
+    size (output elements of one phase); per-launch profiling keeps them serial."""
+    fork = len(launches) > 1 and PROFILE is None and elements <= PHASE_STREAMS_MAX
+    if not fork:
+        for launch in launches:
+            launch()
+        return
+    cur = torch.cuda.current_stream()
+    side = _phase_streams(device, len(launches) - 1)
+    start = torch.cuda.Event()
+    start.record(cur)
+    for i, launch in enumerate(launches):
+        if i == 0:
+            launch()
+            continue
+        side[i - 1].wait_event(start)
+        with torch.cuda.stream(side[i - 1]):
+            launch()
+            done = torch.cuda.Event()
+            done.record(side[i - 1])
+        cur.wait_event(done)
+
+
+PHASE_STREAMS_MAX = int(os.environ.get('WGS_PHASE_STREAMS_MAX', '9000000'))      # up to 256 ch @ 65 x 65 x 8 images per phase
 _PHASE_STREAMS = {}
 
 

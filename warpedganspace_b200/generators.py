@@ -291,8 +291,9 @@ def up_conv_forward(xs, w_fwd, taps, co, ci, out=None, **epilogue):
     n, h, w = xs.shape[0], xs.shape[1], xs.shape[2]
     if out is None and epilogue.get('out_split') is None:
         out = torch.empty(n, 2 * h, 2 * w, co, device=xs.device, dtype=torch.float32)
-    for (py, px), tp in taps.items():
-        C.conv_taps(xs, w_fwd, tp, out, grid=(h, w), out_origin=(py, px), out_step=(2, 2), cout=co, cin=ci, **epilogue)
+    C.run_phases([lambda py=py, px=px, tp=tp: C.conv_taps(xs, w_fwd, tp, out, grid=(h, w), out_origin=(py, px), out_step=(2, 2),
+                                                         cout=co, cin=ci, **epilogue)
+                  for (py, px), tp in taps.items()], n * h * w * co, xs.device)
     return out
 
 
