@@ -568,6 +568,9 @@ class BigGANGenerator(_Frozen):
         return out.permute(0, 2, 3, 1).contiguous()
 
 
+GBLOCK_FORK = os.environ.get('WGS_GBLOCK_FORK', '1') != '0'      # 0 = BigGAN's shortcut branch in line with the main branch (A/B switch)
+
+
 class _GBlockFn(torch.autograd.Function):
     """GBlock (models/BigGAN/layers.py:395-405) as one hand-scheduled node over NHWC fp32 activations:
         r1 = relu(A1 x + B1) -> conv1(up(r1)) + b1 = h1 -> r2 = relu(A2 h1 + B2) -> conv2(r2) + b2 + up(conv_sc(x) + b_sc)
@@ -582,14 +585,28 @@ class _GBlockFn(torch.autograd.Function):
         x = x.contiguous()
         n, h, w, ci = x.shape
         co = e['co']
-        r1s = affine_act_pack(x, A1.detach(), B1.detach(), relu=True)
-        xs = affine_act_pack(x, relu=False)
         # (split_k = 2: batch-independent cluster split-K for the 4 x 4 .. 16 x 16 blocks - 1536 .. 384 channels, up to 432
         # dependent contraction steps per CTA otherwise)
-        out = up_conv_forward(xs, e['wsc'], {(py, px): [(0, 0, 0)] for py in range(2) for px in range(2)}, co, ci,
-                              beta=e['b_conv_sc'], split_k=2)
+        # The shortcut branch (operand pack + 1x1 up-conv) depends on x alone: it runs on a forked stream beside
+        # ccbn -> conv1 -> ccbn of the main branch and is joined in front of conv2, which accumulates on top of it.
+        main = torch.cuda.current_stream()
+        aux = C._phase_streams(x.device, 4)[3] if (GBLOCK_FORK and C.PROFILE is None) else None
+        if aux is not None:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            aux.wait_event(fork)
+        with torch.cuda.stream(aux if aux is not None else main):
+            xs = affine_act_pack(x, relu=False)
+            out = up_conv_forward(xs, e['wsc'], {(py, px): [(0, 0, 0)] for py in range(2) for px in range(2)}, co, ci,
+                                  beta=e['b_conv_sc'], split_k=2)
+            if aux is not None:
+                joined = torch.cuda.Event()
+                joined.record(aux)
+        r1s = affine_act_pack(x, A1.detach(), B1.detach(), relu=True)
         h1 = up_conv_forward(r1s, e['w1'], e['taps1'], co, ci, beta=e['b_conv1'], split_k=2)
         r2s = affine_act_pack(h1, A2.detach(), B2.detach(), relu=True)
+        if aux is not None:
+            main.wait_event(joined)
         C.conv2d(r2s, e['w2'], 3, 3, padding=1, out=out, accumulate=True, beta=e['b_conv2'], cin=co, split_k=2)
         if any(ctx.needs_input_grad[:5]):
             g0 = grad_from
@@ -612,13 +629,29 @@ class _GBlockFn(torch.autograd.Function):
         n, h, w, ci = x.shape
         co = e['co']
         ds = C.pack_split32(d_out.contiguous())
+        # shortcut: adjoint of up(conv_sc(x)) = conv_sc^T of the 2x2 sum-pooled gradient = four stride-2 taps of the 1x1 weight;
+        # it needs ds alone, so it runs on the forked stream beside the main chain and is added at the end
+        sc_taps = [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)]
+        main = torch.cuda.current_stream()
+        aux = C._phase_streams(x.device, 4)[3] if (GBLOCK_FORK and C.PROFILE is None) else None
+        if aux is not None:
+            dsc = torch.empty(n, h, w, ci, device=x.device, dtype=torch.float32)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            aux.wait_event(fork)
+            with torch.cuda.stream(aux):
+                C.conv_taps(ds, e['wsc_bwd'], sc_taps, dsc, grid=(h, w), in_stride=2, cout=ci, cin=co, split_k=2)
+                joined = torch.cuda.Event()
+                joined.record(aux)
         dr2 = C.conv2d(ds, e['w2_bwd'], 3, 3, padding=1, cout=co, cin=co, split_k=2)
         dh1s, dA2, dB2 = affine_act_bwd(dr2, h1, A2.detach(), B2.detach(), relu=True, split=True)
         dr1 = C.conv2d(dh1s, e['w1_bwd'], 4, 4, stride=2, padding=1, cout=ci, cin=co, split_k=2)     # adjoint of up + conv1
         dx, dA1, dB1 = affine_act_bwd(dr1, x, A1.detach(), B1.detach(), relu=True, split=False)
-        # shortcut: adjoint of up(conv_sc(x)) = conv_sc^T of the 2x2 sum-pooled gradient = four stride-2 taps of the 1x1 weight
-        C.conv_taps(ds, e['wsc_bwd'], [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)], dx, grid=(h, w), in_stride=2, cout=ci,
-                    cin=co, accumulate=True, split_k=2)
+        if aux is not None:
+            main.wait_event(joined)
+            dx.add_(dsc)
+        else:
+            C.conv_taps(ds, e['wsc_bwd'], sc_taps, dx, grid=(h, w), in_stride=2, cout=ci, cin=co, accumulate=True, split_k=2)
         return dx, dA1, dB1, dA2, dB2
 
 
