@@ -308,17 +308,26 @@ def affine_act_pack(x, A=None, B=None, relu=True, split=True):
     return out
 
 
-def affine_act_bwd(dz, x, A, B, relu=True, split=True, want_sums=True):
-    """-> (dx [split32 or fp32], dA, dB) for o = [relu](A x + B); A, B [groups, C] (groups = N, or 1 for a per-channel map)."""
+def affine_act_bwd(dz, x, A, B, relu=True, split=True, want_sums=True, pad_rows=0):
+    """-> (dx [split32 or fp32], dA, dB) for o = [relu](A x + B); A, B [groups, C] (groups = N, or 1 for a per-channel map).
+    pad_rows > 0 (per-sample maps, fp32 dx): the results are the trailing rows of tensors with pad_rows leading ZERO rows -
+    the gradient layout autograd wants for a batch whose first pad_rows samples carry no gradient, without a torch.cat."""
     n, h, w, c = x.shape
     groups = A.shape[0]
-    shape = (n, h, w, C.chunks_of(c), 64) if split else x.shape
-    dx = torch.empty(shape, device=x.device, dtype=torch.bfloat16 if split else torch.float32)
-    sums = torch.zeros(2, groups, c, device=x.device, dtype=torch.float32) if want_sums else None
+    assert pad_rows == 0 or (not split and (groups == n or not want_sums))
+    if split:
+        dx_full = torch.empty(n, h, w, C.chunks_of(c), 64, device=x.device, dtype=torch.bfloat16)
+    elif pad_rows:
+        dx_full = torch.zeros(pad_rows + n, h, w, c, device=x.device, dtype=torch.float32)
+    else:
+        dx_full = torch.empty(n, h, w, c, device=x.device, dtype=torch.float32)
+    dx = dx_full[pad_rows:]
+    sums_full = torch.zeros(2, pad_rows + groups, c, device=x.device, dtype=torch.float32) if want_sums else None
+    sums = sums_full[:, pad_rows:] if want_sums else None
     _lib.call('wgs_affine_act_bwd', _lib.ptr(dz), _lib.ptr(x), _lib.ptr(A), _lib.ptr(B), groups, (n * h * w) // groups, c,
               int(relu), _lib.ptr(dx) if split else None, None if split else _lib.ptr(dx),
               _lib.ptr(sums[0]) if want_sums else None, _lib.ptr(sums[1]) if want_sums else None, _lib.stream())
-    return (dx, sums[0], sums[1]) if want_sums else (dx, None, None)
+    return (dx_full, sums_full[0], sums_full[1]) if want_sums else (dx_full, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -531,16 +540,46 @@ class BigGANGenerator(_Frozen):
             ys = [y] * nb
         h = F.linear(z, sn['linear'], t['linear.bias'].detach()).view(z.shape[0], -1, self.bottom_width, self.bottom_width)
         h = h.permute(0, 2, 3, 1).contiguous()                                  # NHWC from here on
+        # The ccbn maps of every block depend on (y, z) alone: all of them are launched up front on a forked stream (four small
+        # library GEMMs per block) and each block waits for its own four only - off the critical path from block 1 on, forward
+        # and (autograd runs a node's backward on its forward stream) backward.
+        main = torch.cuda.current_stream()
+        aux = C._phase_streams(z.device, 5)[4] if (CCBN_FORK and C.PROFILE is None) else None
+        if aux is not None:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            aux.wait_event(fork)
+        ab = []
+        with torch.cuda.stream(aux if aux is not None else main):
+            for i, e in enumerate(P['blocks']):
+                p = 'blocks.%d.0' % i
+                maps = self._ccbn_affine(sn, e, p, 'bn1', ys[i]) + self._ccbn_affine(sn, e, p, 'bn2', ys[i])
+                ready = None
+                if aux is not None:
+                    ready = torch.cuda.Event()
+                    ready.record(aux)
+                ab.append((maps, ready))
         for i, e in enumerate(P['blocks']):
-            p = 'blocks.%d.0' % i
-            A1, B1 = self._ccbn_affine(sn, e, p, 'bn1', ys[i])
-            A2, B2 = self._ccbn_affine(sn, e, p, 'bn2', ys[i])
+            (A1, B1, A2, B2), ready = ab[i]
+            if ready is not None:
+                main.wait_event(ready)
             h = _GBlockFn.apply(h, A1, B1, A2, B2, e, grad_from)
             if self.arch['attn'][i]:
                 if grad_from > 0:          # library ops under autograd: keep the un-shifted rows out of the graph
-                    with torch.no_grad():
+                    # (and on the forked stream: the two halves are independent chains of small library kernels)
+                    if aux is not None:
+                        fork = torch.cuda.Event()
+                        fork.record(main)
+                        aux.wait_event(fork)
+                    with torch.cuda.stream(aux if aux is not None else main), torch.no_grad():
                         h_plain = self._attention(sn, t, 'blocks.%d.1' % i, h[:grad_from])
-                    h = torch.cat([h_plain, self._attention(sn, t, 'blocks.%d.1' % i, h[grad_from:])], dim=0)
+                        if aux is not None:
+                            plain_done = torch.cuda.Event()
+                            plain_done.record(aux)
+                    h_shifted = self._attention(sn, t, 'blocks.%d.1' % i, h[grad_from:])
+                    if aux is not None:
+                        main.wait_event(plain_done)
+                    h = torch.cat([h_plain, h_shifted], dim=0)
                 else:
                     h = self._attention(sn, t, 'blocks.%d.1' % i, h)
         return _OutputFn.apply(h, P['out'], grad_from).permute(0, 3, 1, 2)
@@ -568,6 +607,17 @@ class BigGANGenerator(_Frozen):
         return out.permute(0, 2, 3, 1).contiguous()
 
 
+def _affine_bwd_split_padded(dz, x, A, B, pad_rows):
+    """affine_act_bwd with a split32 dx and dA / dB carrying pad_rows leading zero rows."""
+    n, h, w, c = x.shape
+    dx = torch.empty(n, h, w, C.chunks_of(c), 64, device=x.device, dtype=torch.bfloat16)
+    sums = torch.zeros(2, pad_rows + n, c, device=x.device, dtype=torch.float32)
+    _lib.call('wgs_affine_act_bwd', _lib.ptr(dz), _lib.ptr(x), _lib.ptr(A), _lib.ptr(B), n, h * w, c, 1, _lib.ptr(dx), None,
+              _lib.ptr(sums[0, pad_rows:]), _lib.ptr(sums[1, pad_rows:]), _lib.stream())
+    return dx, sums[0], sums[1]
+
+
+CCBN_FORK = os.environ.get('WGS_CCBN_FORK', '1') != '0'        # 0 = BigGAN's ccbn linears in line, in front of each block (A/B switch)
 GBLOCK_FORK = os.environ.get('WGS_GBLOCK_FORK', '1') != '0'      # 0 = BigGAN's shortcut branch in line with the main branch (A/B switch)
 
 
@@ -618,14 +668,11 @@ class _GBlockFn(torch.autograd.Function):
     def backward(ctx, d_out):
         x, h1, A1, B1, A2, B2 = ctx.saved_tensors           # rows >= grad_from only
         e, g0 = ctx.e, ctx.g0
-        if g0:
-            res = _GBlockFn._backward_rows(x, h1, A1, B1, A2, B2, e, d_out[g0:])
-            pad = lambda t: torch.cat([t.new_zeros(g0, *t.shape[1:]), t], dim=0)
-            return tuple(pad(t) for t in res) + (None, None)
-        return _GBlockFn._backward_rows(x, h1, A1, B1, A2, B2, e, d_out) + (None, None)
+        # (rows < grad_from carry no gradient: the kernels write rows >= grad_from of zero-initialised full-batch tensors)
+        return _GBlockFn._backward_rows(x, h1, A1, B1, A2, B2, e, d_out[g0:] if g0 else d_out, g0) + (None, None)
 
     @staticmethod
-    def _backward_rows(x, h1, A1, B1, A2, B2, e, d_out):
+    def _backward_rows(x, h1, A1, B1, A2, B2, e, d_out, pad_rows=0):
         n, h, w, ci = x.shape
         co = e['co']
         ds = C.pack_split32(d_out.contiguous())
@@ -644,15 +691,16 @@ class _GBlockFn(torch.autograd.Function):
                 joined = torch.cuda.Event()
                 joined.record(aux)
         dr2 = C.conv2d(ds, e['w2_bwd'], 3, 3, padding=1, cout=co, cin=co, split_k=2)
-        dh1s, dA2, dB2 = affine_act_bwd(dr2, h1, A2.detach(), B2.detach(), relu=True, split=True)
+        dh1s, dA2, dB2 = _affine_bwd_split_padded(dr2, h1, A2.detach(), B2.detach(), pad_rows)
         dr1 = C.conv2d(dh1s, e['w1_bwd'], 4, 4, stride=2, padding=1, cout=ci, cin=co, split_k=2)     # adjoint of up + conv1
-        dx, dA1, dB1 = affine_act_bwd(dr1, x, A1.detach(), B1.detach(), relu=True, split=False)
+        dx_full, dA1, dB1 = affine_act_bwd(dr1, x, A1.detach(), B1.detach(), relu=True, split=False, pad_rows=pad_rows)
+        dx = dx_full[pad_rows:]
         if aux is not None:
             main.wait_event(joined)
             dx.add_(dsc)
         else:
             C.conv_taps(ds, e['wsc_bwd'], sc_taps, dx, grid=(h, w), in_stride=2, cout=ci, cin=co, accumulate=True, split_k=2)
-        return dx, dA1, dB1, dA2, dB2
+        return dx_full, dA1, dB1, dA2, dB2
 
 
 class _OutputFn(torch.autograd.Function):
@@ -674,7 +722,5 @@ class _OutputFn(torch.autograd.Function):
         o, g0 = ctx.o, ctx.g0
         g = (dimg[g0:] * (1.0 - img * img)).contiguous()                        # tanh'
         dr = C.conv2d(C.pack_split32(g), o['w_bwd'], 3, 3, padding=1, cout=o['ci'], cin=3)
-        dh, _, _ = affine_act_bwd(dr, h, o['A'], o['B'], relu=True, split=False, want_sums=False)
-        if g0:
-            dh = torch.cat([dh.new_zeros(g0, *dh.shape[1:]), dh], dim=0)
+        dh, _, _ = affine_act_bwd(dr, h, o['A'], o['B'], relu=True, split=False, want_sums=False, pad_rows=g0)
         return dh, None, None
