@@ -60,6 +60,10 @@ def _bn_list(net):
 # B200 (profiles/r02_launch_list_summary.md): the pass it removes costs 0.32 ms per step, the epilogue work it adds 0.33 ms
 # (the multi-tile kernels of the stem / layer 1 are epilogue-bound: 73 -> 100 us per launch) - a wash, so the separate pass
 # stays the default and this is an A/B switch.
+# The projection shortcut of layer 2 / 3 / 4's first block on a forked stream beside the main branch, for blocks of at most this
+# many output elements (latency-bound maps: the 128 x 128 inputs of config 4 gain 2.5 %, 6.96 / 7.06 -> 6.82 ms; on 1024 x 1024
+# inputs every launch fills the GPU and the fork costs 0.4 %, 15.94 / 15.98 -> 16.03 / 16.04 ms); 0 = never
+SHORTCUT_FORK_MAX = int(os.environ.get('WGS_SHORTCUT_FORK_MAX', '1000000'))
 EPILOGUE_STATS = os.environ.get('WGS_EPILOGUE_STATS', '0') == '1'
 
 
@@ -255,19 +259,35 @@ class ResNetFeatures(torch.autograd.Function):
                   _lib.ptr(bn1.running_var), _lib.stream())
         tape['stem'] = (xs2d, y0, st0, pool_idx, (n, ci, h, w))
         tape['blocks'] = []
+        main = torch.cuda.current_stream()
+        aux_stream = C._phase_streams(x.device, 4)[3] if (SHORTCUT_FORK_MAX > 0 and C.PROFILE is None) else None
         for li in range(1, 5):
             for b in getattr(net, 'layer%d' % li):
                 s = b.stride
+                small = cur.shape[0] * (cur.shape[1] // s) * (cur.shape[2] // s) * b.conv2.weight.shape[0] <= SHORTCUT_FORK_MAX
+                aux = aux_stream if small else None
+                if hasattr(b, 'downsample'):
+                    # the projection shortcut (1x1 / 2 conv + BatchNorm: three launches that depend on the block input alone)
+                    # runs on a forked stream beside conv1 -> bn1 -> conv2 and is joined in front of bn2
+                    if aux is not None:
+                        fork = torch.cuda.Event()
+                        fork.record(main)
+                        aux.wait_event(fork)
+                    with torch.cuda.stream(aux if aux is not None else main):
+                        yd, pd = conv(cur_s, b.downsample[0].weight, s, 0, b.downsample[1])
+                        idt, _, std = _bn_forward(yd, b.downsample[1], None, False, False, pool, pre=pd)
+                        if aux is not None:
+                            joined = torch.cuda.Event()
+                            joined.record(aux)
+                else:
+                    yd, std, idt = None, None, cur
                 y1, p1 = conv(cur_s, b.conv1.weight, s, 1, b.bn1)
                 # (the mid-block activation is only needed as the next conv's operand: its ReLU mask is re-derived from y1 in
                 # the backward pass, so the fp32 copy is neither written here nor read there)
                 z1, z1s, st1 = _bn_forward(y1, b.bn1, None, True, True, pool, want_f32=False, pre=p1)
                 y2, p2 = conv(z1s, b.conv2.weight, 1, 1, b.bn2)
-                if hasattr(b, 'downsample'):
-                    yd, pd = conv(cur_s, b.downsample[0].weight, s, 0, b.downsample[1])
-                    idt, _, std = _bn_forward(yd, b.downsample[1], None, False, False, pool, pre=pd)
-                else:
-                    yd, std, idt = None, None, cur
+                if yd is not None and aux is not None:
+                    main.wait_event(joined)
                 out, outs, st2 = _bn_forward(y2, b.bn2, idt, True, True, pool, pre=p2)
                 tape['blocks'].append((b, cur_s, cur.shape, y1, z1, z1s, st1, y2, out, st2, yd, std))
                 cur, cur_s = out, outs
@@ -287,6 +307,8 @@ class ResNetFeatures(torch.autograd.Function):
         pool = _Pool(sum(2 * ((b.num_features + 3) // 4 * 4) for b in bns), dfeat.device)
         n, fh, fw, fc = tape['final_shape']
         dcur = (dfeat.contiguous().view(n, 1, 1, fc) / float(fh * fw)).expand(n, fh, fw, fc).contiguous()
+        main = torch.cuda.current_stream()
+        aux_stream = C._phase_streams(dfeat.device, 4)[3] if (SHORTCUT_FORK_MAX > 0 and C.PROFILE is None) else None
 
         # Weight gradients hang off the data-gradient chain: nothing on the way back to the generator waits for them.
         # With a side stream from the trainer (net._wgs_wgrad_stream, low priority) they are launched there as soon as
@@ -317,11 +339,27 @@ class ResNetFeatures(torch.autograd.Function):
             s = b.stride
             _, xh, xw, xc = x_shape
             dy2s, dres = _bn_backward(dcur, out, y2, st2, b.bn2, True, True, pool, grads)
+            aux = aux_stream if y2.numel() <= SHORTCUT_FORK_MAX else None
+            if yd is not None and aux is not None:
+                # shortcut branch on the forked stream: BatchNorm backward, weight gradient, data gradient into dx; the main
+                # branch accumulates conv1's data gradient on top of it after the join
+                fork = torch.cuda.Event()
+                fork.record(main)
+                aux.wait_event(fork)
+                with torch.cuda.stream(aux):
+                    dyds, _ = _bn_backward(dres, None, yd, std, b.downsample[1], False, False, pool, grads)
+                    wgrad(xs, dyds, b.downsample[0].weight, s, 0)
+                    dx = dgrad(dyds, b.downsample[0].weight, (xh, xw), s, 0)
+                    joined = torch.cuda.Event()
+                    joined.record(aux)
             wgrad(z1s, dy2s, b.conv2.weight, 1, 1)
             dz1 = dgrad(dy2s, b.conv2.weight, (y1.shape[1], y1.shape[2]), 1, 1)
             dy1s, _ = _bn_backward(dz1, z1, y1, st1, b.bn1, True, False, pool, grads)
             wgrad(xs, dy1s, b.conv1.weight, s, 1)
-            if yd is not None:
+            if yd is not None and aux is not None:
+                main.wait_event(joined)
+                dx = dgrad(dy1s, b.conv1.weight, (xh, xw), s, 1, out=dx, accumulate=True)
+            elif yd is not None:
                 dyds, _ = _bn_backward(dres, None, yd, std, b.downsample[1], False, False, pool, grads)
                 wgrad(xs, dyds, b.downsample[0].weight, s, 0)
                 dx = dgrad(dy1s, b.conv1.weight, (xh, xw), s, 1)
