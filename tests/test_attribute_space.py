@@ -65,6 +65,29 @@ def test_oracle_arcface_and_au_match_the_reference_fixture(golden):
     assert rel(o_en.au_heatmaps(sd, (xu - xu.min()) / (xu.max() - xu.min()))[:, :, ::4, ::4], fx['au']['heat']) < 1e-5
 
 
+def test_predictor_modules_carry_the_reference_keys_and_refuse_the_cpu():
+    """Host-side contract of the six predictors (no GPU needed): the parameter trees are the reference's (so the published
+    checkpoints load with load_state_dict) and a CPU call fails loudly instead of falling back."""
+    from warpedganspace_b200.eval_resnet import fairface_resnet34, hopenet_resnet50, celeba_attr_resnet50
+    from warpedganspace_b200.eval_sfd import S3FD
+    from warpedganspace_b200.eval_arcface import IDComparator
+    from warpedganspace_b200.eval_au import FANAU
+    g = gen(5)
+    cases = [(fairface_resnet34(), o_en.init_state('basic', {'fc': 18}, g), torch.zeros(1, 3, 224, 224)),
+             (celeba_attr_resnet50(), o_en.init_celeba_state(g), torch.zeros(1, 3, 224, 224)),
+             (S3FD(), o_en.init_s3fd_state(g), torch.zeros(1, 3, 64, 64)),
+             (IDComparator().backbone, o_en.init_arcface_state(g), torch.zeros(1, 3, 112, 112)),
+             (FANAU(), o_en.init_au_state(g), torch.zeros(1, 3, 256, 256))]
+    for net, sd, x in cases:
+        assert set(net.state_dict()) == set(sd), type(net).__name__
+        net.load_state_dict(sd, strict=True)
+        with pytest.raises(RuntimeError):
+            net(x)
+    hop = hopenet_resnet50()
+    want = set(o_en.init_state('bottleneck', HEADS, g)) | {'fc_finetune.weight', 'fc_finetune.bias'}
+    assert set(hop.state_dict()) == want
+
+
 def _fake_traversal(tmp_path, n_paths=2, n_img=5, size=64):
     from PIL import Image
     exp = tmp_path / 'exp'
