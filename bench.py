@@ -386,13 +386,30 @@ def run_traversal(args, cfg, world, rank, local, device):
     zs = [torch.randn(1, cfg['d'], generator=g) for _ in range(total)]
     paths = list(range(chains))
 
+    copy_stream = torch.cuda.Stream(device=device)
+
     def step(z, host_out=None):
-        sink = []
+        """host_out (pinned uint8 [images, H, W, 3]): every batch of frames is converted on the device and copied out on a second
+        stream as soon as it exists, underneath the rendering of the next batch; the step ends when the last copy has landed."""
+        keep, done = [], 0
+
+        def to_host(lo, hi, img):
+            nonlocal done
+            u8 = images_to_uint8(img, adaptive=True)
+            ready = torch.cuda.Event()
+            ready.record()
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                host_out[done: done + u8.shape[0]].copy_(u8, non_blocking=True)
+            keep.append(u8)
+            done += u8.shape[0]
+
         traverse_paths(G, S, z, paths=paths, eps=EPS, shift_steps=SHIFT_STEPS, batch_size=frames_per, return_images=False,
-                       on_frames=(lambda lo, hi, img: sink.append(images_to_uint8(img, adaptive=True))) if host_out is not None
-                       else (lambda lo, hi, img: None))
+                       on_frames=to_host if host_out is not None else (lambda lo, hi, img: None))
         if host_out is not None:
-            host_out.copy_(torch.cat(sink), non_blocking=True)
+            assert done == host_out.shape[0], (done, host_out.shape)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            return keep
 
     sampler = ClockSampler(local)
     sampler.start()
