@@ -4,7 +4,8 @@ sfd_detector.py:5-43, detect.py:26-62, bbox.py:48-111) on libwgs_b200.
 The network is a VGG-16 style stack of 3x3 convolutions with bias + ReLU, five 2x2 max-pools, three L2-normalised feature
 taps and twelve small detection heads.  Every convolution is one tensor-core launch whose epilogue adds the bias, applies the
 ReLU and - where the next layer is another convolution - writes that layer's split32 operand; max-pool, L2Norm and the
-soft-max / box decoding / NMS of the post-processing are torch library calls on small tensors.  Parameter names are the
+soft-max / box decoding of the post-processing are torch library calls on small tensors, batched over the frames of a path, and
+the NMS is torchvision's CUDA op (on boxes shifted to the reference's pixel-count convention).  Parameter names are the
 reference's (``conv1_1.weight`` ... ``conv7_2_mbox_loc.bias``), so ``s3fd-619a316812.pth`` loads as it is.  CUDA only.
 """
 import numpy as np
@@ -168,6 +169,47 @@ def candidates(olist, j, conf=0.05):
     return torch.cat(rows).cpu().numpy() if rows else np.zeros((0, 5), dtype=np.float32)
 
 
+def candidates_batch(olist, conf=0.05):
+    """`candidates` for every image of the batch at once: per feature level one soft-max / threshold / decode over [B, H, W],
+    one stable sort by image to restore the per-image, level-major order, ONE host synchronisation for the counts.
+    Returns a list of B device tensors [M_j, 5]."""
+    B = olist[0].shape[0]
+    rows, owner = [], []
+    for i in range(len(olist) // 2):
+        ocls = F.softmax(olist[i * 2].float(), dim=1)[:, 1]                        # [B, H, W]
+        oreg = olist[i * 2 + 1].float()                                            # [B, 4, H, W]
+        stride = 2 ** (i + 2)
+        bb, hh, ww = torch.nonzero(ocls > conf, as_tuple=True)
+        if bb.numel() == 0:
+            continue
+        size = torch.full_like(ww, stride * 4, dtype=torch.float32)
+        pri = torch.stack([stride / 2 + ww.float() * stride, stride / 2 + hh.float() * stride, size, size], 1)
+        box = decode(oreg[bb, :, hh, ww].contiguous(), pri)
+        rows.append(torch.cat([box, ocls[bb, hh, ww].unsqueeze(1)], 1))
+        owner.append(bb)
+    if not rows:
+        return [olist[0].new_zeros(0, 5) for _ in range(B)]
+    rows, owner = torch.cat(rows), torch.cat(owner)
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=B).tolist()
+    return list(torch.split(rows[order], counts))
+
+
+def nms_device(dets, thresh):
+    """bbox.py:48-66 on a device tensor [M, 5] -> kept indices in decreasing score order.  torchvision's CUDA NMS measures boxes
+    as (x2 - x1) * (y2 - y1); the reference counts pixels, (x2 - x1 + 1) * (y2 - y1 + 1), in areas and intersections alike, which
+    is the same thing on boxes whose far corner is moved out by one.  Falls back to the host loop above when torchvision's
+    compiled ops are missing (the reference's own NMS is a host loop)."""
+    try:
+        from torchvision.ops import nms as tv_nms
+        boxes = dets[:, :4].clone()
+        boxes[:, 2:] += 1.0
+        return tv_nms(boxes, dets[:, 4].contiguous(), thresh)
+    except (ImportError, RuntimeError, NotImplementedError):
+        keep = nms(dets.cpu().numpy(), thresh)
+        return torch.as_tensor(np.asarray(keep, dtype=np.int64), device=dets.device)
+
+
 class SFDDetector:
     """sfd_detector.SFDDetector: detect_from_batch(tensor [B, 3, H, W], RGB 0..255 - the traversal script feeds it without
     the BGR mean subtraction of the single-image path, sfd_detector.py:23-24) -> (per-image lists of [x1, y1, x2, y2, score]
@@ -183,11 +225,10 @@ class SFDDetector:
     def detect_from_batch(self, tensor):
         olist = self.face_detector(tensor)
         out, error, error_index = [], False, -1
-        for j in range(tensor.shape[0]):
-            cand = candidates(olist, j)
-            keep = nms(cand, 0.3)
-            if len(keep) > 0:
-                out.append([x for x in cand[keep, :] if x[-1] > 0.5])
+        for j, cand in enumerate(candidates_batch(olist)):
+            if cand.shape[0] > 0:
+                kept = cand[nms_device(cand, 0.3)]
+                out.append(list(kept[kept[:, 4] > 0.5].cpu().numpy()))
             else:
                 error, error_index = True, j
                 out.append([])
