@@ -68,7 +68,17 @@ def load_path_images(path_dir, device):
     files = sorted(glob.glob(osp.join(path_dir, '*.jpg')))
     if not files:
         raise FileNotFoundError('no frames under %s' % path_dir)
-    frames = [torch.from_numpy(np.asarray(Image.open(f).convert('RGB'), dtype=np.uint8).copy()) for f in files]
+
+    def decode(f):                      # PIL's decoder (the reference's pixels exactly); it releases the GIL while decoding
+        with Image.open(f) as im:
+            return torch.from_numpy(np.asarray(im.convert('RGB'), dtype=np.uint8).copy())
+
+    if len(files) > 2:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(files), os.cpu_count() or 1, 16)) as pool:
+            frames = list(pool.map(decode, files))
+    else:
+        frames = [decode(f) for f in files]
     return torch.stack(frames).to(device).permute(0, 3, 1, 2).float()
 
 
